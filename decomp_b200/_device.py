@@ -1,0 +1,120 @@
+"""Device-buffer plumbing: torch owns the memory, nothing here computes.
+
+Arrays handed to the kernels are float64 (complex128 viewed as interleaved doubles) with an
+even row pitch, which is what the TMA tensor maps of the GEMM need (16-byte row alignment).
+float32 / complex64 inputs are widened on entry and narrowed on exit: the hot path computes
+in FP64 throughout.
+"""
+import numpy as np
+import torch
+
+from ._lib import DecompError
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise DecompError('decomp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def is_torch(a):
+    return isinstance(a, torch.Tensor)
+
+
+def np_dtype(a):
+    """numpy dtype of a numpy array or torch tensor."""
+    if is_torch(a):
+        return np.dtype(str(a.dtype).replace('torch.', ''))
+    return a.dtype
+
+
+def empty2d(rows, cols, cplx=False, device=None):
+    """Uninitialised [rows, cols] buffer with an even pitch (in doubles)."""
+    device = device or require_cuda()
+    if cplx:
+        return torch.empty((rows, cols), dtype=torch.complex128, device=device)
+    pitch = cols + (cols & 1)
+    base = torch.empty((max(rows, 1), max(pitch, 2)), dtype=torch.float64, device=device)
+    return base[:rows, :cols]
+
+
+def zeros2d(rows, cols, cplx=False, device=None):
+    t = empty2d(rows, cols, cplx, device)
+    t.zero_()
+    return t
+
+
+def full2d(rows, cols, value, cplx=False, device=None):
+    t = empty2d(rows, cols, cplx, device)
+    t.fill_(value)
+    return t
+
+
+def to_device2d(a, device=None, copy=True):
+    """numpy array / torch tensor [rows, cols] -> FP64 (or complex128) device buffer, even pitch.
+
+    With copy=False a suitably laid out CUDA tensor is used in place (read-only inputs)."""
+    device = device or require_cuda()
+    if is_torch(a):
+        src = a
+    else:
+        src = torch.from_numpy(np.ascontiguousarray(a)) if not a.flags.writeable else torch.from_numpy(a)
+    cplx = src.is_complex()
+    want = torch.complex128 if cplx else torch.float64
+    if (not copy and src.is_cuda and src.dtype == want and src.dim() == 2 and src.stride(1) == 1
+            and (cplx or src.stride(0) % 2 == 0) and src.data_ptr() % 16 == 0):
+        return src
+    out = empty2d(src.shape[0], src.shape[1], cplx, device)
+    out.copy_(src, non_blocking=True)
+    return out
+
+
+def to_device1d(a, device=None):
+    device = device or require_cuda()
+    src = a if is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
+    return src.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
+
+
+def to_host(t, like, dtype):
+    """Device result -> same array kind and dtype as the user's input `like`."""
+    tdt = getattr(torch, np.dtype(dtype).name)
+    if is_torch(like):
+        return t.to(dtype=tdt).contiguous()
+    return t.to(dtype=tdt).contiguous().cpu().numpy()
+
+
+def array_kind(*arrays):
+    """'numpy' or 'torch' for the non-None arguments; TypeError when they are mixed.
+
+    Mirrors the reference's ``get_array_module`` contract (decomp/utils/cp_compat.py:9-15): all
+    arrays of one call live in the same array library."""
+    kinds = set()
+    for a in arrays:
+        if a is None:
+            continue
+        if is_torch(a):
+            kinds.add('torch')
+        elif isinstance(a, np.ndarray):
+            kinds.add('numpy')
+        else:
+            raise TypeError('expected numpy arrays or torch tensors, given ' + type(a).__name__)
+    if len(kinds) > 1:
+        raise TypeError('All the data types should be the same.')
+    return kinds.pop() if kinds else 'numpy'
+
+
+def flatten_rows(a):
+    """[..., c] -> [prod(...), c] view (numpy or torch)."""
+    lead = 1
+    for d in a.shape[:-1]:
+        lead *= int(d)
+    return a.reshape(lead, a.shape[-1])
+
+
+def is_complex(a):
+    return np_dtype(a).kind == 'c'
+
+
+def real_dtype(dtype):
+    """complex -> matching real dtype (decomp/utils/dtype.py:5-14)."""
+    return np.zeros(1, dtype).real.dtype

@@ -1,0 +1,313 @@
+// Dictionary (basis) update kernels: the sequential Gauss-Seidel atom sweep as ONE cooperative launch
+// (k grid-wide barriers instead of k host round trips), and the masked Jacobi update, which streams the
+// [k, f, k] statistics tensor once from HBM.  Reference: decomp/dictionary_learning.py:154-159, 206-222.
+#include <cooperative_groups.h>
+
+#include "common.h"
+
+namespace cg = cooperative_groups;
+
+namespace dcp {
+
+constexpr double kEpsDl = 1.0e-15;
+
+__device__ __forceinline__ double warp_sum_dl(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// (a + bi) / (c + di)
+__device__ __forceinline__ double2 cdiv(double a, double b, double c, double d) {
+  const double den = c * c + d * d;
+  return make_double2((a * c + b * d) / den, (b * c - a * d) / den);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gauss-Seidel sweep.  Block = 32 column lanes x 8 row groups; a block owns column groups
+// cgp = blockIdx.x, blockIdx.x + gridDim.x, ...  For atom a:
+//   u_j = (T[a][j] - sum_b S[a][b] D[b][j]) / (S[a][a] + eps) + D[a][j]      (D rows < a already updated)
+//   D[a][j] = u_j / sqrt(max(sum_j |u_j|^2, 1))
+// The only grid-wide dependency is the norm, exchanged through a double-buffered array of block partials.
+// ------------------------------------------------------------------------------------------------
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_sweep_kernel(const double* __restrict__ S, long long lds,
+                                                       const double* __restrict__ T, long long ldt, double* D,
+                                                       long long ldd, int k, int f, double* partials) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red_r[8][33];
+  __shared__ double red_i[8][33];
+  __shared__ double blk[8];
+  __shared__ double bcast;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int groups = (f + 31) / 32;
+  constexpr int CW = CPLX ? 2 : 1;
+
+  for (int a = 0; a < k; ++a) {
+    double local = 0.0;
+    const double* Sa = S + (long long)a * lds;
+    for (int cgp = blockIdx.x; cgp < groups; cgp += gridDim.x) {
+      const int j = cgp * 32 + tx;
+      double sr = 0.0, si = 0.0;
+      if (j < f) {
+        for (int b = ty; b < k; b += 8) {
+          if (CPLX) {
+            const double2 s = *reinterpret_cast<const double2*>(Sa + 2 * b);
+            const double2 d = *reinterpret_cast<const double2*>(D + (long long)b * ldd + 2 * j);
+            sr += s.x * d.x - s.y * d.y;
+            si += s.x * d.y + s.y * d.x;
+          } else {
+            sr += Sa[b] * D[(long long)b * ldd + j];
+          }
+        }
+      }
+      red_r[ty][tx] = sr;
+      if (CPLX) red_i[ty][tx] = si;
+      __syncthreads();
+      if (ty == 0 && j < f) {
+        double dr = 0.0, di = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          dr += red_r[t][tx];
+          if (CPLX) di += red_i[t][tx];
+        }
+        double* dj = D + (long long)a * ldd + CW * j;
+        if (CPLX) {
+          const double2 t2 = *reinterpret_cast<const double2*>(T + (long long)a * ldt + 2 * j);
+          const double2 saa = *reinterpret_cast<const double2*>(Sa + 2 * a);
+          const double2 qv = cdiv(t2.x - dr, t2.y - di, saa.x + kEpsDl, saa.y);
+          const double ur = qv.x + dj[0], ui = qv.y + dj[1];
+          dj[0] = ur;
+          dj[1] = ui;
+          local += ur * ur + ui * ui;
+        } else {
+          const double u = (T[(long long)a * ldt + j] - dr) / (Sa[a] + kEpsDl) + dj[0];
+          dj[0] = u;
+          local += u * u;
+        }
+      }
+      __syncthreads();
+    }
+    // block partial of |u|^2 (only ty == 0 lanes contribute)
+    local = warp_sum_dl(local);
+    if (tx == 0) blk[ty] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) partials[(a & 1) * gridDim.x + blockIdx.x] = blk[0];
+    __threadfence();
+    grid.sync();
+    if (ty == 0) {
+      double tot = 0.0;
+      for (int b = tx; b < (int)gridDim.x; b += 32) tot += partials[(a & 1) * gridDim.x + b];
+      tot = warp_sum_dl(tot);
+      if (tx == 0) bcast = sqrt(fmax(tot, 1.0));
+    }
+    __syncthreads();
+    const double nrm = bcast;
+    if (ty == 0) {
+      for (int cgp = blockIdx.x; cgp < groups; cgp += gridDim.x) {
+        const int j = cgp * 32 + tx;
+        if (j < f) {
+          double* dj = D + (long long)a * ldd + CW * j;
+          dj[0] = dj[0] / nrm;
+          if (CPLX) dj[1] = dj[1] / nrm;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// W[i][b] = conj(x_ia) x_ib
+template <bool CPLX>
+__global__ void atom_weighted_kernel(const double* __restrict__ X, long long ldx, long long rows, int k, int atom,
+                                     double* __restrict__ W, long long ldw) {
+  const long long total = rows * k;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / k;
+    const int b = (int)(idx % k);
+    if (CPLX) {
+      const double2 xa = *reinterpret_cast<const double2*>(X + i * ldx + 2 * atom);
+      const double2 xb = *reinterpret_cast<const double2*>(X + i * ldx + 2 * b);
+      *reinterpret_cast<double2*>(W + i * ldw + 2 * b) =
+          make_double2(xa.x * xb.x + xa.y * xb.y, xa.x * xb.y - xa.y * xb.x);
+    } else {
+      W[i * ldw + b] = X[i * ldx + atom] * X[i * ldx + b];
+    }
+  }
+}
+
+// Dt[j][b] = D[b][j]  (elements are complex pairs when CPLX)
+template <bool CPLX>
+__global__ void transpose_elems_kernel(const double* __restrict__ D, long long ldd, int k, int f,
+                                       double* __restrict__ Dt) {
+  const long long total = (long long)k * f;
+  constexpr int CW = CPLX ? 2 : 1;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long j = idx / k;
+    const int b = (int)(idx % k);
+    Dt[(j * k + b) * CW] = D[(long long)b * ldd + CW * j];
+    if (CPLX) Dt[(j * k + b) * CW + 1] = D[(long long)b * ldd + CW * j + 1];
+  }
+}
+
+// Masked Jacobi update: one CTA per atom a, one warp per column j, lanes over b.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_masked_update_kernel(const double* __restrict__ S,
+                                                               const double* __restrict__ T, long long ldt,
+                                                               const double* __restrict__ D, long long ldd,
+                                                               const double* __restrict__ Dt, int k, int f,
+                                                               double* __restrict__ Dout, long long ldo) {
+  constexpr int CW = CPLX ? 2 : 1;
+  __shared__ double red[2][8];
+  __shared__ double bc[2];
+  const int a = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double* Sa = S + (long long)a * f * k * CW;
+  double saa_r = 0.0, saa_i = 0.0;
+  for (int j = w; j < f; j += 8) {
+    const double* srow = Sa + (long long)j * k * CW;
+    const double* drow = Dt + (long long)j * k * CW;
+    double pr = 0.0, pi = 0.0;
+    for (int b = lane; b < k; b += 32) {
+      if (CPLX) {
+        const double2 s = *reinterpret_cast<const double2*>(srow + 2 * b);
+        const double2 d = *reinterpret_cast<const double2*>(drow + 2 * b);
+        pr += s.x * d.x - s.y * d.y;
+        pi += s.x * d.y + s.y * d.x;
+      } else {
+        pr += srow[b] * drow[b];
+      }
+    }
+    pr = warp_sum_dl(pr);
+    if (CPLX) pi = warp_sum_dl(pi);
+    if (lane == 0) {
+      // numerator T[a][j] - SaD[j], parked in the output row until Saa is known
+      Dout[(long long)a * ldo + CW * j] = T[(long long)a * ldt + CW * j] - pr;
+      if (CPLX) Dout[(long long)a * ldo + 2 * j + 1] = T[(long long)a * ldt + 2 * j + 1] - pi;
+      saa_r += srow[CW * a] + kEpsDl;
+      if (CPLX) saa_i += srow[2 * a + 1];
+    }
+  }
+  if (lane == 0) {
+    red[0][w] = saa_r;
+    red[1][w] = saa_i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0, i = 0.0;
+    for (int t = 0; t < 8; ++t) {
+      r += red[0][t];
+      i += red[1][t];
+    }
+    bc[0] = r;
+    bc[1] = i;
+  }
+  __syncthreads();
+  const double sr = bc[0], si = bc[1];
+  double local = 0.0;
+  for (int j = threadIdx.x; j < f; j += blockDim.x) {
+    double* o = Dout + (long long)a * ldo + CW * j;
+    const double* d = D + (long long)a * ldd + CW * j;
+    if (CPLX) {
+      const double2 qv = cdiv(o[0], o[1], sr, si);
+      const double ur = qv.x + d[0], ui = qv.y + d[1];
+      o[0] = ur;
+      o[1] = ui;
+      local += ur * ur + ui * ui;
+    } else {
+      const double u = o[0] / sr + d[0];
+      o[0] = u;
+      local += u * u;
+    }
+  }
+  local = warp_sum_dl(local);
+  __syncthreads();
+  if (lane == 0) red[0][w] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int t = 0; t < 8; ++t) r += red[0][t];
+    bc[0] = sqrt(fmax(r, 1.0));
+  }
+  __syncthreads();
+  const double nrm = bc[0];
+  for (int j = threadIdx.x; j < f; j += blockDim.x) {
+    double* o = Dout + (long long)a * ldo + CW * j;
+    o[0] = o[0] / nrm;
+    if (CPLX) o[1] = o[1] / nrm;
+  }
+}
+
+}  // namespace dcp
+
+using namespace dcp;
+
+extern "C" {
+
+int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t ldt, double* D, int64_t ldd, int64_t k,
+                        int64_t f, int32_t is_complex, void* stream) {
+  if (k <= 0 || f <= 0) return DECOMP_OK;
+  cudaStream_t st = as_stream(stream);
+  void* kern = is_complex ? (void*)dl_sweep_kernel<true> : (void*)dl_sweep_kernel<false>;
+  int per_sm = 0;
+  int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0), "dl_sweep occupancy");
+  if (rc != DECOMP_OK) return rc;
+  if (per_sm < 1) per_sm = 1;
+  int groups = (int)((f + 31) / 32);
+  int blocks = groups;
+  const int cap = per_sm * num_sms();
+  if (blocks > cap) blocks = cap;
+  double* partials = nullptr;
+  rc = check_cuda(cudaMallocAsync(&partials, sizeof(double) * 2 * blocks, st), "dl_sweep scratch");
+  if (rc != DECOMP_OK) return rc;
+  long long lds_ = lds, ldt_ = ldt, ldd_ = ldd;
+  int k_ = (int)k, f_ = (int)f;
+  void* args[] = {(void*)&S, (void*)&lds_, (void*)&T, (void*)&ldt_, (void*)&D, (void*)&ldd_, (void*)&k_, (void*)&f_,
+                  (void*)&partials};
+  cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st);
+  cudaFreeAsync(partials, st);
+  return check_cuda(e, "dl_sweep launch");
+}
+
+int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int64_t k, int32_t is_complex, int64_t atom,
+                                double* W, int64_t ldw, void* stream) {
+  if (rows <= 0 || k <= 0) return DECOMP_OK;
+  long long total = rows * k;
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (is_complex)
+    atom_weighted_kernel<true><<<(unsigned)b, 256, 0, as_stream(stream)>>>(X, ldx, rows, (int)k, (int)atom, W, ldw);
+  else
+    atom_weighted_kernel<false><<<(unsigned)b, 256, 0, as_stream(stream)>>>(X, ldx, rows, (int)k, (int)atom, W, ldw);
+  DCP_CHECK_LAUNCH("dl_atom_weighted");
+  return DECOMP_OK;
+}
+
+int decomp_dl_masked_update_f64(const double* S, const double* T, int64_t ldt, const double* D, int64_t ldd, int64_t k,
+                                int64_t f, int32_t is_complex, double* D_out, int64_t ldo, double* workspace,
+                                void* stream) {
+  if (k <= 0 || f <= 0) return DECOMP_OK;
+  if (workspace == nullptr) {
+    set_error("decomp_dl_masked_update_f64: workspace (f*k*cw doubles) required");
+    return DECOMP_ERR_INVALID;
+  }
+  cudaStream_t st = as_stream(stream);
+  long long total = k * f;
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (is_complex) {
+    transpose_elems_kernel<true><<<(unsigned)b, 256, 0, st>>>(D, ldd, (int)k, (int)f, workspace);
+    dl_masked_update_kernel<true><<<(unsigned)k, 256, 0, st>>>(S, T, ldt, D, ldd, workspace, (int)k, (int)f, D_out, ldo);
+  } else {
+    transpose_elems_kernel<false><<<(unsigned)b, 256, 0, st>>>(D, ldd, (int)k, (int)f, workspace);
+    dl_masked_update_kernel<false><<<(unsigned)k, 256, 0, st>>>(S, T, ldt, D, ldd, workspace, (int)k, (int)f, D_out, ldo);
+  }
+  DCP_CHECK_LAUNCH("dl_masked_update");
+  return DECOMP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+// C-ABI entry points of the FP64 GEMM family (see include/decomp_b200.h).
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "gemm.cuh"
+
+namespace dcp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return DECOMP_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return DECOMP_ERR_CUDA;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                    uint32_t box_inner, uint32_t box_outer) {
+  auto enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DECOMP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld & 1u) != 0) {
+    set_error("GEMM operand must be 16-byte aligned with an even leading dimension (ptr=%p ld=%llu)", (const void*)base,
+              (unsigned long long)ld);
+    return DECOMP_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return DECOMP_ERR_CUDA;
+  }
+  return DECOMP_OK;
+}
+
+// CTA tile 128x64, four consumer warps of 64x32, 4-stage ring (96 KB) -> two CTAs per SM so that one CTA's
+// epilogue overlaps the other's mainloop.
+using CfgMain = GemmCfg<128, 64, 64, 32, 4, 2>;
+
+template <class C, bool TN, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& gs, const decomp_epilogue_t& ep,
+                  double* partial, const int32_t* skip_if, cudaStream_t stream) {
+  auto kern = gemm_f64_kernel<C, TN, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm smem)");
+    configured = true;
+  }
+  const long long ctas = (long long)gs.tiles_m * gs.tiles_n * gs.splits;
+  if (ctas <= 0) return DECOMP_OK;
+  if (ctas > 2147483647LL) {
+    set_error("GEMM grid too large");
+    return DECOMP_ERR_INVALID;
+  }
+  kern<<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, gs, ep, partial, skip_if);
+  return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
+  using C = CfgMain;
+  gs->M = M;
+  gs->N = N;
+  gs->K = K;
+  gs->tiles_m = (int)((M + C::BM - 1) / C::BM);
+  gs->tiles_n = (int)((N + C::BN - 1) / C::BN);
+  gs->kblocks_total = (int)((K + BK - 1) / BK);
+  const long long tiles = (long long)gs->tiles_m * gs->tiles_n;
+  const long long target = (long long)num_sms() * C::MINB * 4;  // ~4 waves
+  long long splits = tiles > 0 ? (target + tiles - 1) / tiles : 1;
+  const long long max_splits = gs->kblocks_total / 8 > 0 ? gs->kblocks_total / 8 : 1;  // >= 128 rows per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  gs->kblocks_per_split = (int)((gs->kblocks_total + splits - 1) / splits);
+  if (gs->kblocks_per_split < 1) gs->kblocks_per_split = 1;
+  gs->splits = (gs->kblocks_total + gs->kblocks_per_split - 1) / gs->kblocks_per_split;
+  if (gs->splits < 1) gs->splits = 1;
+  gs->ld_partial = (N + 1) & ~1LL;
+}
+
+}  // namespace dcp
+
+using namespace dcp;
+
+extern "C" {
+
+const char* decomp_last_error(void) { return g_err; }
+int decomp_abi_version(void) { return DECOMP_ABI_VERSION; }
+
+int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                       const decomp_epilogue_t* epi, const int32_t* skip_if, void* stream) {
+  using C = CfgMain;
+  if (epi == nullptr || M < 0 || N < 0 || K < 0) {
+    set_error("decomp_gemm_nt_f64: invalid argument");
+    return DECOMP_ERR_INVALID;
+  }
+  if (M == 0 || N == 0) return DECOMP_OK;
+  if (K == 0) {
+    set_error("decomp_gemm_nt_f64: K must be positive");
+    return DECOMP_ERR_INVALID;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tensor_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, C::BM);
+  if (rc != DECOMP_OK) return rc;
+  rc = make_tensor_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, C::BN);
+  if (rc != DECOMP_OK) return rc;
+  GemmGeom gs;
+  gs.M = M;
+  gs.N = N;
+  gs.K = K;
+  gs.tiles_m = (int)((M + C::BM - 1) / C::BM);
+  gs.tiles_n = (int)((N + C::BN - 1) / C::BN);
+  gs.splits = 1;
+  gs.kblocks_total = (int)((K + BK - 1) / BK);
+  gs.kblocks_per_split = gs.kblocks_total;
+  gs.ld_partial = 0;
+  cudaStream_t st = as_stream(stream);
+  switch (epi->kind) {
+    case DECOMP_EPI_STORE:
+      return launch<C, false, DECOMP_EPI_STORE>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_STORE_MASK:
+      return launch<C, false, DECOMP_EPI_STORE_MASK>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_MU_NUM:
+      return launch<C, false, DECOMP_EPI_MU_NUM>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_MU_DEN:
+      return launch<C, false, DECOMP_EPI_MU_DEN>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_PROX:
+      if (epi->check && (epi->latch == nullptr || epi->scratch == nullptr)) {
+        set_error("PROX epilogue with check needs latch and scratch");
+        return DECOMP_ERR_INVALID;
+      }
+      return launch<C, false, DECOMP_EPI_PROX>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_KL_RATIO:
+      return launch<C, false, DECOMP_EPI_KL_RATIO>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    default:
+      set_error("decomp_gemm_nt_f64: unknown epilogue kind %d", epi->kind);
+      return DECOMP_ERR_INVALID;
+  }
+}
+
+size_t decomp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  GemmGeom gs;
+  tn_plan(M, N, K, &gs);
+  return (size_t)gs.splits * (size_t)M * (size_t)gs.ld_partial * sizeof(double);
+}
+
+int decomp_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                       double* out, int64_t ldo, int32_t combine, double beta, void* workspace,
+                       size_t workspace_bytes, const int32_t* skip_if, void* stream) {
+  using C = CfgMain;
+  if (M < 0 || N < 0 || K <= 0 || combine < 0 || combine > 3) {
+    set_error("decomp_gemm_tn_f64: invalid argument");
+    return DECOMP_ERR_INVALID;
+  }
+  if (M == 0 || N == 0) return DECOMP_OK;
+  if (combine >= 2 && ((M & 1) || (N & 1))) {
+    set_error("decomp_gemm_tn_f64: complex combine needs even M and N");
+    return DECOMP_ERR_INVALID;
+  }
+  GemmGeom gs;
+  tn_plan(M, N, K, &gs);
+  const size_t need = (size_t)gs.splits * (size_t)M * (size_t)gs.ld_partial * sizeof(double);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("decomp_gemm_tn_f64: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DECOMP_ERR_INVALID;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tensor_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, BK);
+  if (rc != DECOMP_OK) return rc;
+  rc = make_tensor_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 16, BK);
+  if (rc != DECOMP_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  decomp_epilogue_t ep;
+  memset(&ep, 0, sizeof(ep));
+  double* partial = reinterpret_cast<double*>(workspace);
+  rc = launch<C, true, EPI_PARTIAL>(ta, tb, gs, ep, partial, skip_if, st);
+  if (rc != DECOMP_OK) return rc;
+  const long long total = (combine >= 2) ? (M / 2) * (N / 2) : M * N;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (combine) {
+    case 0:
+      reduce_partials_kernel<0><<<blocks, 256, 0, st>>>(partial, gs.splits, M, N, gs.ld_partial, out, ldo, beta, skip_if);
+      break;
+    case 1:
+      reduce_partials_kernel<1><<<blocks, 256, 0, st>>>(partial, gs.splits, M, N, gs.ld_partial, out, ldo, beta, skip_if);
+      break;
+    case 2:
+      reduce_partials_kernel<2><<<blocks, 256, 0, st>>>(partial, gs.splits, M, N, gs.ld_partial, out, ldo, beta, skip_if);
+      break;
+    default:
+      reduce_partials_kernel<3><<<blocks, 256, 0, st>>>(partial, gs.splits, M, N, gs.ld_partial, out, ldo, beta, skip_if);
+      break;
+  }
+  return check_cuda(cudaGetLastError(), "reduce_partials launch");
+}
+
+}  // extern "C"

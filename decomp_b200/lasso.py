@@ -1,0 +1,246 @@
+"""Batched Lasso by ISTA / FISTA / accelerated ISTA on the B200.
+
+Drop-in for the reference's ``decomp.lasso`` (``solve`` :19-94, ``solve_fastpath`` :97-189):
+same signatures, defaults, validation errors and return tuple ``(it, x)``.
+
+    argmin_x  1/(2n) |y - x A|^2 + alpha |x|      y [..., f],  x [..., k],  A [k, f]
+
+Device data flow (all FP64; complex data as interleaved doubles through the 2x2 real embedding):
+
+    prologue   s_k = |A_k|, A <- A/s, alpha_k, tol_k, x <- x*s               lasso.py:120-138,163
+               G = A A^H (mask: (A * mean(mask)) A^H), 1/L by Gershgorin       lasso.py:285-287,317-319
+               yAh = y A^H (mask: (y*mask) A^H)                                lasso.py:289,321
+    iteration  x_new = shrink(w + (yAh - w G)/L, alpha/L)  [+ momentum, + convergence latch]
+               one NT GEMM launch whose epilogue does the whole update         lasso.py:244-256,405-414
+               (mask: w A -> *mask fused in the first GEMM's epilogue, then the same fused launch)
+    epilogue   x / s                                                           lasso.py:189
+
+The convergence test (every 10th iteration, global over the batch, lasso.py:293/409) is evaluated inside
+the update launch; when it passes, a device latch is set and every later launch returns immediately, so
+the host never has to synchronise inside the loop to get the reference's result.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from ._device import (array_kind, empty2d, flatten_rows, is_torch, np_dtype, require_cuda, to_device1d,
+                      to_device2d, to_host)
+from ._lib import rview
+from .utils import assertion
+
+AVAILABLE_METHODS = ['ista', 'cd', 'acc_ista', 'fista', 'parallel_cd', 'admm']
+AVAILABLE_NNLS_METHODS = ['ista_pos', 'cd_pos', 'acc_ista_pos', 'fista_pos', 'parallel_cd_pos', 'admm_pos']
+DEVICE_RULES = ('ista', 'fista', 'acc_ista')
+POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
+
+
+def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=None, **kwargs):
+    """Solve the batched Lasso problem; see the module docstring. Returns ``(it, x)``.
+
+    Arguments are numpy arrays (result: numpy) or CUDA torch tensors (result: torch, no host copy).
+    ``method``: 'ista' | 'fista' | 'acc_ista', optionally suffixed '_pos' for non-negative x.
+    The reference's sequential / inverse-based methods ('cd', 'parallel_cd', 'admm') are outside the
+    hot path and raise ``NotImplementedError``.
+    """
+    array_kind(y, A, x, mask)
+    if x is None:
+        if is_torch(y):
+            x = torch.zeros(tuple(y.shape[:-1]) + (A.shape[0],), dtype=y.dtype, device=y.device)
+        else:
+            x = np.zeros(y.shape[:-1] + (A.shape[0],), dtype=y.dtype)
+
+    assertion.assert_dtypes(y=y, A=A, x=x)
+    assertion.assert_dtypes(mask=mask, dtypes='f')
+    assertion.assert_nonnegative(mask)
+    assertion.assert_ndim('A', A, ndim=2)
+    assertion.assert_shapes('x', x, 'A', A, axes=1)
+    assertion.assert_shapes('y', y, 'x', x, axes=list(range(x.ndim - 1)))
+    assertion.assert_shapes('y', y, 'A', A, axes=[-1])
+    if mask is not None and mask.ndim == 1:
+        assertion.assert_shapes('y', y, 'mask', mask, axes=[-1])
+    else:
+        assertion.assert_shapes('y', y, 'mask', mask)
+    if method not in AVAILABLE_METHODS + AVAILABLE_NNLS_METHODS:
+        raise ValueError('Available methods are {0:s}. Given {1:s}'.format(str(AVAILABLE_METHODS), method))
+    assert np_dtype(A).kind != 'c' or method[-4:] != '_pos'
+    return solve_fastpath(y, A, alpha, x, tol, maxiter, method, None, mask=mask, **kwargs)
+
+
+def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, group=None, **kwargs):
+    """Assertion-free entry (reference: decomp/lasso.py:97-189). ``xp`` is accepted and ignored.
+
+    ``group``: optional ``torch.distributed`` process group; the batch rows given to this rank are its
+    shard, ``A`` is replicated, and only the convergence decision is exchanged (one int32 every 10th
+    iteration), so that every rank stops at the same iteration as the single-device run would.
+    """
+    positive = method[-4:] == '_pos'
+    rule = method[:-4] if positive else method
+    if rule not in DEVICE_RULES:
+        if rule in AVAILABLE_METHODS:
+            raise NotImplementedError('Method ' + method + ' is not on the B200 hot path '
+                                      '(ista, fista, acc_ista and their _pos variants are).')
+        raise NotImplementedError('Method ' + method + ' is not yet implemented.')
+    if kwargs:
+        raise TypeError('unexpected keyword arguments ' + str(sorted(kwargs)))
+    if np.ndim(alpha) != 0:
+        raise NotImplementedError('alpha must be a scalar')
+
+    device = require_cuda()
+    out_dtype = np_dtype(y)
+    batch_shape = tuple(y.shape[:-1])
+    k = A.shape[0]
+    y2 = to_device2d(flatten_rows(y), device, copy=False)
+    x2 = to_device2d(flatten_rows(x), device, copy=False)
+    A2 = to_device2d(A, device, copy=False)
+    m2 = None
+    if mask is not None:
+        m2 = to_device1d(mask, device) if mask.ndim == 1 else to_device2d(flatten_rows(mask), device, copy=False)
+
+    state = lasso_device(y2, A2, float(alpha), x2, float(tol), int(maxiter), rule, positive, m2, group=group)
+    it = state.iterations()
+    res = to_host(state.result, y, out_dtype)
+    return it, res.reshape(batch_shape + (k,))
+
+
+class LassoState(object):
+    """Handle on an enqueued device solve: ``result`` [B, k] and the lazily read iteration count."""
+
+    def __init__(self, result, latch, maxiter):
+        self.result = result
+        self.latch = latch
+        self.maxiter = maxiter
+
+    def iterations(self):
+        fired = int(self.latch.item()) if self.latch is not None else 0
+        return fired - 1 if fired > 0 else self.maxiter - 1
+
+
+def _momentum_schedule(rule, maxiter):
+    """Extrapolation weight applied after iteration i (lasso.py:411-412 fista, :355 acc_ista)."""
+    if rule == 'ista':
+        return [0.0] * maxiter
+    if rule == 'acc_ista':
+        return [i / (i + 3) for i in range(maxiter)]
+    out, beta = [], 1.0
+    for _ in range(maxiter):
+        beta_next = 0.5 * (1.0 + math.sqrt(1.0 + 4.0 * beta * beta))
+        out.append((beta - 1.0) / beta_next)
+        beta = beta_next
+    return out
+
+
+def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None):
+    """Enqueue a whole solve on the current stream. All arguments are device tensors ([B, f], [k, f],
+    [B, k]; mask None, [f] or [B, f]). Nothing is synchronised unless the latch has to be polled
+    (``tol > 0`` and more than POLL_EVERY iterations). Returns a ``LassoState``."""
+    dev = y.device
+    cplx = A.is_complex()
+    cw = 2 if cplx else 1
+    B, f = y.shape
+    k = A.shape[0]
+    yr, Ar = rview(y), rview(A)
+    full_mask = mask is not None and mask.dim() == 2
+    shrink = ops.SHRINK_POSITIVE if positive else (ops.SHRINK_COMPLEX if cplx else ops.SHRINK_REAL)
+
+    # ---- prologue (lasso.py:120-138, 163)
+    mult_dev = None
+    if mask is not None and not full_mask:
+        Am, ym = empty2d(k, f, cplx, dev), empty2d(B, f, cplx, dev)
+        ops.scale(Ar, rview(Am), cwidth=cw, colscale=mask)
+        ops.scale(yr, rview(ym), cwidth=cw, colscale=mask)
+        Ar, yr = rview(Am), rview(ym)
+        mult_dev = ops.row_sums(mask.view(1, f))
+    s = ops.row_norms(Ar, cplx)
+    An = empty2d(k, f, cplx, dev)
+    ops.scale(Ar, rview(An), cwidth=cw, rowscale=s, invert_row=True)
+    Anr = rview(An)
+    alpha_vec, tol_vec = ops.lasso_vectors(s, alpha, tol, mult=1.0 if full_mask else float(f), mult_dev=mult_dev)
+    X = empty2d(B, k, cplx, dev)
+    ops.scale(rview(x), rview(X), cwidth=cw, colscale=s)
+
+    # ---- Gram matrix, step 1/L, yAh (lasso.py:276-289, 306-321)
+    AH = ops.make_rhs(Anr, True, True) if cplx else Anr          # NT operand of  . A^H
+    G = empty2d(k, k, cplx, dev)
+    rowvec = None
+    if full_mask:
+        rowvec = ops.row_sums(mask)                               # sum(mask, -1): alpha per problem
+        mean = ops.col_sums(mask, 1.0 / B)
+        if group is not None:
+            mean = _global_mask_mean(mask, B, group)
+        Amean = empty2d(k, f, cplx, dev)
+        ops.scale(Anr, rview(Amean), cwidth=cw, colscale=mean)
+        ops.gemm_nt(rview(Amean), AH, ops.epilogue(ops.EPI_STORE, rview(G)))
+    else:
+        ops.gemm_nt(Anr, AH, ops.epilogue(ops.EPI_STORE, rview(G)))
+    step = torch.empty(1, dtype=torch.float64, device=dev)
+    ops.gershgorin_step(rview(G), cplx, step)
+    yAh = empty2d(B, k, cplx, dev)
+    if full_mask:
+        T = empty2d(B, f, cplx, dev)                              # also the per-iteration [B, f] temporary
+        ops.mask_mul(yr, mask, rview(T), cwidth=cw)
+        ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
+        A_rhs = ops.make_rhs(Anr, cplx, False)                    # NT operand of  w . A
+    else:
+        G_rhs = ops.make_rhs(rview(G), cplx, False)               # NT operand of  w . G
+
+    # ---- iterations
+    checks = tol > 0.0
+    latch = torch.zeros(1, dtype=torch.int32, device=dev) if checks else None
+    scratch = torch.zeros(2, dtype=torch.int32, device=dev) if checks else None
+    W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
+    W[0].copy_(X)
+    Xr, yAhr = rview(X), rview(yAh)
+    mom = _momentum_schedule(rule, maxiter)
+
+    def launch(i, out_x):
+        check = checks and i % 10 == 0
+        epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
+                           other=yAhr, prev=Xr, colvec=alpha_vec, colvec2=tol_vec, rowvec=rowvec, step=step,
+                           momentum=mom[i], shrink=shrink, check=check, latch=latch, scratch=scratch,
+                           latch_value=i + 1)
+        if full_mask:
+            ops.gemm_nt(rview(W[i % 2]), A_rhs,
+                        ops.epilogue(ops.EPI_STORE_MASK, rview(T), cwidth=cw, mask=mask), skip=latch)
+            ops.gemm_nt(rview(T), AH, epi, skip=latch)
+        else:
+            ops.gemm_nt(rview(W[i % 2]), G_rhs, epi, skip=latch)
+        if check and group is not None:
+            # the latch fires only if every shard passed the test (reference: one max over the whole batch)
+            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=group)
+
+    # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
+    # matters if it is a checking one, and then only when the check passes.
+    n_inplace = maxiter - 1 if (rule == 'acc_ista' and maxiter > 0) else maxiter
+    stopped = False
+    for i in range(n_inplace):
+        if checks and i > 0 and i % POLL_EVERY == 0 and int(latch.item()) != 0:
+            stopped = True
+            break
+        launch(i, Xr)
+    final = X
+    if rule == 'acc_ista' and maxiter > 0 and not stopped and checks and (maxiter - 1) % 10 == 0:
+        XL = empty2d(B, k, cplx, dev)
+        launch(maxiter - 1, rview(XL))
+        if int(latch.item()) == maxiter:
+            final = XL
+
+    # ---- x / s (lasso.py:189)
+    if out is None:
+        out = empty2d(B, k, cplx, dev)
+    ops.scale(rview(final), rview(out), cwidth=cw, colscale=s, invert_col=True)
+    return LassoState(out, latch, maxiter)
+
+
+def _global_mask_mean(mask, local_rows, group):
+    """mean over the whole (sharded) batch of the mask, lasso.py:300-303: one [f] all-reduce at set-up."""
+    dist = torch.distributed
+    sums = ops.col_sums(mask, 1.0)
+    rows = torch.tensor([float(local_rows)], dtype=torch.float64, device=mask.device)
+    dist.all_reduce(sums, group=group)
+    dist.all_reduce(rows, group=group)
+    f = sums.numel()
+    mean = torch.empty_like(sums)
+    ops.scale(sums.view(1, f), mean.view(1, f), rowscale=rows, invert_row=True)
+    return mean

@@ -1,0 +1,219 @@
+"""Typed Python wrappers over the C ABI (one function per exported symbol).
+
+Every argument that is a matrix is a 2-D float64 CUDA tensor with unit inner stride and an
+even row pitch ("real view"; complex data is passed as interleaved doubles, see
+``_lib.rview``).  Nothing here computes: each function marshals pointers and calls the
+shared library on torch's current stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_KL_RATIO, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EPI_STORE_MASK,  # noqa: F401
+                   SHRINK_COMPLEX, SHRINK_POSITIVE, SHRINK_REAL, Epilogue, ld, ptr, rview)
+from ._device import empty2d
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def epilogue(kind, out, cwidth=1, **kw):
+    """Build a decomp_epilogue_t. Keyword tensors: out2, x, other, prev, mask, colvec, colvec2, rowvec, step,
+    latch, scratch; scalars: shrink, check, momentum, latch_value."""
+    e = Epilogue()
+    e.kind = kind
+    e.cwidth = cwidth
+    e.shrink = kw.get('shrink', SHRINK_REAL)
+    e.check = 1 if kw.get('check', False) else 0
+    e.out, e.ldo = out.data_ptr(), ld(out)
+    for name, ldname in (('out2', 'ldo2'), ('x', 'ldx'), ('other', 'ldother'), ('prev', 'ldprev'),
+                         ('mask', 'ldmask')):
+        t = kw.get(name)
+        if t is not None:
+            setattr(e, name, t.data_ptr())
+            setattr(e, ldname, ld(t))
+    for name in ('colvec', 'colvec2', 'rowvec', 'step', 'latch', 'scratch'):
+        t = kw.get(name)
+        if t is not None:
+            setattr(e, name, t.data_ptr())
+    e.momentum = float(kw.get('momentum', 0.0))
+    e.latch_value = int(kw.get('latch_value', 0))
+    return e
+
+
+def gemm_nt(A, B, epi, skip=None):
+    """acc = A . B^T  (A [M, K], B [N, K]) followed by the fused epilogue ``epi``."""
+    M, K = A.shape
+    N, K2 = B.shape
+    assert K == K2, 'inner dimensions differ'
+    rc = _lib.lib().decomp_gemm_nt_f64(_p(A), ld(A), _p(B), ld(B), M, N, K, ctypes.byref(epi), _p(skip),
+                                       _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_nt_f64')
+
+
+def gemm_tn_workspace(M, N, K, device):
+    nbytes = _lib.lib().decomp_gemm_tn_workspace_bytes(M, N, K)
+    return torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=device)
+
+
+def gemm_tn_workspace_for(shapes, device):
+    """One workspace large enough for every (M, N, K) in ``shapes``."""
+    nbytes = max(_lib.lib().decomp_gemm_tn_workspace_bytes(M, N, K) for M, N, K in shapes)
+    return torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=device)
+
+
+def gemm_tn(A, B, out, combine=0, beta=0.0, workspace=None, skip=None):
+    """out = [beta*out +] A^T . B  (A [K, M], B [K, N]); combine 2/3: conj(A)^T . B on interleaved complex."""
+    K, M = A.shape
+    K2, N = B.shape
+    assert K == K2, 'row counts differ'
+    if workspace is None:
+        workspace = gemm_tn_workspace(M, N, K, A.device)
+    rc = _lib.lib().decomp_gemm_tn_f64(_p(A), ld(A), _p(B), ld(B), M, N, K, _p(out), ld(out), combine, float(beta),
+                                       _p(workspace), workspace.numel() * 8, _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_tn_f64')
+    return out
+
+
+def make_rhs(S, is_complex, conj_transpose, out=None, skip=None):
+    """NT right-hand operand for X.S (conj_transpose=False) or X.S^H (True); S is the real view of [p, q]."""
+    cw = 2 if is_complex else 1
+    p, q = S.shape[0], S.shape[1] // cw
+    rows, cols = (p * cw, q * cw) if conj_transpose else (q * cw, p * cw)
+    if out is None:
+        out = empty2d(rows, cols, False, S.device)
+    rc = _lib.lib().decomp_make_rhs_f64(_p(S), ld(S), p, q, int(is_complex), int(conj_transpose), _p(out), ld(out),
+                                        _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_make_rhs_f64')
+    return out
+
+
+def row_norms(A, is_complex, out=None):
+    cw = 2 if is_complex else 1
+    rows, cols = A.shape[0], A.shape[1] // cw
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device=A.device)
+    rc = _lib.lib().decomp_row_norms_f64(_p(A), ld(A), rows, cols, int(is_complex), _p(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_row_norms_f64')
+    return out
+
+
+def scale(A, out, cwidth=1, rowscale=None, invert_row=False, colscale=None, invert_col=False):
+    rows, cols = A.shape
+    rc = _lib.lib().decomp_scale_f64(_p(A), ld(A), rows, cols, cwidth, _p(rowscale), int(invert_row), _p(colscale),
+                                     int(invert_col), _p(out), ld(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_scale_f64')
+    return out
+
+
+def mask_mul(A, mask, out, cwidth=1):
+    rows, cols = A.shape
+    rc = _lib.lib().decomp_mask_mul_f64(_p(A), ld(A), _p(mask), ld(mask), rows, cols, cwidth, _p(out), ld(out),
+                                        _lib.stream_ptr())
+    _lib.check(rc, 'decomp_mask_mul_f64')
+    return out
+
+
+def col_sums(A, scale_=1.0, out=None):
+    rows, cols = A.shape
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float64, device=A.device)
+    rc = _lib.lib().decomp_col_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_col_sums_f64')
+    return out
+
+
+def row_sums(A, scale_=1.0, out=None):
+    rows, cols = A.shape
+    if out is None:
+        out = torch.empty(rows, dtype=torch.float64, device=A.device)
+    rc = _lib.lib().decomp_row_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_row_sums_f64')
+    return out
+
+
+def gershgorin_step(G, is_complex, step_out, alpha_scaled=None, thr_out=None):
+    cw = 2 if is_complex else 1
+    k = G.shape[0]
+    assert G.shape[1] == k * cw
+    rc = _lib.lib().decomp_gershgorin_step_f64(_p(G), ld(G), k, int(is_complex), _p(alpha_scaled), _p(step_out),
+                                               _p(thr_out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gershgorin_step_f64')
+    return step_out
+
+
+def normalize_rows(D_in, D_out, is_complex, strict, D_ref=None, tol=0.0, latch=None, latch_value=0, maxdiff=None,
+                   scratch=None, skip=None):
+    cw = 2 if is_complex else 1
+    rows, cols = D_in.shape[0], D_in.shape[1] // cw
+    rc = _lib.lib().decomp_normalize_rows_f64(
+        _p(D_in), ld(D_in), rows, cols, int(is_complex), int(strict), _p(D_out), ld(D_out), _p(D_ref),
+        ld(D_ref) if D_ref is not None else 0, float(tol), _p(latch), int(latch_value), _p(maxdiff), _p(scratch),
+        _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_normalize_rows_f64')
+    return D_out
+
+
+def gather_rows(src, index, out):
+    rows, cols = out.shape
+    rc = _lib.lib().decomp_gather_rows_f64(_p(src), ld(src), _p(index), rows, cols, _p(out), ld(out),
+                                           _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gather_rows_f64')
+    return out
+
+
+def dl_sweep(S, T, D, is_complex):
+    cw = 2 if is_complex else 1
+    k, f = D.shape[0], D.shape[1] // cw
+    rc = _lib.lib().decomp_dl_sweep_f64(_p(S), ld(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex),
+                                        _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_sweep_f64')
+    return D
+
+
+def dl_atom_weighted(X, is_complex, atom, W):
+    cw = 2 if is_complex else 1
+    rows, k = X.shape[0], X.shape[1] // cw
+    rc = _lib.lib().decomp_dl_atom_weighted_f64(_p(X), ld(X), rows, k, int(is_complex), int(atom), _p(W), ld(W),
+                                                _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_atom_weighted_f64')
+    return W
+
+
+def dl_masked_update(S, T, D, D_out, is_complex, workspace):
+    cw = 2 if is_complex else 1
+    k, f = D.shape[0], D.shape[1] // cw
+    rc = _lib.lib().decomp_dl_masked_update_f64(_p(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex), _p(D_out),
+                                                ld(D_out), _p(workspace), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_masked_update_f64')
+    return D_out
+
+
+def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):
+    k = s.numel()
+    alpha_out = torch.empty(k, dtype=torch.float64, device=s.device)
+    tol_out = torch.empty(k, dtype=torch.float64, device=s.device)
+    rc = _lib.lib().decomp_lasso_vectors_f64(_p(s), k, float(alpha), float(tol), float(mult), _p(mult_dev),
+                                             _p(alpha_out), _p(tol_out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_lasso_vectors_f64')
+    return alpha_out, tol_out
+
+
+def mu_update(x, num, den, out, skip=None):
+    rows, cols = x.shape
+    rc = _lib.lib().decomp_mu_update_f64(_p(x), ld(x), _p(num), ld(num), _p(den), ld(den), rows, cols, _p(out), ld(out),
+                                         _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_mu_update_f64')
+    return out
+
+
+def max_abs_diff(A, B, is_complex, result, scratch, tol=0.0, latch=None, latch_value=0, skip=None):
+    cw = 2 if is_complex else 1
+    rows, cols = A.shape[0], A.shape[1] // cw
+    rc = _lib.lib().decomp_max_abs_diff_f64(_p(A), ld(A), _p(B), ld(B), rows, cols, int(is_complex), float(tol),
+                                            _p(latch), int(latch_value), _p(result), _p(scratch), _p(skip),
+                                            _lib.stream_ptr())
+    _lib.check(rc, 'decomp_max_abs_diff_f64')
+    return result

@@ -1,0 +1,179 @@
+/*
+ * decomp_b200 C ABI -- the drop-in boundary of the B200-native deComP hot path.
+ *
+ * Plain C: raw DEVICE pointers, sizes, leading dimensions (in elements of double) and a
+ * cudaStream_t passed as void*.  No torch types, nothing allocated or freed on behalf of
+ * the caller: workspaces are sized by the *_workspace_bytes() queries and supplied by the
+ * caller.  Every function returns 0 on success and a negative code on failure; the text
+ * is available from decomp_last_error().
+ *
+ * The reference (fujii-team/deComP) is pure Python over an `xp` array namespace; what a
+ * maintainer would bind with ctypes are the array expressions inside its update rules.
+ * Each entry point below names the reference lines it replaces (paths relative to the
+ * reference root).  All matrices are row-major.  Complex data is passed as interleaved
+ * (re, im) doubles, i.e. a complex [r, c] matrix is the real [r, 2c] matrix with the same
+ * bytes; the real kernels below then compute complex products exactly through the 2x2
+ * real block embedding prepared by decomp_make_rhs_f64().
+ *
+ * Alignment contract (needed by TMA): base pointers of GEMM operands are 16-byte aligned
+ * and their leading dimensions are even.  The Python host pads to satisfy this.
+ */
+#ifndef DECOMP_B200_H_
+#define DECOMP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DECOMP_OK 0
+#define DECOMP_ERR_INVALID (-1)
+#define DECOMP_ERR_CUDA (-2)
+#define DECOMP_ERR_UNSUPPORTED (-3)
+
+#define DECOMP_ABI_VERSION 1
+
+/* ---- epilogue fused into the NT GEMM ------------------------------------------------ */
+enum decomp_epilogue_kind {
+  DECOMP_EPI_STORE = 0,     /* out = acc                                                     */
+  DECOMP_EPI_STORE_MASK = 1,/* out = acc * mask[row, col / cwidth]      (grads.py:112,122; lasso.py:260) */
+  DECOMP_EPI_MU_NUM = 2,    /* out = x * max(acc,0) / max(other,eps)    (grads.py:84,93: acc is the positive part) */
+  DECOMP_EPI_MU_DEN = 3,    /* out = x * max(other,0) / max(acc,eps)    (acc is the negative part) */
+  DECOMP_EPI_PROX = 4,      /* ISTA/FISTA step, see decomp_epilogue_t   (lasso.py:244-271, 405-414) */
+  DECOMP_EPI_KL_RATIO = 5   /* out = other / (acc + eps) [* mask]       (grads.py:142-160) */
+};
+
+enum decomp_shrink_kind {
+  DECOMP_SHRINK_REAL = 0,    /* lasso.py:192-207 */
+  DECOMP_SHRINK_COMPLEX = 1, /* lasso.py:210-225, column pairs are (re, im) */
+  DECOMP_SHRINK_POSITIVE = 2 /* lasso.py:228-241 */
+};
+
+typedef struct decomp_epilogue {
+  int32_t kind;              /* decomp_epilogue_kind */
+  int32_t shrink;            /* decomp_shrink_kind (PROX only) */
+  int32_t cwidth;            /* 1 real, 2 complex: mask / per-column vectors are indexed by col / cwidth */
+  int32_t check;             /* PROX: 1 -> evaluate the convergence test of lasso.py:293/409 in this launch */
+  double* out;               /* primary output [M, N] */
+  int64_t ldo;
+  double* out2;              /* PROX: extrapolated point w_next (may be NULL for ISTA) */
+  int64_t ldo2;
+  const double* x;           /* MU: factor being updated; PROX: the point the gradient is taken at (w) */
+  int64_t ldx;
+  const double* other;       /* MU: the other gradient part; PROX: yAt; KL: y */
+  int64_t ldother;
+  const double* prev;        /* PROX: previous iterate x_prev */
+  int64_t ldprev;
+  const double* mask;        /* STORE_MASK / KL_RATIO: mask [M, N / cwidth] (may be NULL for KL) */
+  int64_t ldmask;
+  const double* colvec;      /* PROX: threshold per column  step * alpha_k  [N / cwidth] */
+  const double* colvec2;     /* PROX: tolerance per column  tol * s_k        [N / cwidth] */
+  const double* rowvec;      /* PROX (full mask): per-row factor sum_j mask[row, j]; NULL -> 1 */
+  const double* step;        /* PROX: device scalar 1 / L */
+  double momentum;           /* PROX: (beta - 1) / beta_next, or i / (i + 3), or 0 */
+  int32_t* latch;            /* PROX+check: set to `latch_value` by the last CTA if converged */
+  int32_t* scratch;          /* PROX+check: two int32 (violation flag, CTA ticket), zero-initialised */
+  int32_t latch_value;
+  int32_t reserved;
+} decomp_epilogue_t;
+
+const char* decomp_last_error(void);
+int decomp_abi_version(void);
+
+/* acc[m][n] = sum_k A[m*lda + k] * B[n*ldb + k]   (A: [M,K], B: [N,K], both K-contiguous),
+ * followed by the fused epilogue.  TMA-fed, DMMA.8x8x4 mainloop.
+ * Replaces: y.dot(d.T), f.dot(d.T), x.dot(d) (grads.py:108-125), xp.dot(A, At), xp.tensordot(y, At),
+ * xp.tensordot(x0, AAt) (lasso.py:245,285-289) together with the elementwise expressions named above.
+ * If `skip_if` is non-NULL and *skip_if != 0 on the device the launch is a no-op (convergence latch). */
+int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N,
+                       int64_t K, const decomp_epilogue_t* epi, const int32_t* skip_if, void* stream);
+
+/* acc[m][n] = sum_k A[k*lda + m] * B[k*ldb + n]   (A: [K,M], B: [K,N]; contraction over rows = samples),
+ * split along K across CTAs with a deterministic two-stage reduction through `workspace`.
+ *   combine = 0: out = acc             (x.T.dot(y), x.T.dot(f), grads.py:120-125)
+ *   combine = 1: out = beta*out + acc  (A = beta*A + xT.x, B = beta*B + xT.y, dictionary_learning.py:151-152)
+ *   combine = 2/3: as 0/1 but A,B are interleaved complex and out[i][j] = sum_k conj(a_ki) b_kj is written as
+ *                  interleaved complex [M/2, N/2] (ldo in doubles)       (dictionary_learning.py:147-152) */
+size_t decomp_gemm_tn_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int decomp_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N,
+                       int64_t K, double* out, int64_t ldo, int32_t combine, double beta, void* workspace,
+                       size_t workspace_bytes, const int32_t* skip_if, void* stream);
+
+/* Right-hand operand preparation for X . S or X . S^H with a small matrix S [p, q] (complex: interleaved):
+ * writes the [N, K] K-contiguous operand B of decomp_gemm_nt_f64 such that X_real . B^T equals the product.
+ *   conj_transpose = 0: product X . S    -> B is [q*cw, p*cw]
+ *   conj_transpose = 1: product X . S^H  -> B is [p*cw, q*cw]  (for real data B == S, copied) */
+int decomp_make_rhs_f64(const double* S, int64_t lds, int64_t p, int64_t q, int32_t is_complex,
+                        int32_t conj_transpose, double* B, int64_t ldb, const int32_t* skip_if, void* stream);
+
+/* ---- vector / reduction kernels ------------------------------------------------------- */
+/* out[i] = sqrt(sum_j |A[i][j]|^2)                                  (lasso.py:124-127; normalize.py:17-20) */
+int decomp_row_norms_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, int32_t is_complex,
+                         double* out, void* stream);
+/* out[i][j] = A[i][j] * (rowscale ? (invert_row ? 1/rowscale[i] : rowscale[i]) : 1)
+ *                     * (colscale ? (invert_col ? 1/colscale[j/cw] : colscale[j/cw]) : 1)
+ * (A / s[:, None], x * s, x / s, y * mask1d, A * mean(mask): lasso.py:121-131,189,317) */
+int decomp_scale_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, int32_t cwidth,
+                     const double* rowscale, int32_t invert_row, const double* colscale, int32_t invert_col,
+                     double* out, int64_t ldo, void* stream);
+/* out = A * Mask (elementwise, mask indexed by col / cwidth)         (grads.py:113,123; lasso.py:321,433) */
+int decomp_mask_mul_f64(const double* A, int64_t lda, const double* mask, int64_t ldm, int64_t rows, int64_t cols,
+                        int32_t cwidth, double* out, int64_t ldo, void* stream);
+/* out[j] = sum_i A[i][j] * scale   (column sums: mean over the batch of the mask, lasso.py:300-303;
+ * with rows<->cols swapped by the caller it is also the per-row mask count of lasso.py:163) */
+int decomp_col_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
+                        void* stream);
+int decomp_row_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
+                        void* stream);
+/* Lipschitz bound: *step_out = 1 / max_j sum_i |G[i][j]| for a [k,k] (complex: interleaved) matrix
+ * (math_utils/eigen.py:9-20; lasso.py:286), and thr[j] = step * alpha_scaled[j] (lasso.py:287). */
+int decomp_gershgorin_step_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex,
+                               const double* alpha_scaled, double* step_out, double* thr_out, void* stream);
+/* D_out[i] = D_in[i] / ||D_in[i]|| (strict) or / sqrt(max(||.||^2, 1)) (soft); *maxdiff = max |D_ref - D_out|;
+ * if tol_latch != NULL and maxdiff < tol: *tol_latch = latch_value  (normalize.py:2-21; batch_mu.py:21-23) */
+int decomp_normalize_rows_f64(const double* D_in, int64_t ldi, int64_t rows, int64_t cols, int32_t is_complex,
+                              int32_t strict, double* D_out, int64_t ldo, const double* D_ref, int64_t ldr,
+                              double tol, int32_t* tol_latch, int32_t latch_value, double* maxdiff,
+                              int32_t* scratch, const int32_t* skip_if, void* stream);
+/* out[r] = in[index[r]] row gather (MinibatchData.shuffle / .array, utils/data.py:147-156) */
+int decomp_gather_rows_f64(const double* in, int64_t ldi, const int64_t* index, int64_t rows, int64_t cols,
+                           double* out, int64_t ldo, void* stream);
+
+/* Lasso prologue vectors: alpha_out[j] = (alpha / s[j]) * mult, tol_out[j] = tol * s[j]; `mult` is read from the
+ * device scalar mult_dev when that is non-NULL (sum of a 1-D mask)   (lasso.py:129-130, 136-138) */
+int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double tol, double mult, const double* mult_dev,
+                             double* alpha_out, double* tol_out, void* stream);
+/* out = x * max(num, 0) / max(den, eps), elementwise (masked D update, grads.py:93 with :122-125) */
+int decomp_mu_update_f64(const double* x, int64_t ldx, const double* num, int64_t ldn, const double* den, int64_t ldd,
+                         int64_t rows, int64_t cols, double* out, int64_t ldo, const int32_t* skip_if, void* stream);
+/* result[1] = max |A - B| (result[0] is a zero-initialised accumulator); sets *tol_latch = latch_value when the
+ * maximum is < tol   (dictionary_learning.py:161,224) */
+int decomp_max_abs_diff_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t rows, int64_t cols,
+                            int32_t is_complex, double tol, int32_t* tol_latch, int32_t latch_value, double* result,
+                            int32_t* scratch, const int32_t* skip_if, void* stream);
+
+/* ---- dictionary-learning basis update ------------------------------------------------- */
+/* Gauss-Seidel atom sweep, dictionary_learning.py:154-159:
+ *   for a in 0..k-1: u = (T[a] - S[a].D) / (S[a][a] + eps) + D[a];  D[a] = u / sqrt(max(|u|^2, 1))
+ * in place on D (initialised by the caller with the old dictionary). One cooperative launch. */
+int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t ldt, double* D, int64_t ldd,
+                        int64_t k, int64_t f, int32_t is_complex, void* stream);
+/* Masked statistics, dictionary_learning.py:210-213:  S[a][j][b] = beta*S[a][j][b] + sum_i conj(x_ia) x_ib m_ij.
+ * Per atom a this is the TN product  Mask^T . W_a  with  W_a[i][b] = conj(x_ia) x_ib ; this entry point forms W_a
+ * (interleaved complex when is_complex) and the caller feeds it to decomp_gemm_tn_f64(combine=1, beta) with
+ * A = Mask, out = S[a].  Internal layout of S is [k][f][k*cw] doubles (never returned to the user). */
+int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int64_t k, int32_t is_complex,
+                                int64_t atom, double* W, int64_t ldw, void* stream);
+/* Masked Jacobi atom update, dictionary_learning.py:216-222:
+ *   SaD[j] = sum_b S[a][j][b] D[b][j];  Saa = sum_j (S[a][j][a] + eps);  u = (T[a] - SaD)/Saa + D[a];  l2(u)
+ * `workspace` holds the transposed dictionary: f * k * cw doubles. */
+int decomp_dl_masked_update_f64(const double* S, const double* T, int64_t ldt, const double* D, int64_t ldd,
+                                int64_t k, int64_t f, int32_t is_complex, double* D_out, int64_t ldo,
+                                double* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECOMP_B200_H_ */

@@ -1,0 +1,325 @@
+"""Unit parity of every C-ABI kernel against numpy on the same inputs (GPU only)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RT = 1.0e-12
+
+
+def dev(a):
+    from decomp_b200._device import to_device2d
+    return to_device2d(a)
+
+
+def rv(t):
+    from decomp_b200._lib import rview
+    return rview(t)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def close(a, b, rtol=RT):
+    scale = max(np.max(np.abs(b)), 1e-300)
+    err = np.max(np.abs(a - b)) / scale
+    assert err <= rtol, 'rel err %g' % err
+
+
+SHAPES = [(1, 1, 1), (5, 3, 7), (8, 8, 16), (130, 70, 45), (257, 129, 300), (1000, 20, 200), (64, 256, 256)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+def test_gemm_nt_store(M, N, K):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(M + N + K)
+    A, B = rng.randn(M, K), rng.randn(N, K)
+    dA, dB = dev(A), dev(B)
+    out = dev(np.zeros((M, N)))
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_STORE, out))
+    torch.cuda.synchronize()
+    close(host(out), A.dot(B.T))
+
+
+@pytest.mark.parametrize('M,N,K', [(130, 70, 45), (257, 33, 300)])
+def test_gemm_nt_elementwise_epilogues(M, N, K):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(1)
+    A, B = np.abs(rng.randn(M, K)), np.abs(rng.randn(N, K))
+    X, O = np.abs(rng.randn(M, N)), rng.randn(M, N)
+    mask = np.rint(rng.uniform(0.3, 1, size=(M, N)))
+    acc = A.dot(B.T)
+    dA, dB, dX, dO, dM = dev(A), dev(B), dev(X), dev(O), dev(mask)
+    out = dev(np.zeros((M, N)))
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_MU_NUM, out, x=dX, other=dO))
+    close(host(out), X * np.maximum(acc, 0) / np.maximum(O, 1e-15))
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_MU_DEN, out, x=dX, other=dO))
+    close(host(out), X * np.maximum(O, 0) / np.maximum(acc, 1e-15))
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_STORE_MASK, out, mask=dM))
+    close(host(out), acc * mask)
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_KL_RATIO, out, other=dO, mask=dM))
+    close(host(out), (O * mask) / (acc + 1e-15))
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_KL_RATIO, out, other=dO))
+    close(host(out), O / (acc + 1e-15))
+    # in-place MU update (out aliases x), as the NMF driver uses it
+    ops.gemm_nt(dA, dB, ops.epilogue(ops.EPI_MU_NUM, dX, x=dX, other=dO))
+    close(host(dX), X * np.maximum(acc, 0) / np.maximum(O, 1e-15))
+
+
+def test_gemm_nt_complex_mask_epilogue():
+    from decomp_b200 import ops
+    rng = np.random.RandomState(2)
+    Bn, k, f = 77, 6, 19
+    w = rng.randn(Bn, k) + 1j * rng.randn(Bn, k)
+    A = rng.randn(k, f) + 1j * rng.randn(k, f)
+    mask = np.rint(rng.uniform(0.3, 1, size=(Bn, f)))
+    dw, dA, dM = dev(w), dev(A), dev(mask)
+    rhs = ops.make_rhs(rv(dA), True, False)
+    out = dev(np.zeros((Bn, f), dtype=complex))
+    ops.gemm_nt(rv(dw), rhs, ops.epilogue(ops.EPI_STORE_MASK, rv(out), cwidth=2, mask=dM))
+    close(host(out), w.dot(A) * mask)
+    rhs_h = ops.make_rhs(rv(dA), True, True)
+    y = rng.randn(Bn, f) + 1j * rng.randn(Bn, f)
+    out2 = dev(np.zeros((Bn, k), dtype=complex))
+    ops.gemm_nt(rv(dev(y)), rhs_h, ops.epilogue(ops.EPI_STORE, rv(out2)))
+    close(host(out2), y.dot(np.conj(A.T)))
+
+
+def _prox_ref(w, G, yAt, xprev, step, alpha, tol, mom, kind, rowfac=None):
+    z = w + step * (yAt - w.dot(G))
+    thr = step * (alpha * rowfac[:, None]) if rowfac is not None else step * alpha
+    if kind == 'complex':
+        r = np.abs(z)
+        xn = np.maximum(r - thr, 0) * (z / (r + 1e-15))
+    elif kind == 'positive':
+        xn = np.maximum(z - thr, 0)
+    else:
+        xn = np.maximum(np.abs(z) - thr, 0) * np.sign(z)
+    wn = xn + mom * (xn - xprev)
+    viol = not (np.max(np.abs(xn - xprev) - tol) < 0)
+    return xn, wn, viol
+
+
+@pytest.mark.parametrize('kind', ['real', 'positive', 'complex'])
+@pytest.mark.parametrize('rowvec', [False, True])
+def test_gemm_nt_prox(kind, rowvec):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(3)
+    Bn, k = 203, 23
+    cplx = kind == 'complex'
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    A = randn(k, 31)
+    G = A.dot(np.conj(A.T))
+    w, yAt, xprev = randn(Bn, k), randn(Bn, k) * 5, randn(Bn, k)
+    alpha = np.abs(rng.randn(k)) * 0.5
+    tol = np.full(k, 1e-3)
+    rowfac = np.abs(rng.randn(Bn)) + 0.5 if rowvec else None
+    step = 1.0 / np.max(np.sum(np.abs(G), axis=0))
+    xn_ref, wn_ref, viol = _prox_ref(w, G, yAt, xprev, step, alpha, tol, 0.37, kind, rowfac)
+
+    dG = dev(G)
+    rhs = ops.make_rhs(rv(dG), cplx, False)
+    dw, dy, dxp = dev(w), dev(yAt), dev(xprev)
+    xn, wn = dev(np.zeros_like(w)), dev(np.zeros_like(w))
+    dalpha = torch.from_numpy(alpha).cuda()
+    dtol = torch.from_numpy(tol).cuda()
+    drow = torch.from_numpy(rowfac).cuda() if rowvec else None
+    dstep = torch.zeros(1, dtype=torch.float64, device='cuda')
+    ops.gershgorin_step(rv(dG), cplx, dstep)
+    close(host(dstep), np.array([step]))
+    latch = torch.zeros(1, dtype=torch.int32, device='cuda')
+    scratch = torch.zeros(2, dtype=torch.int32, device='cuda')
+    shrink = {'real': ops.SHRINK_REAL, 'positive': ops.SHRINK_POSITIVE, 'complex': ops.SHRINK_COMPLEX}[kind]
+    epi = ops.epilogue(ops.EPI_PROX, rv(xn), cwidth=2 if cplx else 1, out2=rv(wn), x=rv(dw), other=rv(dy),
+                       prev=rv(dxp), colvec=dalpha, colvec2=dtol, rowvec=drow, step=dstep, momentum=0.37,
+                       shrink=shrink, check=True, latch=latch, scratch=scratch, latch_value=7)
+    ops.gemm_nt(rv(dw), rhs, epi)
+    torch.cuda.synchronize()
+    close(host(xn), xn_ref)
+    close(host(wn), wn_ref)
+    assert viol and int(latch.item()) == 0
+    assert scratch.tolist() == [0, 0]
+    # converged case: prev == new iterate -> latch fires, and a latched launch is a no-op
+    dxp2 = dev(xn_ref)
+    epi = ops.epilogue(ops.EPI_PROX, rv(xn), cwidth=2 if cplx else 1, out2=rv(wn), x=rv(dw), other=rv(dy),
+                       prev=rv(dxp2), colvec=dalpha, colvec2=dtol, rowvec=drow, step=dstep, momentum=0.0,
+                       shrink=shrink, check=True, latch=latch, scratch=scratch, latch_value=7)
+    ops.gemm_nt(rv(dw), rhs, epi)
+    torch.cuda.synchronize()
+    assert int(latch.item()) == 7
+    xn.zero_()
+    ops.gemm_nt(rv(dw), rhs, epi, skip=latch)
+    torch.cuda.synchronize()
+    assert float(xn.abs().max().item()) == 0.0
+
+
+@pytest.mark.parametrize('K,M,N', [(1, 1, 1), (37, 5, 9), (5000, 20, 200), (4099, 130, 70), (20000, 256, 64)])
+def test_gemm_tn(K, M, N):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(K)
+    A, B = rng.randn(K, M), rng.randn(K, N)
+    dA, dB = dev(A), dev(B)
+    out = dev(np.zeros((M, N)))
+    ops.gemm_tn(dA, dB, out, combine=0)
+    torch.cuda.synchronize()
+    ref = A.T.dot(B)
+    close(host(out), ref)
+    first = host(out).copy()
+    ops.gemm_tn(dA, dB, out, combine=0)
+    assert np.array_equal(host(out), first), 'split-K reduction must be bitwise reproducible'
+    ops.gemm_tn(dA, dB, out, combine=1, beta=0.25)
+    close(host(out), 0.25 * ref + ref)
+
+
+@pytest.mark.parametrize('K,M,N', [(300, 3, 5), (2500, 12, 33)])
+def test_gemm_tn_complex(K, M, N):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(K)
+    A = rng.randn(K, M) + 1j * rng.randn(K, M)
+    B = rng.randn(K, N) + 1j * rng.randn(K, N)
+    dA, dB = dev(A), dev(B)
+    out = dev(np.zeros((M, N), dtype=complex))
+    ops.gemm_tn(rv(dA), rv(dB), rv(out), combine=2)
+    ref = np.conj(A.T).dot(B)
+    close(host(out), ref)
+    ops.gemm_tn(rv(dA), rv(dB), rv(out), combine=3, beta=0.5)
+    close(host(out), 0.5 * ref + ref)
+
+
+def test_make_rhs_real():
+    from decomp_b200 import ops
+    rng = np.random.RandomState(0)
+    S = rng.randn(37, 101)
+    dS = dev(S)
+    close(host(ops.make_rhs(dS, False, False)), S.T)
+    close(host(ops.make_rhs(dS, False, True)), S)
+
+
+def test_vector_kernels():
+    from decomp_b200 import ops
+    rng = np.random.RandomState(5)
+    A = rng.randn(41, 67)
+    Ac = rng.randn(41, 33) + 1j * rng.randn(41, 33)
+    dA, dAc = dev(A), dev(Ac)
+    close(host(ops.row_norms(dA, False)), np.sqrt((A * A).sum(-1)))
+    close(host(ops.row_norms(rv(dAc), True)), np.sqrt((np.abs(Ac) ** 2).sum(-1)))
+    close(host(ops.col_sums(dA, 0.5)), A.sum(0) * 0.5)
+    close(host(ops.row_sums(dA, 2.0)), A.sum(1) * 2.0)
+    big = rng.randn(9000, 13)
+    close(host(ops.col_sums(dev(big), 1.0 / 9000)), big.mean(0))
+    rs, cs = np.abs(rng.randn(41)) + 0.1, np.abs(rng.randn(67)) + 0.1
+    drs, dcs = torch.from_numpy(rs).cuda(), torch.from_numpy(cs).cuda()
+    out = dev(np.zeros_like(A))
+    close(host(ops.scale(dA, out, rowscale=drs, invert_row=True, colscale=dcs)), A / rs[:, None] * cs)
+    cs2 = np.abs(rng.randn(33)) + 0.1
+    outc = dev(np.zeros_like(Ac))
+    ops.scale(rv(dAc), rv(outc), cwidth=2, colscale=torch.from_numpy(cs2).cuda(), invert_col=True)
+    close(host(outc), Ac / cs2)
+    mask = np.rint(rng.uniform(0.3, 1, size=A.shape))
+    close(host(ops.mask_mul(dA, dev(mask), out)), A * mask)
+    maskc = np.rint(rng.uniform(0.3, 1, size=Ac.shape))
+    ops.mask_mul(rv(dAc), dev(maskc), rv(outc), cwidth=2)
+    close(host(outc), Ac * maskc)
+    idx = rng.permutation(41)
+    g = dev(np.zeros_like(A))
+    ops.gather_rows(dA, torch.from_numpy(idx).cuda(), g)
+    close(host(g), A[idx])
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+def test_normalize_rows_and_latch(cplx):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(6)
+    D = rng.randn(9, 45) + (1j * rng.randn(9, 45) if cplx else 0)
+    ref_prev = D / np.sqrt((np.abs(D) ** 2).sum(-1, keepdims=True)) + 1e-3 * rng.randn(9, 45)
+    dD, dR = dev(D), dev(ref_prev)
+    out = dev(np.zeros_like(D))
+    latch = torch.zeros(1, dtype=torch.int32, device='cuda')
+    scratch = torch.zeros(1, dtype=torch.int32, device='cuda')
+    maxdiff = torch.zeros(2, dtype=torch.float64, device='cuda')
+    ops.normalize_rows(rv(dD), rv(out), cplx, True, D_ref=rv(dR), tol=1e-6, latch=latch, latch_value=5,
+                       maxdiff=maxdiff, scratch=scratch)
+    want = D / np.sqrt((np.abs(D) ** 2).sum(-1, keepdims=True))
+    close(host(out), want)
+    close(host(maxdiff)[1:], np.array([np.max(np.abs(ref_prev - want))]))
+    assert int(latch.item()) == 0 and float(maxdiff[0].item()) == 0.0
+    ops.normalize_rows(rv(dD), rv(out), cplx, True, D_ref=rv(dR), tol=1.0, latch=latch, latch_value=5,
+                       maxdiff=maxdiff, scratch=scratch)
+    assert int(latch.item()) == 5
+    big = D * 10
+    ops.normalize_rows(rv(dev(big)), rv(out), cplx, False)
+    close(host(out), big / np.sqrt(np.maximum((np.abs(big) ** 2).sum(-1, keepdims=True), 1.0)))
+    small = D * 1e-3
+    ops.normalize_rows(rv(dev(small)), rv(out), cplx, False)
+    close(host(out), small)
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('k,f', [(3, 5), (9, 70), (40, 300)])
+def test_dl_sweep(cplx, k, f):
+    from decomp_b200 import ops
+    rng = np.random.RandomState(k * f)
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    X = randn(4 * k + 3, k)
+    S = np.conj(X.T).dot(X)
+    T = randn(k, f) * 3
+    D = randn(k, f)
+    D = D / np.sqrt((np.abs(D) ** 2).sum(-1, keepdims=True))
+    Dn = D.copy()
+    for a in range(k):
+        u = (T[a] - np.dot(S[a], Dn)) / (S[a, a] + 1e-15) + Dn[a]
+        Dn[a] = u / np.sqrt(np.maximum(np.sum(np.abs(u) ** 2), 1.0))
+    dD = dev(D)
+    ops.dl_sweep(rv(dev(S)), rv(dev(T)), rv(dD), cplx)
+    torch.cuda.synchronize()
+    close(host(dD), Dn, 1e-10)
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('k,f,mb', [(3, 5, 20), (7, 33, 50)])
+def test_dl_masked_stats_and_update(cplx, k, f, mb):
+    from decomp_b200 import ops
+    from decomp_b200._device import zeros2d, empty2d
+    rng = np.random.RandomState(k * f)
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    X = randn(mb, k)
+    mask = np.rint(rng.uniform(0.3, 1, size=(mb, f)))
+    S0 = randn(k, f, k)
+    beta = 0.3
+    xh = np.conj(X.T)
+    S_ref = beta * S0 + np.tensordot(xh, np.expand_dims(X, -2) * np.expand_dims(mask, -1), axes=1)
+    cw = 2 if cplx else 1
+    dX, dM = dev(X), dev(mask)
+    dS = torch.from_numpy(np.ascontiguousarray(S0)).cuda()          # [k, f, k] (complex) contiguous
+    dS_r = torch.view_as_real(dS).reshape(k, f, k * 2) if cplx else dS
+    W = empty2d(mb, k, cplx)
+    for a in range(k):
+        ops.dl_atom_weighted(rv(dX), cplx, a, rv(W))
+        ops.gemm_tn(dM, rv(W), dS_r[a], combine=1, beta=beta)
+    torch.cuda.synchronize()
+    close(host(dS), S_ref)
+    # Jacobi update
+    T = randn(k, f)
+    D = randn(k, f)
+    Dn = D.copy()
+    for a in range(k):
+        SaD = np.einsum('jk,kj->j', S_ref[a], D)
+        Saa = np.sum(S_ref[a, :, a] + 1e-15)
+        u = (T[a] - SaD) / Saa + Dn[a]
+        Dn[a] = u / np.sqrt(np.maximum(np.sum(np.abs(u) ** 2), 1.0))
+    dOut = dev(np.zeros_like(D))
+    ws = torch.empty(f * k * cw, dtype=torch.float64, device='cuda')
+    ops.dl_masked_update(dS_r, rv(dev(T)), rv(dev(D)), rv(dOut), cplx, ws)
+    torch.cuda.synchronize()
+    close(host(dOut), Dn, 1e-10)

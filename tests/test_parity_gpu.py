@@ -1,0 +1,164 @@
+"""Parity of the public solve() entry points (CUDA path, through the C ABI) against
+
+  * the golden outputs of the unmodified reference (tests/golden/, made by tools/make_golden.py), and
+  * the numpy oracle on larger seeded inputs the oracle finishes in seconds.
+
+Tolerance: 1e-10 relative (max-norm) on the returned factors for the FP64 path, as BASELINE.json's
+north_star states; iteration counts must be identical.  float32 inputs are widened to FP64 on the
+device, so they are compared with the reference's float32 result at float32 accuracy.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RTOL = 1.0e-10
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + '.npz'))
+
+
+def rel_err(a, b):
+    scale = max(np.max(np.abs(b)), 1.0e-300)
+    return np.max(np.abs(a - b)) / scale
+
+
+def assert_close(a, b, rtol=RTOL, what=''):
+    assert a.shape == b.shape, '%s shape %s vs %s' % (what, a.shape, b.shape)
+    assert a.dtype == b.dtype, '%s dtype %s vs %s' % (what, a.dtype, b.dtype)
+    err = rel_err(a, b)
+    assert err <= rtol, '%s relative error %.3g > %.1g' % (what, err, rtol)
+
+
+# ----------------------------------------------------------------------------------- golden: NMF
+@pytest.mark.parametrize('name', list(gc.nmf_cases().keys()))
+def test_nmf_golden(name):
+    from decomp_b200 import nmf
+    case = gc.nmf_cases()[name]
+    g = load('nmf_' + name)
+    it, D, x = nmf.solve(case['y'], case['D'].copy(), tol=case['tol'], maxiter=case['maxiter'],
+                         likelihood=case['likelihood'], mask=case['mask'])
+    assert isinstance(it, int) and it == int(g['it'])
+    assert_close(D, g['D'], what='D')
+    assert_close(x, g['x'], what='x')
+
+
+# ----------------------------------------------------------------------------------- golden: Lasso
+@pytest.mark.parametrize('name', list(gc.lasso_cases().keys()))
+def test_lasso_golden(name):
+    from decomp_b200 import lasso
+    case = gc.lasso_cases()[name]
+    g = load('lasso_' + name)
+    it, x = lasso.solve(case['y'], case['A'], case['alpha'], tol=case['tol'], method=case['method'],
+                        maxiter=case['maxiter'], mask=case['mask'])
+    single = x.dtype in (np.float32, np.complex64)
+    if not single:
+        assert it == int(g['it'])
+    assert_close(x, g['x'], rtol=2.0e-4 if single else RTOL, what='x')
+
+
+# ----------------------------------------------------------------------------------- golden: dictionary learning
+@pytest.mark.parametrize('name', list(gc.dl_cases().keys()))
+def test_dictionary_learning_golden(name):
+    from decomp_b200 import dictionary_learning
+    case = gc.dl_cases()[name]
+    g = load('dl_' + name)
+    kw = {k: v for k, v in case.items() if k not in ('y', 'D', 'alpha')}
+    it, D, x = dictionary_learning.solve(case['y'], case['D'].copy(), case['alpha'], **kw)
+    assert it == int(g['it'])
+    assert_close(D, g['D'], rtol=1.0e-9, what='D')
+    assert_close(x, g['x'], rtol=1.0e-9, what='x')
+
+
+# ----------------------------------------------------------------------------------- oracle on larger inputs
+@pytest.mark.parametrize('masked', [False, True])
+def test_nmf_vs_oracle_multi_tile(masked):
+    """Several row tiles, ragged edges, k spanning more than one N tile."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(3001, 517, 70, 11)
+    m = mask if masked else None
+    it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=21, mask=m)
+    it, D, x = nmf.solve(y, D0.copy(), tol=0.0, maxiter=21, mask=m)
+    assert it == it0 == 21
+    assert_close(D, D_ref, what='D')
+    assert_close(x, x_ref, what='x')
+    obj, obj_ref = orc.nmf_objective(y, x, D, m), orc.nmf_objective(y, x_ref, D_ref, m)
+    assert abs(obj - obj_ref) <= RTOL * abs(obj_ref)
+
+
+@pytest.mark.parametrize('method', ['ista', 'fista', 'fista_pos'])
+@pytest.mark.parametrize('mask_kind', ['nomask', 'mask'])
+def test_lasso_vs_oracle_multi_tile(method, mask_kind):
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((2500,), 150, 333, 7, positive=method.endswith('_pos'))
+    m = mask if mask_kind == 'mask' else None
+    it0, x_ref = orc.lasso(y, A, 0.05, tol=0.0, method=method, maxiter=30, mask=m)
+    it, x = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=30, mask=m)
+    assert it == it0 == 29
+    assert_close(x, x_ref, what='x')
+    obj, obj_ref = orc.lasso_objective(y, A, x, 0.05, m), orc.lasso_objective(y, A, x_ref, 0.05, m)
+    assert abs(obj - obj_ref) <= RTOL * abs(obj_ref)
+
+
+def test_lasso_complex_vs_oracle_multi_tile():
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((700,), 90, 130, 8, complex_=True)
+    for m in (None, mask):
+        it0, x_ref = orc.lasso(y, A, 0.05, tol=0.0, method='fista', maxiter=25, mask=m)
+        it, x = lasso.solve(y, A, 0.05, tol=0.0, method='fista', maxiter=25, mask=m)
+        assert it == it0
+        assert_close(x, x_ref, what='x')
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('masked', [False, True])
+def test_dictionary_learning_vs_oracle(cplx, masked):
+    from decomp_b200 import dictionary_learning
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._dl_data(1030, 75, 40, 9, cplx)
+    m = mask if masked else None
+    yy = y * mask if masked else y
+    kw = dict(tol=0.0, minibatch=256, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5, mask=m,
+              random_seed=4)
+    it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, **kw)
+    it, D, x = dictionary_learning.solve(yy, D0.copy(), 0.05, **kw)
+    assert it == it0
+    assert_close(D, D_ref, rtol=1.0e-9, what='D')
+    assert_close(x, x_ref, rtol=1.0e-9, what='x')
+
+
+# ----------------------------------------------------------------------------------- API behaviour
+def test_torch_inputs_stay_on_device():
+    import torch
+    from decomp_b200 import lasso, nmf
+    case = gc.lasso_cases()['mat_fista_nomask']
+    g = load('lasso_mat_fista_nomask')
+    it, x = lasso.solve(torch.from_numpy(case['y']).cuda(), torch.from_numpy(case['A']).cuda(), case['alpha'],
+                        tol=case['tol'], method='fista', maxiter=case['maxiter'])
+    assert isinstance(x, torch.Tensor) and x.is_cuda and it == int(g['it'])
+    assert rel_err(x.cpu().numpy(), g['x']) <= RTOL
+    case = gc.nmf_cases()['ragged_l2']
+    g = load('nmf_ragged_l2')
+    it, D, x = nmf.solve(torch.from_numpy(case['y']).cuda(), torch.from_numpy(case['D']).cuda(), tol=0.0,
+                         maxiter=case['maxiter'])
+    assert D.is_cuda and x.is_cuda and it == int(g['it'])
+    assert rel_err(D.cpu().numpy(), g['D']) <= RTOL
+
+
+def test_inputs_are_not_mutated():
+    from decomp_b200 import nmf
+    case = gc.nmf_cases()['ragged_l2_mask']
+    y, D, mask = case['y'].copy(), case['D'].copy(), case['mask'].copy()
+    x0 = np.ones((y.shape[0], D.shape[0]))
+    nmf.solve(y, D, x=x0, tol=0.0, maxiter=5, mask=mask)
+    assert np.array_equal(y, case['y']) and np.array_equal(D, case['D']) and np.array_equal(mask, case['mask'])
+    assert np.array_equal(x0, np.ones_like(x0))
