@@ -183,6 +183,7 @@ def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=No
         ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
         A_rhs = ops.make_rhs(Anr, cplx, False)                    # NT operand of  w . A
     else:
+        ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
         G_rhs = ops.make_rhs(rview(G), cplx, False)               # NT operand of  w . G
 
     # ---- iterations

@@ -60,7 +60,13 @@ def test_lasso_golden(name):
     single = x.dtype in (np.float32, np.complex64)
     if not single:
         assert it == int(g['it'])
-    assert_close(x, g['x'], rtol=2.0e-4 if single else RTOL, what='x')
+    if single:
+        # the reference's output dtype for float32 inputs is an accident of numpy scalar promotion (float64 for
+        # fista, float32 for ista); we return the input dtype and compare values at float32 accuracy
+        assert x.dtype == case['y'].dtype
+        assert rel_err(x.astype(np.float64), g['x'].astype(np.float64)) <= 2.0e-4
+    else:
+        assert_close(x, g['x'], what='x')
 
 
 # ----------------------------------------------------------------------------------- golden: dictionary learning
