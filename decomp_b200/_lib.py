@@ -46,6 +46,7 @@ _lib = None
 def _declare(lib):
     lib.decomp_last_error.restype = ctypes.c_char_p
     lib.decomp_abi_version.restype = ctypes.c_int
+    lib.decomp_probe_dmma_tflops.argtypes = [ctypes.POINTER(ctypes.c_double)]
     lib.decomp_gemm_nt_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i64,
                                        ctypes.POINTER(Epilogue), c_dp, c_dp]
     lib.decomp_gemm_tn_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
@@ -78,7 +79,7 @@ def _declare(lib):
 
 
 EXPORTS = (
-    'decomp_last_error', 'decomp_abi_version', 'decomp_gemm_nt_f64', 'decomp_gemm_tn_workspace_bytes',
+    'decomp_last_error', 'decomp_abi_version', 'decomp_probe_dmma_tflops', 'decomp_gemm_nt_f64', 'decomp_gemm_tn_workspace_bytes',
     'decomp_gemm_tn_f64', 'decomp_make_rhs_f64', 'decomp_row_norms_f64', 'decomp_scale_f64', 'decomp_mask_mul_f64',
     'decomp_col_sums_f64', 'decomp_row_sums_f64', 'decomp_gershgorin_step_f64', 'decomp_normalize_rows_f64',
     'decomp_gather_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',

@@ -403,6 +403,27 @@ __global__ void max_abs_diff_kernel(const double* __restrict__ A, long long lda,
   }
 }
 
+// ------------------------------------------------------------------------------------ DMMA issue-rate probe
+// Roofline denominator for the FP64 tensor path (MEASURED_PEAKS.json has no FP64 entry): every warp issues
+// independent DMMA.8x8x4 chains from registers, no memory traffic.
+__global__ void dmma_rate_kernel(double* out, const double* in, int iters) {
+  double a = in[threadIdx.x & 31], b = in[32 + (threadIdx.x & 31)];
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[j][0]), "+d"(c[j][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == 123.456) out[threadIdx.x] = s;
+}
+
 static int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -416,6 +437,35 @@ static int grid_for(long long total, int threads) {
 using namespace dcp;
 
 extern "C" {
+
+int decomp_probe_dmma_tflops(double* tflops_out) {
+  if (tflops_out == nullptr) return DECOMP_ERR_INVALID;
+  double* buf = nullptr;
+  int rc = check_cuda(cudaMalloc(&buf, (64 + 1024) * sizeof(double)), "probe alloc");
+  if (rc != DECOMP_OK) return rc;
+  cudaMemset(buf, 0, (64 + 1024) * sizeof(double));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 8192, warps = 16, sms = num_sms();
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {
+    cudaEventRecord(e0);
+    dmma_rate_kernel<<<sms, warps * 32>>>(buf + 64, buf, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (e != cudaSuccess) return check_cuda(e, "dmma probe");
+  *tflops_out = 2.0 * 256.0 * 8.0 * iters * warps * sms / (best * 1e-3) / 1e12;
+  return DECOMP_OK;
+}
 
 int decomp_make_rhs_f64(const double* S, int64_t lds, int64_t p, int64_t q, int32_t is_complex,
                         int32_t conj_transpose, double* B, int64_t ldb, const int32_t* skip_if, void* stream) {

@@ -45,18 +45,15 @@ def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=Non
     hot path and raise ``NotImplementedError``.
     """
     array_kind(y, A, x, mask)
-    if x is None:
-        if is_torch(y):
-            x = torch.zeros(tuple(y.shape[:-1]) + (A.shape[0],), dtype=y.dtype, device=y.device)
-        else:
-            x = np.zeros(y.shape[:-1] + (A.shape[0],), dtype=y.dtype)
+    # x = None means zeros(y.shape[:-1] + (k,), y.dtype) (lasso.py:73-74); they are created on the device
 
     assertion.assert_dtypes(y=y, A=A, x=x)
     assertion.assert_dtypes(mask=mask, dtypes='f')
     assertion.assert_nonnegative(mask)
     assertion.assert_ndim('A', A, ndim=2)
     assertion.assert_shapes('x', x, 'A', A, axes=1)
-    assertion.assert_shapes('y', y, 'x', x, axes=list(range(x.ndim - 1)))
+    if x is not None:
+        assertion.assert_shapes('y', y, 'x', x, axes=list(range(x.ndim - 1)))
     assertion.assert_shapes('y', y, 'A', A, axes=[-1])
     if mask is not None and mask.ndim == 1:
         assertion.assert_shapes('y', y, 'mask', mask, axes=[-1])
@@ -92,7 +89,7 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
     batch_shape = tuple(y.shape[:-1])
     k = A.shape[0]
     y2 = to_device2d(flatten_rows(y), device, copy=False)
-    x2 = to_device2d(flatten_rows(x), device, copy=False)
+    x2 = to_device2d(flatten_rows(x), device, copy=False) if x is not None else None
     A2 = to_device2d(A, device, copy=False)
     m2 = None
     if mask is not None:
@@ -133,105 +130,125 @@ def _momentum_schedule(rule, maxiter):
 
 def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None):
     """Enqueue a whole solve on the current stream. All arguments are device tensors ([B, f], [k, f],
-    [B, k]; mask None, [f] or [B, f]). Nothing is synchronised unless the latch has to be polled
-    (``tol > 0`` and more than POLL_EVERY iterations). Returns a ``LassoState``."""
-    dev = y.device
-    cplx = A.is_complex()
-    cw = 2 if cplx else 1
-    B, f = y.shape
-    k = A.shape[0]
-    yr, Ar = rview(y), rview(A)
-    full_mask = mask is not None and mask.dim() == 2
-    shrink = ops.SHRINK_POSITIVE if positive else (ops.SHRINK_COMPLEX if cplx else ops.SHRINK_REAL)
+    [B, k] or None for zeros; mask None, [f] or [B, f]). Nothing is synchronised unless the latch has to
+    be polled (``tol > 0`` and more than POLL_EVERY iterations). Returns a ``LassoState``."""
+    solver = LassoSolver(y, A, alpha, x, tol, maxiter, rule, positive, mask=mask, group=group)
+    solver.iterate(0, solver.n_inplace)
+    return solver.finish(out)
 
-    # ---- prologue (lasso.py:120-138, 163)
-    mult_dev = None
-    if mask is not None and not full_mask:
-        Am, ym = empty2d(k, f, cplx, dev), empty2d(B, f, cplx, dev)
-        ops.scale(Ar, rview(Am), cwidth=cw, colscale=mask)
-        ops.scale(yr, rview(ym), cwidth=cw, colscale=mask)
-        Ar, yr = rview(Am), rview(ym)
-        mult_dev = ops.row_sums(mask.view(1, f))
-    s = ops.row_norms(Ar, cplx)
-    An = empty2d(k, f, cplx, dev)
-    ops.scale(Ar, rview(An), cwidth=cw, rowscale=s, invert_row=True)
-    Anr = rview(An)
-    alpha_vec, tol_vec = ops.lasso_vectors(s, alpha, tol, mult=1.0 if full_mask else float(f), mult_dev=mult_dev)
-    X = empty2d(B, k, cplx, dev)
-    ops.scale(rview(x), rview(X), cwidth=cw, colscale=s)
 
-    # ---- Gram matrix, step 1/L, yAh (lasso.py:276-289, 306-321)
-    AH = ops.make_rhs(Anr, True, True) if cplx else Anr          # NT operand of  . A^H
-    G = empty2d(k, k, cplx, dev)
-    rowvec = None
-    if full_mask:
-        rowvec = ops.row_sums(mask)                               # sum(mask, -1): alpha per problem
-        mean = ops.col_sums(mask, 1.0 / B)
-        if group is not None:
-            mean = _global_mask_mean(mask, B, group)
-        Amean = empty2d(k, f, cplx, dev)
-        ops.scale(Anr, rview(Amean), cwidth=cw, colscale=mean)
-        ops.gemm_nt(rview(Amean), AH, ops.epilogue(ops.EPI_STORE, rview(G)))
-    else:
-        ops.gemm_nt(Anr, AH, ops.epilogue(ops.EPI_STORE, rview(G)))
-    step = torch.empty(1, dtype=torch.float64, device=dev)
-    ops.gershgorin_step(rview(G), cplx, step)
-    yAh = empty2d(B, k, cplx, dev)
-    if full_mask:
-        T = empty2d(B, f, cplx, dev)                              # also the per-iteration [B, f] temporary
-        ops.mask_mul(yr, mask, rview(T), cwidth=cw)
-        ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
-        A_rhs = ops.make_rhs(Anr, cplx, False)                    # NT operand of  w . A
-    else:
-        ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
-        G_rhs = ops.make_rhs(rview(G), cplx, False)               # NT operand of  w . G
+class LassoSolver(object):
+    """One batched Lasso solve, split into set-up / iterations / read-out so that callers (and bench.py) can
+    enqueue exactly the iterations they want. Every method only enqueues work on the current stream."""
 
-    # ---- iterations
-    checks = tol > 0.0
-    latch = torch.zeros(1, dtype=torch.int32, device=dev) if checks else None
-    scratch = torch.zeros(2, dtype=torch.int32, device=dev) if checks else None
-    W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
-    W[0].copy_(X)
-    Xr, yAhr = rview(X), rview(yAh)
-    mom = _momentum_schedule(rule, maxiter)
+    def __init__(self, y, A, alpha, x, tol, maxiter, rule, positive, mask=None, group=None):
+        dev = y.device
+        self.cplx = cplx = A.is_complex()
+        self.cw = cw = 2 if cplx else 1
+        self.B, self.f = B, f = y.shape
+        self.k = k = A.shape[0]
+        self.rule, self.maxiter, self.group, self.mask = rule, maxiter, group, mask
+        yr, Ar = rview(y), rview(A)
+        self.full_mask = full_mask = mask is not None and mask.dim() == 2
+        self.shrink = ops.SHRINK_POSITIVE if positive else (ops.SHRINK_COMPLEX if cplx else ops.SHRINK_REAL)
 
-    def launch(i, out_x):
-        check = checks and i % 10 == 0
-        epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
-                           other=yAhr, prev=Xr, colvec=alpha_vec, colvec2=tol_vec, rowvec=rowvec, step=step,
-                           momentum=mom[i], shrink=shrink, check=check, latch=latch, scratch=scratch,
-                           latch_value=i + 1)
-        if full_mask:
-            ops.gemm_nt(rview(W[i % 2]), A_rhs,
-                        ops.epilogue(ops.EPI_STORE_MASK, rview(T), cwidth=cw, mask=mask), skip=latch)
-            ops.gemm_nt(rview(T), AH, epi, skip=latch)
+        # ---- prologue (lasso.py:120-138, 163)
+        mult_dev = None
+        if mask is not None and not full_mask:
+            Am, ym = empty2d(k, f, cplx, dev), empty2d(B, f, cplx, dev)
+            ops.scale(Ar, rview(Am), cwidth=cw, colscale=mask)
+            ops.scale(yr, rview(ym), cwidth=cw, colscale=mask)
+            Ar, yr = rview(Am), rview(ym)
+            mult_dev = ops.row_sums(mask.view(1, f))
+        self.s = s = ops.row_norms(Ar, cplx)
+        An = empty2d(k, f, cplx, dev)
+        ops.scale(Ar, rview(An), cwidth=cw, rowscale=s, invert_row=True)
+        Anr = rview(An)
+        self.alpha_vec, self.tol_vec = ops.lasso_vectors(s, alpha, tol, mult=1.0 if full_mask else float(f),
+                                                         mult_dev=mult_dev)
+        self.X = X = empty2d(B, k, cplx, dev)
+        if x is None:
+            X.zero_()                                              # default x = zeros (lasso.py:73-74)
         else:
-            ops.gemm_nt(rview(W[i % 2]), G_rhs, epi, skip=latch)
-        if check and group is not None:
+            ops.scale(rview(x), rview(X), cwidth=cw, colscale=s)
+
+        # ---- Gram matrix, step 1/L, yAh (lasso.py:276-289, 306-321)
+        self.AH = AH = ops.make_rhs(Anr, True, True) if cplx else Anr    # NT operand of  . A^H
+        G = empty2d(k, k, cplx, dev)
+        self.rowvec = None
+        if full_mask:
+            self.rowvec = ops.row_sums(mask)                       # sum(mask, -1): alpha per problem
+            if group is not None:
+                mean = _global_mask_mean(mask, B, group)
+            else:
+                mean = ops.col_sums(mask, 1.0 / B)
+            Amean = empty2d(k, f, cplx, dev)
+            ops.scale(Anr, rview(Amean), cwidth=cw, colscale=mean)
+            ops.gemm_nt(rview(Amean), AH, ops.epilogue(ops.EPI_STORE, rview(G)))
+        else:
+            ops.gemm_nt(Anr, AH, ops.epilogue(ops.EPI_STORE, rview(G)))
+        self.step = torch.empty(1, dtype=torch.float64, device=dev)
+        ops.gershgorin_step(rview(G), cplx, self.step)
+        self.yAh = yAh = empty2d(B, k, cplx, dev)
+        if full_mask:
+            self.T = T = empty2d(B, f, cplx, dev)                  # also the per-iteration [B, f] temporary
+            ops.mask_mul(yr, mask, rview(T), cwidth=cw)
+            ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
+            self.A_rhs = ops.make_rhs(Anr, cplx, False)            # NT operand of  w . A
+        else:
+            ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
+            self.G_rhs = ops.make_rhs(rview(G), cplx, False)       # NT operand of  w . G
+
+        # ---- iteration state
+        self.checks = checks = tol > 0.0
+        self.latch = torch.zeros(1, dtype=torch.int32, device=dev) if checks else None
+        self.scratch = torch.zeros(2, dtype=torch.int32, device=dev) if checks else None
+        self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
+        self.W[0].copy_(X)
+        self.mom = _momentum_schedule(rule, maxiter)
+        # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
+        # matters if it is a checking one, and then only when the check passes.
+        self.n_inplace = maxiter - 1 if (rule == 'acc_ista' and maxiter > 0) else maxiter
+        self.stopped = False
+
+    def _launch(self, i, out_x):
+        W, cw, latch = self.W, self.cw, self.latch
+        check = self.checks and i % 10 == 0
+        epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
+                           other=rview(self.yAh), prev=rview(self.X), colvec=self.alpha_vec, colvec2=self.tol_vec,
+                           rowvec=self.rowvec, step=self.step, momentum=self.mom[i], shrink=self.shrink,
+                           check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
+        if self.full_mask:
+            ops.gemm_nt(rview(W[i % 2]), self.A_rhs,
+                        ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
+            ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
+        else:
+            ops.gemm_nt(rview(W[i % 2]), self.G_rhs, epi, skip=latch)
+        if check and self.group is not None:
             # the latch fires only if every shard passed the test (reference: one max over the whole batch)
-            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=group)
+            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
 
-    # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
-    # matters if it is a checking one, and then only when the check passes.
-    n_inplace = maxiter - 1 if (rule == 'acc_ista' and maxiter > 0) else maxiter
-    stopped = False
-    for i in range(n_inplace):
-        if checks and i > 0 and i % POLL_EVERY == 0 and int(latch.item()) != 0:
-            stopped = True
-            break
-        launch(i, Xr)
-    final = X
-    if rule == 'acc_ista' and maxiter > 0 and not stopped and checks and (maxiter - 1) % 10 == 0:
-        XL = empty2d(B, k, cplx, dev)
-        launch(maxiter - 1, rview(XL))
-        if int(latch.item()) == maxiter:
-            final = XL
+    def iterate(self, begin, end):
+        """Enqueue iterations ``begin <= i < end`` (in place on X)."""
+        for i in range(begin, min(end, self.n_inplace)):
+            if self.checks and i > 0 and i % POLL_EVERY == 0 and int(self.latch.item()) != 0:
+                self.stopped = True
+                break
+            self._launch(i, rview(self.X))
 
-    # ---- x / s (lasso.py:189)
-    if out is None:
-        out = empty2d(B, k, cplx, dev)
-    ops.scale(rview(final), rview(out), cwidth=cw, colscale=s, invert_col=True)
-    return LassoState(out, latch, maxiter)
+    def finish(self, out=None):
+        """x / s (lasso.py:189) into ``out``; returns a ``LassoState``."""
+        final, maxiter = self.X, self.maxiter
+        if (self.rule == 'acc_ista' and maxiter > 0 and not self.stopped and self.checks
+                and (maxiter - 1) % 10 == 0):
+            XL = empty2d(self.B, self.k, self.cplx, self.X.device)
+            self._launch(maxiter - 1, rview(XL))
+            if int(self.latch.item()) == maxiter:
+                final = XL
+        if out is None:
+            out = empty2d(self.B, self.k, self.cplx, self.X.device)
+        ops.scale(rview(final), rview(out), cwidth=self.cw, colscale=self.s, invert_col=True)
+        return LassoState(out, self.latch, maxiter)
 
 
 def _global_mask_mean(mask, local_rows, group):

@@ -88,52 +88,66 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
 
 def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None):
     """Full-batch MU on device tensors; ``X`` [n, k] is updated in place. Returns ``(it, D, X)``."""
-    dev = y.device
-    n, f = y.shape
-    k = D0.shape[0]
-    dist = torch.distributed if group is not None else None
-
-    Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]
-    ops.normalize_rows(D0, Dbuf[0], False, True)                     # nmf.py:70
-    Draw = empty2d(k, f, False, dev)
-    Dt = empty2d(f, k, False, dev)
-    POS = empty2d(k, f, False, dev)
-    NEG = empty2d(n, k, False, dev)
-    ws = ops.gemm_tn_workspace_for([(k, f, n), (k, k, n)], dev)
-    checks = tol > 0.0
-    latch = torch.zeros(1, dtype=torch.int32, device=dev) if checks else None
-    scratch = torch.zeros(1, dtype=torch.int32, device=dev)
-    maxdiff = torch.zeros(2, dtype=torch.float64, device=dev)
-
-    ym = y
-    if mask is not None:
-        ym = empty2d(n, f, False, dev)
-        ops.mask_mul(y, mask, ym)                                     # y * mask, once (grads.py:113,123)
-    if mask is not None or kl:
-        F = empty2d(n, f, False, dev)                                 # the [n, f] intermediate
-        NEGD = empty2d(k, f, False, dev)
-    else:
-        G = empty2d(k, k, False, dev)
-        S = empty2d(k, k, False, dev)
-    if kl and mask is None:
-        ones_kf = full2d(k, f, 1.0, False, dev)
-        dsum = torch.empty(k, dtype=torch.float64, device=dev)
-        xsum = torch.empty(k, dtype=torch.float64, device=dev)
-        dsum_row = dsum.view(1, k)
-
-    def E(kind, out, **kw):
-        return ops.epilogue(kind, out, **kw)
-
-    it_done = maxiter
+    solver = MuSolver(y, D0, X, tol, kl=kl, mask=mask, group=group)
     stopped_at = 0
     for it in range(1, maxiter):
-        if checks and it % POLL_EVERY == 0:
-            fired = int(latch.item())
-            if fired:
-                stopped_at = fired
+        if solver.checks and it % POLL_EVERY == 0:
+            stopped_at = solver.fired()
+            if stopped_at:
                 break
-        D, Dn = Dbuf[(it - 1) % 2], Dbuf[it % 2]
-        if not kl and mask is None:
+        solver.sweep(it)
+    if solver.checks and not stopped_at:
+        stopped_at = solver.fired()
+    if stopped_at:
+        return stopped_at, solver.Dbuf[stopped_at % 2], X
+    return maxiter, solver.Dbuf[max(maxiter - 1, 0) % 2], X
+
+
+class MuSolver(object):
+    """Device state of a full-batch MU run; ``sweep(it)`` enqueues sweep number ``it`` (1-based, reading
+    ``Dbuf[(it - 1) % 2]`` and writing ``Dbuf[it % 2]``) on the current stream without synchronising."""
+
+    def __init__(self, y, D0, X, tol, kl=False, mask=None, group=None):
+        dev = y.device
+        self.y, self.X, self.mask, self.kl, self.tol, self.group = y, X, mask, kl, tol, group
+        self.n, self.f = n, f = y.shape
+        self.k = k = D0.shape[0]
+        self.Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]
+        ops.normalize_rows(D0, self.Dbuf[0], False, True)                 # nmf.py:70
+        self.Draw = empty2d(k, f, False, dev)
+        self.Dt = empty2d(f, k, False, dev)
+        self.POS = empty2d(k, f, False, dev)
+        self.NEG = empty2d(n, k, False, dev)
+        self.ws = ops.gemm_tn_workspace_for([(k, f, n), (k, k, n)], dev)
+        self.checks = tol > 0.0
+        self.latch = torch.zeros(1, dtype=torch.int32, device=dev) if self.checks else None
+        self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.maxdiff = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.ym = y
+        if mask is not None:
+            self.ym = empty2d(n, f, False, dev)
+            ops.mask_mul(y, mask, self.ym)                                # y * mask, once (grads.py:113,123)
+        if mask is not None or kl:
+            self.F = empty2d(n, f, False, dev)                            # the [n, f] intermediate
+            self.NEGD = empty2d(k, f, False, dev)
+        else:
+            self.G = empty2d(k, k, False, dev)
+            self.S = empty2d(k, k, False, dev)
+        if kl and mask is None:
+            self.ones_kf = full2d(k, f, 1.0, False, dev)
+            self.dsum = torch.empty(k, dtype=torch.float64, device=dev)
+            self.xsum = torch.empty(k, dtype=torch.float64, device=dev)
+
+    def fired(self):
+        return int(self.latch.item()) if self.latch is not None else 0
+
+    def sweep(self, it):
+        E = ops.epilogue
+        y, ym, X, mask, latch, ws, group = self.y, self.ym, self.X, self.mask, self.latch, self.ws, self.group
+        D, Dn = self.Dbuf[(it - 1) % 2], self.Dbuf[it % 2]
+        Dt, POS, NEG, Draw = self.Dt, self.POS, self.NEG, self.Draw
+        if not self.kl and mask is None:
+            G, S = self.G, self.S
             # ---- x update (grads.py:108-111 with f.dot(d.T) re-associated)
             ops.gemm_nt(D, D, E(ops.EPI_STORE, G), skip=latch)
             ops.gemm_nt(X, G, E(ops.EPI_STORE, NEG), skip=latch)
@@ -141,14 +155,15 @@ def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None):
             # ---- D update (grads.py:117-121): sufficient statistics over the sample axis
             ops.gemm_tn(X, y, POS, workspace=ws, skip=latch)
             ops.gemm_tn(X, X, S, workspace=ws, skip=latch)
-            if dist is not None:
+            if group is not None:
                 _allreduce2d(POS, group)
                 _allreduce2d(S, group)
             ops.make_rhs(D, False, False, out=Dt, skip=latch)
             ops.gemm_nt(S, Dt, E(ops.EPI_MU_DEN, Draw, x=D, other=POS), skip=latch)
         else:
+            F, NEGD = self.F, self.NEGD
             ops.make_rhs(D, False, False, out=Dt, skip=latch)
-            if not kl:
+            if not self.kl:
                 # ---- masked l2 (grads.py:112-115, 122-125)
                 ops.gemm_nt(X, Dt, E(ops.EPI_STORE_MASK, F, mask=mask), skip=latch)
                 ops.gemm_nt(F, D, E(ops.EPI_STORE, NEG), skip=latch)
@@ -160,8 +175,8 @@ def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None):
                 # ---- Poisson / KL (grads.py:142-160)
                 ops.gemm_nt(X, Dt, E(ops.EPI_KL_RATIO, F, other=y, mask=mask), skip=latch)
                 if mask is None:
-                    ops.row_sums(D, 1.0, out=dsum)
-                    neg_x = E(ops.EPI_MU_NUM, X, x=X, other=dsum_row)
+                    ops.row_sums(D, 1.0, out=self.dsum)
+                    neg_x = E(ops.EPI_MU_NUM, X, x=X, other=self.dsum.view(1, self.k))
                     neg_x.ldother = 0                                  # one [1, k] row for every sample
                     ops.gemm_nt(F, D, neg_x, skip=latch)
                 else:
@@ -170,28 +185,21 @@ def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None):
                 ops.gemm_nt(X, Dt, E(ops.EPI_KL_RATIO, F, other=y, mask=mask), skip=latch)
                 ops.gemm_tn(X, F, POS, workspace=ws, skip=latch)
                 if mask is None:
-                    ops.col_sums(X, 1.0, out=xsum)
-                    if dist is not None:
-                        dist.all_reduce(xsum, group=group)
-                    ops.scale(ones_kf, NEGD, rowscale=xsum)
+                    ops.col_sums(X, 1.0, out=self.xsum)
+                    if group is not None:
+                        torch.distributed.all_reduce(self.xsum, group=group)
+                    ops.scale(self.ones_kf, NEGD, rowscale=self.xsum)
                 else:
                     ops.gemm_tn(X, mask, NEGD, workspace=ws, skip=latch)
-            if dist is not None:
+            if group is not None:
                 _allreduce2d(POS, group)
-                if not (kl and mask is None):
+                if not (self.kl and mask is None):
                     _allreduce2d(NEGD, group)
             ops.mu_update(D, POS, NEGD, Draw, skip=latch)
         # ---- l2_strict + max|D - D_new| < tol (batch_mu.py:21-23)
-        ops.normalize_rows(Draw, Dn, False, True, D_ref=D if checks else None, tol=tol, latch=latch,
-                           latch_value=it, maxdiff=maxdiff if checks else None, scratch=scratch, skip=latch)
-        it_done = it
-    if checks and not stopped_at:
-        stopped_at = int(latch.item())
-    if stopped_at:
-        return stopped_at, Dbuf[stopped_at % 2], X
-    if maxiter <= 1:
-        return maxiter, Dbuf[0], X
-    return maxiter, Dbuf[it_done % 2], X
+        ops.normalize_rows(Draw, Dn, False, True, D_ref=D if self.checks else None, tol=self.tol, latch=latch,
+                           latch_value=it, maxdiff=self.maxdiff if self.checks else None, scratch=self.scratch,
+                           skip=latch)
 
 
 def _allreduce2d(t, group):

@@ -15,8 +15,23 @@ from ._lib import (EPI_KL_RATIO, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EP
 from ._device import empty2d
 
 
+LAUNCHES = 0   # kernels of libdecomp_b200.so launched through this module (bench.py reports the count)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def probe_dmma_tflops():
+    """Measured DMMA.8x8x4 issue rate of the current device (TFLOP/s); roofline denominator of the FP64 GEMMs."""
+    v = ctypes.c_double(0.0)
+    _lib.check(_lib.lib().decomp_probe_dmma_tflops(ctypes.byref(v)), 'decomp_probe_dmma_tflops')
+    return v.value
 
 
 def epilogue(kind, out, cwidth=1, **kw):
@@ -51,6 +66,7 @@ def gemm_nt(A, B, epi, skip=None):
     rc = _lib.lib().decomp_gemm_nt_f64(_p(A), ld(A), _p(B), ld(B), M, N, K, ctypes.byref(epi), _p(skip),
                                        _lib.stream_ptr())
     _lib.check(rc, 'decomp_gemm_nt_f64')
+    _count(1)
 
 
 def gemm_tn_workspace(M, N, K, device):
@@ -74,6 +90,7 @@ def gemm_tn(A, B, out, combine=0, beta=0.0, workspace=None, skip=None):
     rc = _lib.lib().decomp_gemm_tn_f64(_p(A), ld(A), _p(B), ld(B), M, N, K, _p(out), ld(out), combine, float(beta),
                                        _p(workspace), workspace.numel() * 8, _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_gemm_tn_f64')
+    _count(2)
     return out
 
 
@@ -87,6 +104,7 @@ def make_rhs(S, is_complex, conj_transpose, out=None, skip=None):
     rc = _lib.lib().decomp_make_rhs_f64(_p(S), ld(S), p, q, int(is_complex), int(conj_transpose), _p(out), ld(out),
                                         _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_make_rhs_f64')
+    _count(1)
     return out
 
 
@@ -97,6 +115,7 @@ def row_norms(A, is_complex, out=None):
         out = torch.empty(rows, dtype=torch.float64, device=A.device)
     rc = _lib.lib().decomp_row_norms_f64(_p(A), ld(A), rows, cols, int(is_complex), _p(out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_row_norms_f64')
+    _count(1)
     return out
 
 
@@ -105,6 +124,7 @@ def scale(A, out, cwidth=1, rowscale=None, invert_row=False, colscale=None, inve
     rc = _lib.lib().decomp_scale_f64(_p(A), ld(A), rows, cols, cwidth, _p(rowscale), int(invert_row), _p(colscale),
                                      int(invert_col), _p(out), ld(out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_scale_f64')
+    _count(1)
     return out
 
 
@@ -113,6 +133,7 @@ def mask_mul(A, mask, out, cwidth=1):
     rc = _lib.lib().decomp_mask_mul_f64(_p(A), ld(A), _p(mask), ld(mask), rows, cols, cwidth, _p(out), ld(out),
                                         _lib.stream_ptr())
     _lib.check(rc, 'decomp_mask_mul_f64')
+    _count(1)
     return out
 
 
@@ -122,6 +143,7 @@ def col_sums(A, scale_=1.0, out=None):
         out = torch.empty(cols, dtype=torch.float64, device=A.device)
     rc = _lib.lib().decomp_col_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_col_sums_f64')
+    _count(2)
     return out
 
 
@@ -131,6 +153,7 @@ def row_sums(A, scale_=1.0, out=None):
         out = torch.empty(rows, dtype=torch.float64, device=A.device)
     rc = _lib.lib().decomp_row_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_row_sums_f64')
+    _count(1)
     return out
 
 
@@ -141,6 +164,7 @@ def gershgorin_step(G, is_complex, step_out, alpha_scaled=None, thr_out=None):
     rc = _lib.lib().decomp_gershgorin_step_f64(_p(G), ld(G), k, int(is_complex), _p(alpha_scaled), _p(step_out),
                                                _p(thr_out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_gershgorin_step_f64')
+    _count(1)
     return step_out
 
 
@@ -153,6 +177,7 @@ def normalize_rows(D_in, D_out, is_complex, strict, D_ref=None, tol=0.0, latch=N
         ld(D_ref) if D_ref is not None else 0, float(tol), _p(latch), int(latch_value), _p(maxdiff), _p(scratch),
         _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_normalize_rows_f64')
+    _count(1)
     return D_out
 
 
@@ -161,6 +186,7 @@ def gather_rows(src, index, out):
     rc = _lib.lib().decomp_gather_rows_f64(_p(src), ld(src), _p(index), rows, cols, _p(out), ld(out),
                                            _lib.stream_ptr())
     _lib.check(rc, 'decomp_gather_rows_f64')
+    _count(1)
     return out
 
 
@@ -170,6 +196,7 @@ def dl_sweep(S, T, D, is_complex):
     rc = _lib.lib().decomp_dl_sweep_f64(_p(S), ld(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex),
                                         _lib.stream_ptr())
     _lib.check(rc, 'decomp_dl_sweep_f64')
+    _count(1)
     return D
 
 
@@ -179,6 +206,7 @@ def dl_atom_weighted(X, is_complex, atom, W):
     rc = _lib.lib().decomp_dl_atom_weighted_f64(_p(X), ld(X), rows, k, int(is_complex), int(atom), _p(W), ld(W),
                                                 _lib.stream_ptr())
     _lib.check(rc, 'decomp_dl_atom_weighted_f64')
+    _count(1)
     return W
 
 
@@ -188,6 +216,7 @@ def dl_masked_update(S, T, D, D_out, is_complex, workspace):
     rc = _lib.lib().decomp_dl_masked_update_f64(_p(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex), _p(D_out),
                                                 ld(D_out), _p(workspace), _lib.stream_ptr())
     _lib.check(rc, 'decomp_dl_masked_update_f64')
+    _count(2)
     return D_out
 
 
@@ -198,6 +227,7 @@ def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):
     rc = _lib.lib().decomp_lasso_vectors_f64(_p(s), k, float(alpha), float(tol), float(mult), _p(mult_dev),
                                              _p(alpha_out), _p(tol_out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_lasso_vectors_f64')
+    _count(1)
     return alpha_out, tol_out
 
 
@@ -206,6 +236,7 @@ def mu_update(x, num, den, out, skip=None):
     rc = _lib.lib().decomp_mu_update_f64(_p(x), ld(x), _p(num), ld(num), _p(den), ld(den), rows, cols, _p(out), ld(out),
                                          _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_mu_update_f64')
+    _count(1)
     return out
 
 
@@ -216,4 +247,5 @@ def max_abs_diff(A, B, is_complex, result, scratch, tol=0.0, latch=None, latch_v
                                             _p(latch), int(latch_value), _p(result), _p(scratch), _p(skip),
                                             _lib.stream_ptr())
     _lib.check(rc, 'decomp_max_abs_diff_f64')
+    _count(1)
     return result

@@ -81,6 +81,10 @@ typedef struct decomp_epilogue {
 
 const char* decomp_last_error(void);
 int decomp_abi_version(void);
+/* Measurement aid (bench.py only): issue rate of the FP64 tensor instruction (DMMA.8x8x4 from registers, no
+ * memory traffic) on the current device in TFLOP/s -- the roofline denominator of the FP64 GEMM kernels.
+ * Synchronises the device. */
+int decomp_probe_dmma_tflops(double* tflops_out);
 
 /* acc[m][n] = sum_k A[m*lda + k] * B[n*ldb + k]   (A: [M,K], B: [N,K], both K-contiguous),
  * followed by the fused epilogue.  TMA-fed, DMMA.8x8x4 mainloop.
