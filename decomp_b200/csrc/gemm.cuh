@@ -71,94 +71,149 @@ __device__ __forceinline__ void st_pair(double* p, double a, double b, bool two)
   }
 }
 
-template <int KIND>
+// Each epilogue processes one output row of a warp tile at a time: the NJ column pairs (col = cbase + 8 j,
+// col + 1) a lane owns in that row.  All global loads of the row are issued before the first store so that
+// they are in flight together (the operands may alias the outputs -- in-place updates -- so the compiler
+// cannot hoist loads over stores by itself).
+template <int KIND, int NJ>
 struct Epilogue {
-  // returns true if the convergence test is violated by this pair (PROX with check only)
-  static __device__ __forceinline__ bool apply(const decomp_epilogue_t& ep, long long row, long long col, double v0,
-                                               double v1, bool two) {
+  // returns true if the convergence test is violated by any pair of this row (PROX with check only)
+  static __device__ __forceinline__ bool row(const decomp_epilogue_t& ep, long long row, long long cbase, long long N,
+                                             const double (&acc)[NJ][2]) {
+    bool ok[NJ], two[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      ok[j] = cbase + 8 * j < N;
+      two[j] = cbase + 8 * j + 1 < N;
+    }
     if constexpr (KIND == DECOMP_EPI_STORE) {
-      st_pair(ep.out + row * ep.ldo + col, v0, v1, two);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (ok[j]) st_pair(ep.out + row * ep.ldo + cbase + 8 * j, acc[j][0], acc[j][1], two[j]);
     } else if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
-      double m0, m1;
-      if (ep.cwidth == 2) {
-        m0 = m1 = ep.mask[row * ep.ldmask + (col >> 1)];
-      } else {
-        Pair m = ld_pair(ep.mask + row * ep.ldmask + col, two);
-        m0 = m.a;
-        m1 = m.b;
+      Pair m[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        const long long col = cbase + 8 * j;
+        if (ep.cwidth == 2) {
+          m[j].a = m[j].b = ep.mask[row * ep.ldmask + (col >> 1)];
+        } else {
+          m[j] = ld_pair(ep.mask + row * ep.ldmask + col, two[j]);
+        }
       }
-      st_pair(ep.out + row * ep.ldo + col, v0 * m0, v1 * m1, two);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        if (ok[j]) st_pair(ep.out + row * ep.ldo + cbase + 8 * j, acc[j][0] * m[j].a, acc[j][1] * m[j].b, two[j]);
     } else if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
-      Pair x = ld_pair(ep.x + row * ep.ldx + col, two);
-      Pair o = ld_pair(ep.other + row * ep.ldother + col, two);
-      double n0, n1, d0, d1;
-      if constexpr (KIND == DECOMP_EPI_MU_NUM) {
-        n0 = v0; n1 = v1; d0 = o.a; d1 = o.b;
-      } else {
-        n0 = o.a; n1 = o.b; d0 = v0; d1 = v1;
+      Pair x[NJ], o[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        const long long col = cbase + 8 * j;
+        x[j] = ld_pair(ep.x + row * ep.ldx + col, two[j]);
+        o[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
       }
-      // x * max(pos, 0) / max(neg, eps), evaluated left to right like the reference (grads.py:84,93)
-      double r0 = __ddiv_rn(__dmul_rn(x.a, fmax(n0, 0.0)), fmax(d0, kEps));
-      double r1 = __ddiv_rn(__dmul_rn(x.b, fmax(n1, 0.0)), fmax(d1, kEps));
-      st_pair(ep.out + row * ep.ldo + col, r0, r1, two);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        double n0, n1, d0, d1;
+        if constexpr (KIND == DECOMP_EPI_MU_NUM) {
+          n0 = acc[j][0]; n1 = acc[j][1]; d0 = o[j].a; d1 = o[j].b;
+        } else {
+          n0 = o[j].a; n1 = o[j].b; d0 = acc[j][0]; d1 = acc[j][1];
+        }
+        // x * max(pos, 0) / max(neg, eps), evaluated left to right like the reference (grads.py:84,93)
+        const double r0 = __ddiv_rn(__dmul_rn(x[j].a, fmax(n0, 0.0)), fmax(d0, kEps));
+        const double r1 = __ddiv_rn(__dmul_rn(x[j].b, fmax(n1, 0.0)), fmax(d1, kEps));
+        st_pair(ep.out + row * ep.ldo + cbase + 8 * j, r0, r1, two[j]);
+      }
     } else if constexpr (KIND == DECOMP_EPI_KL_RATIO) {
-      Pair y = ld_pair(ep.other + row * ep.ldother + col, two);
-      if (ep.mask != nullptr) {
-        Pair m = ld_pair(ep.mask + row * ep.ldmask + col, two);
-        y.a *= m.a;
-        y.b *= m.b;
+      Pair y[NJ], m[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        const long long col = cbase + 8 * j;
+        y[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
+        if (ep.mask != nullptr) m[j] = ld_pair(ep.mask + row * ep.ldmask + col, two[j]);
       }
-      st_pair(ep.out + row * ep.ldo + col, y.a / (v0 + kEps), y.b / (v1 + kEps), two);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        if (ep.mask != nullptr) {
+          y[j].a *= m[j].a;
+          y[j].b *= m[j].b;
+        }
+        st_pair(ep.out + row * ep.ldo + cbase + 8 * j, y[j].a / (acc[j][0] + kEps), y[j].b / (acc[j][1] + kEps),
+                two[j]);
+      }
     } else if constexpr (KIND == DECOMP_EPI_PROX) {
       const double step = *ep.step;
-      Pair w = ld_pair(ep.x + row * ep.ldx + col, two);
-      Pair ya = ld_pair(ep.other + row * ep.ldother + col, two);
-      Pair xp = ld_pair(ep.prev + row * ep.ldprev + col, two);
       const double rowfac = ep.rowvec != nullptr ? ep.rowvec[row] : 1.0;
-      // z = w + step * (yAt - w.G)   (lasso.py:245-246)
-      double z0 = w.a + step * (ya.a - v0);
-      double z1 = w.b + step * (ya.b - v1);
-      double x0, x1;
+      Pair w[NJ], ya[NJ], xp[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        const long long col = cbase + 8 * j;
+        w[j] = ld_pair(ep.x + row * ep.ldx + col, two[j]);
+        ya[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
+        xp[j] = ld_pair(ep.prev + row * ep.ldprev + col, two[j]);
+      }
       bool bad = false;
-      if (ep.shrink == DECOMP_SHRINK_COMPLEX) {
-        const long long c = col >> 1;
-        double thr = ep.rowvec != nullptr ? step * (ep.colvec[c] * rowfac) : step * ep.colvec[c];
-        double r = hypot(z0, z1);
-        double den = r + kEps;
-        double mag = fmax(r - thr, 0.0);
-        x0 = mag * (z0 / den);
-        x1 = mag * (z1 / den);
-        if (ep.check) {
-          double d = hypot(x0 - xp.a, x1 - xp.b) - ep.colvec2[c];
-          bad = !(d < 0.0);
-        }
-      } else {
-        double a0 = ep.colvec[col], a1 = two ? ep.colvec[col + 1] : 0.0;
-        double t0 = ep.rowvec != nullptr ? step * (a0 * rowfac) : step * a0;
-        double t1 = ep.rowvec != nullptr ? step * (a1 * rowfac) : step * a1;
-        if (ep.shrink == DECOMP_SHRINK_POSITIVE) {
-          x0 = fmax(z0 - t0, 0.0);
-          x1 = fmax(z1 - t1, 0.0);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (!ok[j]) continue;
+        const long long col = cbase + 8 * j;
+        // z = w + step * (yAt - w.G)   (lasso.py:245-246)
+        const double z0 = w[j].a + step * (ya[j].a - acc[j][0]);
+        const double z1 = w[j].b + step * (ya[j].b - acc[j][1]);
+        // threshold step * alpha  (lasso.py:287; full mask: alpha carries the per-problem mask count, :163);
+        // the per-column vectors are a few kB and stay in L1
+        Pair thr, tol;
+        tol.a = tol.b = 0.0;
+        if (ep.shrink == DECOMP_SHRINK_COMPLEX) {
+          thr.a = thr.b = __ldg(ep.colvec + (col >> 1));
+          if (ep.check) tol.a = __ldg(ep.colvec2 + (col >> 1));
         } else {
-          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
-          double s0 = (z0 > 0.0) ? 1.0 : ((z0 < 0.0) ? -1.0 : z0);
-          double s1 = (z1 > 0.0) ? 1.0 : ((z1 < 0.0) ? -1.0 : z1);
-          x0 = fmax(fabs(z0) - t0, 0.0) * s0;
-          x1 = fmax(fabs(z1) - t1, 0.0) * s1;
-        }
-        if (ep.check) {
-          double d0 = fabs(x0 - xp.a) - ep.colvec2[col];
-          bad = !(d0 < 0.0);
-          if (two) {
-            double d1 = fabs(x1 - xp.b) - ep.colvec2[col + 1];
-            bad = bad || !(d1 < 0.0);
+          thr.a = __ldg(ep.colvec + col);
+          thr.b = two[j] ? __ldg(ep.colvec + col + 1) : 0.0;
+          if (ep.check) {
+            tol.a = __ldg(ep.colvec2 + col);
+            tol.b = two[j] ? __ldg(ep.colvec2 + col + 1) : 0.0;
           }
         }
-      }
-      st_pair(ep.out + row * ep.ldo + col, x0, x1, two);
-      if (ep.out2 != nullptr) {
-        // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
-        st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * (x0 - xp.a), x1 + ep.momentum * (x1 - xp.b), two);
+        const double t0 = ep.rowvec != nullptr ? step * (thr.a * rowfac) : step * thr.a;
+        const double t1 = ep.rowvec != nullptr ? step * (thr.b * rowfac) : step * thr.b;
+        double x0, x1;
+        if (ep.shrink == DECOMP_SHRINK_COMPLEX) {
+          const double r = hypot(z0, z1);
+          const double den = r + kEps;
+          const double mag = fmax(r - t0, 0.0);
+          x0 = mag * (z0 / den);
+          x1 = mag * (z1 / den);
+          if (ep.check) bad = bad || !(hypot(x0 - xp[j].a, x1 - xp[j].b) - tol.a < 0.0);
+        } else {
+          if (ep.shrink == DECOMP_SHRINK_POSITIVE) {
+            x0 = fmax(z0 - t0, 0.0);
+            x1 = fmax(z1 - t1, 0.0);
+          } else {
+            // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
+            const double s0 = (z0 > 0.0) ? 1.0 : ((z0 < 0.0) ? -1.0 : z0);
+            const double s1 = (z1 > 0.0) ? 1.0 : ((z1 < 0.0) ? -1.0 : z1);
+            x0 = fmax(fabs(z0) - t0, 0.0) * s0;
+            x1 = fmax(fabs(z1) - t1, 0.0) * s1;
+          }
+          if (ep.check) {
+            bad = bad || !(fabs(x0 - xp[j].a) - tol.a < 0.0);
+            if (two[j]) bad = bad || !(fabs(x1 - xp[j].b) - tol.b < 0.0);
+          }
+        }
+        st_pair(ep.out + row * ep.ldo + col, x0, x1, two[j]);
+        if (ep.out2 != nullptr) {
+          // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
+          st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * (x0 - xp[j].a),
+                  x1 + ep.momentum * (x1 - xp[j].b), two[j]);
+        }
       }
       return bad;
     }
@@ -307,17 +362,16 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < C::MI; ++i) {
       const long long row = rbase + 8 * i;
       if (row < gs.M) {
+        if constexpr (EPI == EPI_PARTIAL) {
 #pragma unroll
-        for (int j = 0; j < C::NJ; ++j) {
-          const long long col = cbase + 8 * j;
-          if (col < gs.N) {
-            const bool two = (col + 1 < gs.N);
-            if constexpr (EPI == EPI_PARTIAL) {
-              st_pair(partial + ((long long)z * gs.M + row) * gs.ld_partial + col, acc[i][j][0], acc[i][j][1], two);
-            } else {
-              violated |= Epilogue<EPI>::apply(ep, row, col, acc[i][j][0], acc[i][j][1], two);
-            }
+          for (int j = 0; j < C::NJ; ++j) {
+            const long long col = cbase + 8 * j;
+            if (col < gs.N)
+              st_pair(partial + ((long long)z * gs.M + row) * gs.ld_partial + col, acc[i][j][0], acc[i][j][1],
+                      col + 1 < gs.N);
           }
+        } else {
+          violated |= Epilogue<EPI, C::NJ>::row(ep, row, cbase, gs.N, acc[i]);
         }
       }
     }
