@@ -1,12 +1,23 @@
-// FP64 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor, 128-byte swizzle) feeds a
-// multi-stage shared-memory ring guarded by mbarriers; one producer warp issues the copies,
-// the consumer warps run DMMA.8x8x4 out of conflict-free swizzled LDS.64 reads and apply the
-// fused epilogue (MU ratio / mask / ISTA-FISTA proximal step) straight from registers.
+// FP64 tensor-core GEMM for sm_100a, persistent and warp-specialised:
+//
+//   * grid = (CTAs per SM) x (SM count); every CTA walks the tile list with stride gridDim.x
+//   * operand k-blocks stream through a shared-memory ring filled by TMA (cp.async.bulk.tensor, 128-byte
+//     swizzle) and guarded by full/empty mbarriers; one elected thread refills the stage that was consumed one
+//     k-block earlier, and the ring keeps running across tile boundaries, so the next tile's operands arrive
+//     while the current tile's epilogue is still executing.  There is deliberately no dedicated producer warp:
+//     4 warps per CTA x 2 CTAs = 2 warps per SM sub-partition leaves 255 registers per thread (a fifth warp
+//     would cap it at 168 and spill the 128 accumulator registers in the epilogue)
+//   * four warps run DMMA.8x8x4 out of conflict-free swizzled LDS.64 reads
+//   * epilogue: the accumulators are staged through a padded shared-memory buffer (half a tile at a time) and the
+//     consumer warps then sweep it row-contiguously (512-byte rows, 16 bytes per lane), loading the epilogue
+//     operands of four elements per thread before the first store; the fused update (MU ratio, mask, ISTA/FISTA
+//     proximal step + momentum + convergence test) runs in that sweep
+//   * two CTAs per SM, so one CTA's epilogue overlaps the other's mainloop on the DMMA pipe
 //
 //   NT: acc[m][n] = sum_k A[m][k] B[n][k]   both operands K-contiguous   (y.dot(d.T), x.dot(G), ...)
 //   TN: acc[m][n] = sum_k A[k][m] B[k][n]   both operands M/N-contiguous (x.T.dot(y), contraction over samples)
 //
-// Shared-memory layouts (BK = 16 doubles = one 128-byte swizzle row):
+// Shared-memory operand layouts (BK = 16 doubles = one 128-byte swizzle row):
 //   NT tile: [rows][16]      one TMA box {16, rows};            element (r, kk) at r*128 + (((kk>>1)^(r&7))<<4) + (kk&1)*8
 //   TN tile: [rows/16][16][16] one TMA box {16, 16} per 16 rows; element (kk, m) at (m>>4)*2048 + kk*128 +
 //                                                                 ((((m&15)>>1)^(kk&7))<<4) + (m&1)*8
@@ -23,6 +34,10 @@ namespace dcp {
 constexpr int BK = 16;
 constexpr double kEps = 1.0e-15;  // the reference's _JITTER
 
+// internal epilogue selectors (template arguments); the PROX kind of the ABI is split by shrink rule
+constexpr int EPI_PROX_REAL = 40, EPI_PROX_COMPLEX = 41, EPI_PROX_POSITIVE = 42;
+constexpr int EPI_PARTIAL = 100;  // TN split-K: raw partial tile into the workspace slab of this split
+
 struct GemmGeom {
   long long M, N, K;
   int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
@@ -34,17 +49,30 @@ struct GemmCfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int NCONS = WARPS_M * WARPS_N;
-  static constexpr int THREADS = (NCONS + 1) * 32;
+  static constexpr int CONS_THREADS = NCONS * 32;
+  static constexpr int THREADS = NCONS * 32;
   static constexpr int MI = WM / 8, NJ = WN / 8;
   static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  // epilogue staging: WM rows of the tile at a time, row pitch BN + 8 doubles (pitch = 64 bytes mod 128, so that
+  // the 8 rows x 64 bytes a warp stores per instruction fall into 4 conflict-free wavefronts)
+  static constexpr int EPI_ROWS = WM, EPI_PITCH = BN + 8;
+  static constexpr int EPI_BYTES = EPI_ROWS * EPI_PITCH * 8;
+  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 2 * STAGES * 8;
+  static constexpr int EPI_BATCH = 4;
+  static constexpr int EPI_PAIRS = EPI_ROWS * (BN / 2);
   static_assert(WM % 16 == 0 && WN % 16 == 0, "warp tile must be a multiple of 16 (TN sub-boxes)");
   static_assert(BM % 16 == 0 && BN % 16 == 0, "CTA tile must be a multiple of 16");
+  static_assert(EPI_PAIRS % (CONS_THREADS * EPI_BATCH) == 0, "epilogue sweep must divide evenly");
+  static_assert(RING_BYTES % 1024 == 0, "staging buffer must stay 16-byte aligned behind the ring");
 };
 
 // --------------------------------------------------------------------------------------------------
-// Epilogues.  Each handles the adjacent column pair (col, col+1) a lane owns in one 8x8 DMMA tile.
+// Epilogues.  Each handles the adjacent column pair (col, col+1); `two` is false for the last odd column.
+// load() only issues global loads, apply() computes and stores, so that a batch of loads is in flight
+// before the first store (operands may alias outputs -- in-place updates -- which forbids the compiler
+// from hoisting loads over stores by itself).
 // --------------------------------------------------------------------------------------------------
 struct Pair {
   double a, b;
@@ -71,149 +99,116 @@ __device__ __forceinline__ void st_pair(double* p, double a, double b, bool two)
   }
 }
 
-// Each epilogue processes one output row of a warp tile at a time: the NJ column pairs (col = cbase + 8 j,
-// col + 1) a lane owns in that row.  All global loads of the row are issued before the first store so that
-// they are in flight together (the operands may alias the outputs -- in-place updates -- so the compiler
-// cannot hoist loads over stores by itself).
-template <int KIND, int NJ>
+struct EpiIn {
+  Pair p0, p1, p2;
+  double rowfac;
+};
+
+template <int KIND>
 struct Epilogue {
-  // returns true if the convergence test is violated by any pair of this row (PROX with check only)
-  static __device__ __forceinline__ bool row(const decomp_epilogue_t& ep, long long row, long long cbase, long long N,
-                                             const double (&acc)[NJ][2]) {
-    bool ok[NJ], two[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      ok[j] = cbase + 8 * j < N;
-      two[j] = cbase + 8 * j + 1 < N;
-    }
-    if constexpr (KIND == DECOMP_EPI_STORE) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (ok[j]) st_pair(ep.out + row * ep.ldo + cbase + 8 * j, acc[j][0], acc[j][1], two[j]);
-    } else if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
-      Pair m[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        const long long col = cbase + 8 * j;
-        if (ep.cwidth == 2) {
-          m[j].a = m[j].b = ep.mask[row * ep.ldmask + (col >> 1)];
-        } else {
-          m[j] = ld_pair(ep.mask + row * ep.ldmask + col, two[j]);
-        }
+  static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
+
+  static __device__ __forceinline__ void load(const decomp_epilogue_t& ep, long long row, long long col, bool two,
+                                              EpiIn& in) {
+    if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
+      if (ep.cwidth == 2) {
+        in.p0.a = in.p0.b = ep.mask[row * ep.ldmask + (col >> 1)];
+      } else {
+        in.p0 = ld_pair(ep.mask + row * ep.ldmask + col, two);
       }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j)
-        if (ok[j]) st_pair(ep.out + row * ep.ldo + cbase + 8 * j, acc[j][0] * m[j].a, acc[j][1] * m[j].b, two[j]);
     } else if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
-      Pair x[NJ], o[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        const long long col = cbase + 8 * j;
-        x[j] = ld_pair(ep.x + row * ep.ldx + col, two[j]);
-        o[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        double n0, n1, d0, d1;
-        if constexpr (KIND == DECOMP_EPI_MU_NUM) {
-          n0 = acc[j][0]; n1 = acc[j][1]; d0 = o[j].a; d1 = o[j].b;
-        } else {
-          n0 = o[j].a; n1 = o[j].b; d0 = acc[j][0]; d1 = acc[j][1];
-        }
-        // x * max(pos, 0) / max(neg, eps), evaluated left to right like the reference (grads.py:84,93)
-        const double r0 = __ddiv_rn(__dmul_rn(x[j].a, fmax(n0, 0.0)), fmax(d0, kEps));
-        const double r1 = __ddiv_rn(__dmul_rn(x[j].b, fmax(n1, 0.0)), fmax(d1, kEps));
-        st_pair(ep.out + row * ep.ldo + cbase + 8 * j, r0, r1, two[j]);
-      }
+      in.p0 = ld_pair(ep.x + row * ep.ldx + col, two);
+      in.p1 = ld_pair(ep.other + row * ep.ldother + col, two);
     } else if constexpr (KIND == DECOMP_EPI_KL_RATIO) {
-      Pair y[NJ], m[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        const long long col = cbase + 8 * j;
-        y[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
-        if (ep.mask != nullptr) m[j] = ld_pair(ep.mask + row * ep.ldmask + col, two[j]);
+      in.p0 = ld_pair(ep.other + row * ep.ldother + col, two);
+      if (ep.mask != nullptr) in.p1 = ld_pair(ep.mask + row * ep.ldmask + col, two);
+    } else if constexpr (kProx) {
+      in.p0 = ld_pair(ep.x + row * ep.ldx + col, two);
+      in.p1 = ld_pair(ep.other + row * ep.ldother + col, two);
+      in.p2 = ld_pair(ep.prev + row * ep.ldprev + col, two);
+      in.rowfac = ep.rowvec != nullptr ? ep.rowvec[row] : 1.0;
+    }
+  }
+
+  // returns true if the convergence test is violated by this pair (PROX with check only)
+  static __device__ __forceinline__ bool apply(const decomp_epilogue_t& ep, double* __restrict__ pbase,
+                                               long long ldp, long long row, long long col, bool two, double v0,
+                                               double v1, const EpiIn& in, double step) {
+    if constexpr (KIND == EPI_PARTIAL) {
+      st_pair(pbase + row * ldp + col, v0, v1, two);
+    } else if constexpr (KIND == DECOMP_EPI_STORE) {
+      st_pair(ep.out + row * ep.ldo + col, v0, v1, two);
+    } else if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
+      st_pair(ep.out + row * ep.ldo + col, v0 * in.p0.a, v1 * in.p0.b, two);
+    } else if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
+      double n0, n1, d0, d1;
+      if constexpr (KIND == DECOMP_EPI_MU_NUM) {
+        n0 = v0; n1 = v1; d0 = in.p1.a; d1 = in.p1.b;
+      } else {
+        n0 = in.p1.a; n1 = in.p1.b; d0 = v0; d1 = v1;
       }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        if (ep.mask != nullptr) {
-          y[j].a *= m[j].a;
-          y[j].b *= m[j].b;
+      // x * max(pos, 0) / max(neg, eps), evaluated left to right like the reference (grads.py:84,93)
+      const double r0 = __ddiv_rn(__dmul_rn(in.p0.a, fmax(n0, 0.0)), fmax(d0, kEps));
+      const double r1 = __ddiv_rn(__dmul_rn(in.p0.b, fmax(n1, 0.0)), fmax(d1, kEps));
+      st_pair(ep.out + row * ep.ldo + col, r0, r1, two);
+    } else if constexpr (KIND == DECOMP_EPI_KL_RATIO) {
+      double y0 = in.p0.a, y1 = in.p0.b;
+      if (ep.mask != nullptr) {
+        y0 *= in.p1.a;
+        y1 *= in.p1.b;
+      }
+      st_pair(ep.out + row * ep.ldo + col, y0 / (v0 + kEps), y1 / (v1 + kEps), two);
+    } else if constexpr (kProx) {
+      // z = w + step * (yAt - w.G)   (lasso.py:245-246)
+      const double z0 = in.p0.a + step * (in.p1.a - v0);
+      const double z1 = in.p0.b + step * (in.p1.b - v1);
+      // threshold step * alpha (lasso.py:287); under a full mask alpha carries the per-problem mask count (:163).
+      // The per-column vectors are a few kB and stay in L1.
+      double a0, a1, tol0 = 0.0, tol1 = 0.0;
+      if constexpr (KIND == EPI_PROX_COMPLEX) {
+        a0 = a1 = __ldg(ep.colvec + (col >> 1));
+        if (ep.check) tol0 = __ldg(ep.colvec2 + (col >> 1));
+      } else {
+        a0 = __ldg(ep.colvec + col);
+        a1 = two ? __ldg(ep.colvec + col + 1) : 0.0;
+        if (ep.check) {
+          tol0 = __ldg(ep.colvec2 + col);
+          tol1 = two ? __ldg(ep.colvec2 + col + 1) : 0.0;
         }
-        st_pair(ep.out + row * ep.ldo + cbase + 8 * j, y[j].a / (acc[j][0] + kEps), y[j].b / (acc[j][1] + kEps),
-                two[j]);
       }
-    } else if constexpr (KIND == DECOMP_EPI_PROX) {
-      const double step = *ep.step;
-      const double rowfac = ep.rowvec != nullptr ? ep.rowvec[row] : 1.0;
-      Pair w[NJ], ya[NJ], xp[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        const long long col = cbase + 8 * j;
-        w[j] = ld_pair(ep.x + row * ep.ldx + col, two[j]);
-        ya[j] = ld_pair(ep.other + row * ep.ldother + col, two[j]);
-        xp[j] = ld_pair(ep.prev + row * ep.ldprev + col, two[j]);
-      }
+      const double t0 = ep.rowvec != nullptr ? step * (a0 * in.rowfac) : step * a0;
+      const double t1 = ep.rowvec != nullptr ? step * (a1 * in.rowfac) : step * a1;
+      double x0, x1;
       bool bad = false;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (!ok[j]) continue;
-        const long long col = cbase + 8 * j;
-        // z = w + step * (yAt - w.G)   (lasso.py:245-246)
-        const double z0 = w[j].a + step * (ya[j].a - acc[j][0]);
-        const double z1 = w[j].b + step * (ya[j].b - acc[j][1]);
-        // threshold step * alpha  (lasso.py:287; full mask: alpha carries the per-problem mask count, :163);
-        // the per-column vectors are a few kB and stay in L1
-        Pair thr, tol;
-        tol.a = tol.b = 0.0;
-        if (ep.shrink == DECOMP_SHRINK_COMPLEX) {
-          thr.a = thr.b = __ldg(ep.colvec + (col >> 1));
-          if (ep.check) tol.a = __ldg(ep.colvec2 + (col >> 1));
+      if constexpr (KIND == EPI_PROX_COMPLEX) {
+        // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
+        const double r = hypot(z0, z1);
+        const double den = r + kEps;
+        const double mag = fmax(r - t0, 0.0);
+        x0 = mag * (z0 / den);
+        x1 = mag * (z1 / den);
+        if (ep.check) bad = !(hypot(x0 - in.p2.a, x1 - in.p2.b) - tol0 < 0.0);
+      } else {
+        if constexpr (KIND == EPI_PROX_POSITIVE) {
+          x0 = fmax(z0 - t0, 0.0);   // lasso.py:228-241
+          x1 = fmax(z1 - t1, 0.0);
         } else {
-          thr.a = __ldg(ep.colvec + col);
-          thr.b = two[j] ? __ldg(ep.colvec + col + 1) : 0.0;
-          if (ep.check) {
-            tol.a = __ldg(ep.colvec2 + col);
-            tol.b = two[j] ? __ldg(ep.colvec2 + col + 1) : 0.0;
-          }
+          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
+          const double s0 = (z0 > 0.0) ? 1.0 : ((z0 < 0.0) ? -1.0 : z0);
+          const double s1 = (z1 > 0.0) ? 1.0 : ((z1 < 0.0) ? -1.0 : z1);
+          x0 = fmax(fabs(z0) - t0, 0.0) * s0;
+          x1 = fmax(fabs(z1) - t1, 0.0) * s1;
         }
-        const double t0 = ep.rowvec != nullptr ? step * (thr.a * rowfac) : step * thr.a;
-        const double t1 = ep.rowvec != nullptr ? step * (thr.b * rowfac) : step * thr.b;
-        double x0, x1;
-        if (ep.shrink == DECOMP_SHRINK_COMPLEX) {
-          const double r = hypot(z0, z1);
-          const double den = r + kEps;
-          const double mag = fmax(r - t0, 0.0);
-          x0 = mag * (z0 / den);
-          x1 = mag * (z1 / den);
-          if (ep.check) bad = bad || !(hypot(x0 - xp[j].a, x1 - xp[j].b) - tol.a < 0.0);
-        } else {
-          if (ep.shrink == DECOMP_SHRINK_POSITIVE) {
-            x0 = fmax(z0 - t0, 0.0);
-            x1 = fmax(z1 - t1, 0.0);
-          } else {
-            // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
-            const double s0 = (z0 > 0.0) ? 1.0 : ((z0 < 0.0) ? -1.0 : z0);
-            const double s1 = (z1 > 0.0) ? 1.0 : ((z1 < 0.0) ? -1.0 : z1);
-            x0 = fmax(fabs(z0) - t0, 0.0) * s0;
-            x1 = fmax(fabs(z1) - t1, 0.0) * s1;
-          }
-          if (ep.check) {
-            bad = bad || !(fabs(x0 - xp[j].a) - tol.a < 0.0);
-            if (two[j]) bad = bad || !(fabs(x1 - xp[j].b) - tol.b < 0.0);
-          }
+        if (ep.check) {
+          bad = !(fabs(x0 - in.p2.a) - tol0 < 0.0);
+          if (two) bad = bad || !(fabs(x1 - in.p2.b) - tol1 < 0.0);
         }
-        st_pair(ep.out + row * ep.ldo + col, x0, x1, two[j]);
-        if (ep.out2 != nullptr) {
-          // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
-          st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * (x0 - xp[j].a),
-                  x1 + ep.momentum * (x1 - xp[j].b), two[j]);
-        }
+      }
+      st_pair(ep.out + row * ep.ldo + col, x0, x1, two);
+      if (ep.out2 != nullptr) {
+        // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
+        st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * (x0 - in.p2.a), x1 + ep.momentum * (x1 - in.p2.b),
+                two);
       }
       return bad;
     }
@@ -221,7 +216,23 @@ struct Epilogue {
   }
 };
 
-constexpr int EPI_PARTIAL = 100;  // TN split-K: raw partial tile into the workspace slab of this split
+struct TileInfo {
+  int m0, n0, kb0, nkb, z;
+};
+
+__device__ __forceinline__ TileInfo tile_info(const GemmGeom& gs, int tiles_mn, int tile, int BM, int BN) {
+  TileInfo t;
+  const int tn = tile % gs.tiles_n;
+  const int tm = (tile / gs.tiles_n) % gs.tiles_m;
+  t.z = tile / tiles_mn;
+  t.m0 = tm * BM;
+  t.n0 = tn * BN;
+  t.kb0 = t.z * gs.kblocks_per_split;
+  t.nkb = gs.kblocks_total - t.kb0;
+  if (t.nkb > gs.kblocks_per_split) t.nkb = gs.kblocks_per_split;
+  if (t.nkb < 0) t.nkb = 0;
+  return t;
+}
 
 // --------------------------------------------------------------------------------------------------
 // The kernel
@@ -233,65 +244,97 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (skip_if != nullptr && *skip_if != 0) return;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  double* epi_buf = reinterpret_cast<double*>(smem + C::RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_mn = gs.tiles_m * gs.tiles_n;
+  const int tiles_total = tiles_mn * gs.splits;
+  const bool elected = threadIdx.x == 0;
 
-  int tile = blockIdx.x;
-  const int tn = tile % gs.tiles_n;
-  tile /= gs.tiles_n;
-  const int tm = tile % gs.tiles_m;
-  const int z = tile / gs.tiles_m;
-  const int m0 = tm * C::BM, n0 = tn * C::BN;
-  const int kb0 = z * gs.kblocks_per_split;
-  int nkb = gs.kblocks_total - kb0;
-  if (nkb > gs.kblocks_per_split) nkb = gs.kblocks_per_split;
-  if (nkb < 0) nkb = 0;
+  // ---- producer cursor (meaningful in the elected thread only): next k-block to request
+  int p_tile = blockIdx.x, p_i = 0, p_stage = 0;
+  uint32_t p_phase = 0;      // parity of the `empty` completion the next refill of p_stage has to wait for
+  bool p_wait = false;       // false while the ring is being filled for the first time
+  TileInfo p_t = tile_info(gs, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
 
-  if (threadIdx.x == 0) {
+  auto produce_one = [&]() {
+    // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
+    while (p_tile < tiles_total && p_i >= p_t.nkb) {
+      p_tile += gridDim.x;
+      p_i = 0;
+      if (p_tile < tiles_total) p_t = tile_info(gs, tiles_mn, p_tile, C::BM, C::BN);
+    }
+    if (p_tile >= tiles_total) return;
+    if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
+    mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
+    unsigned char* sa = smem + p_stage * C::STAGE_BYTES;
+    unsigned char* sb = sa + C::A_BYTES;
+    const int k0 = (p_t.kb0 + p_i) * BK;
+    if constexpr (!TN) {
+      tma_load_2d(sa, &tmA, &full_bar[p_stage], k0, p_t.m0);
+      tma_load_2d(sb, &tmB, &full_bar[p_stage], k0, p_t.n0);
+    } else {
+#pragma unroll
+      for (int b = 0; b < C::BM / 16; ++b) tma_load_2d(sa + b * 2048, &tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);
+#pragma unroll
+      for (int b = 0; b < C::BN / 16; ++b) tma_load_2d(sb + b * 2048, &tmB, &full_bar[p_stage], p_t.n0 + 16 * b, k0);
+    }
+    ++p_i;
+    if (++p_stage == C::STAGES) {
+      p_stage = 0;
+      if (p_wait) p_phase ^= 1u;
+      p_wait = true;
+    }
+  };
+
+  if (elected) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], C::NCONS);
     }
     fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
   }
   __syncthreads();
+  if (elected) {
+#pragma unroll 1
+    for (int s = 0; s < C::STAGES; ++s) produce_one();   // fill the ring
+  }
 
   bool violated = false;
+  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+  const int g = lane >> 2, q = lane & 3;
 
-  if (warp == C::NCONS) {
-    // ---------------------------------------------------------------- TMA producer (one lane)
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-        unsigned char* sa = smem + s * C::STAGE_BYTES;
-        unsigned char* sb = sa + C::A_BYTES;
-        const int k0 = (kb0 + i) * BK;
-        if constexpr (!TN) {
-          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
-          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
-        } else {
+  // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
+  int offA[4], offB[4];
+  if constexpr (!TN) {
 #pragma unroll
-          for (int b = 0; b < C::BM / 16; ++b) tma_load_2d(sa + b * 2048, &tmA, &full_bar[s], m0 + 16 * b, k0);
-#pragma unroll
-          for (int b = 0; b < C::BN / 16; ++b) tma_load_2d(sb + b * 2048, &tmB, &full_bar[s], n0 + 16 * b, k0);
-        }
-        if (++s == C::STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
+      offA[s4] = (wm * C::WM + g) * 128 + o;
+      offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
     }
   } else {
-    // ---------------------------------------------------------------- DMMA consumers
-    const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
-    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
+      // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
+      offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
+      offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
+    }
+  }
+  double step = 0.0;
+  if constexpr (Epilogue<EPI>::kProx) step = *ep.step;
+
+  int s = 0;
+  uint32_t ph = 0;
+  bool first = true;   // no refill after the very first k-block: the ring was filled STAGES deep
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
 
     double acc[C::MI][C::NJ][2];
 #pragma unroll
@@ -299,28 +342,8 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
-    int offA[4], offB[4];
-    if constexpr (!TN) {
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
-        offA[s4] = (wm * C::WM + g) * 128 + o;
-        offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
-      }
-    } else {
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
-        // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
-        offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-        offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-      }
-    }
-
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
+#pragma unroll 1
+    for (int it = 0; it < t.nkb; ++it) {
       mbar_wait(&full_bar[s], ph);
       const unsigned char* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
@@ -349,35 +372,58 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
+      // refill the stage consumed one k-block ago (prefetch distance STAGES - 1)
+      if (elected && !first) produce_one();
+      first = false;
       if (++s == C::STAGES) {
         s = 0;
         ph ^= 1u;
       }
     }
 
-    // ---------------------------------------------------------------- epilogue from registers
-    const long long rbase = (long long)m0 + wm * C::WM + g;
-    const long long cbase = (long long)n0 + wn * C::WN + 2 * q;
+    // -------------------------------------------------------------- epilogue through shared memory
+    double* pbase = nullptr;
+    if constexpr (EPI == EPI_PARTIAL) pbase = partial + (long long)t.z * gs.M * gs.ld_partial;
 #pragma unroll
-    for (int i = 0; i < C::MI; ++i) {
-      const long long row = rbase + 8 * i;
-      if (row < gs.M) {
-        if constexpr (EPI == EPI_PARTIAL) {
+    for (int h = 0; h < C::WARPS_M; ++h) {
+      __syncthreads();  // the previous sweep has finished reading the staging buffer
+      if (wm == h) {
 #pragma unroll
-          for (int j = 0; j < C::NJ; ++j) {
-            const long long col = cbase + 8 * j;
-            if (col < gs.N)
-              st_pair(partial + ((long long)z * gs.M + row) * gs.ld_partial + col, acc[i][j][0], acc[i][j][1],
-                      col + 1 < gs.N);
-          }
-        } else {
-          violated |= Epilogue<EPI, C::NJ>::row(ep, row, cbase, gs.N, acc[i]);
+        for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+          for (int j = 0; j < C::NJ; ++j)
+            *reinterpret_cast<double2*>(epi_buf + (g + 8 * i) * C::EPI_PITCH + wn * C::WN + 8 * j + 2 * q) =
+                make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+      __syncthreads();
+      const long long row0 = (long long)t.m0 + h * C::EPI_ROWS;
+#pragma unroll 1
+      for (int base = threadIdx.x; base < C::EPI_PAIRS; base += C::CONS_THREADS * C::EPI_BATCH) {
+        EpiIn in[C::EPI_BATCH];
+        double2 v[C::EPI_BATCH];
+        bool ok[C::EPI_BATCH], two[C::EPI_BATCH];
+        long long row[C::EPI_BATCH], col[C::EPI_BATCH];
+#pragma unroll
+        for (int b = 0; b < C::EPI_BATCH; ++b) {
+          const int p = base + b * C::CONS_THREADS;
+          const int r = p / (C::BN / 2), c2 = p % (C::BN / 2);
+          row[b] = row0 + r;
+          col[b] = (long long)t.n0 + 2 * c2;
+          ok[b] = row[b] < gs.M && col[b] < gs.N;
+          two[b] = col[b] + 1 < gs.N;
+          v[b] = *reinterpret_cast<const double2*>(epi_buf + r * C::EPI_PITCH + 2 * c2);
+          if (ok[b]) Epilogue<EPI>::load(ep, row[b], col[b], two[b], in[b]);
         }
+#pragma unroll
+        for (int b = 0; b < C::EPI_BATCH; ++b)
+          if (ok[b])
+            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row[b], col[b], two[b], v[b].x, v[b].y,
+                                             in[b], step);
       }
     }
   }
 
-  if constexpr (EPI == DECOMP_EPI_PROX) {
+  if constexpr (Epilogue<EPI>::kProx) {
     // convergence latch (lasso.py:293/409): the last CTA to finish decides for the whole batch
     if (ep.check) {
       const int any = __syncthreads_or(violated ? 1 : 0);

@@ -76,9 +76,9 @@ int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64
   return DECOMP_OK;
 }
 
-// CTA tile 128x64, four consumer warps of 64x32, 4-stage ring (96 KB) -> two CTAs per SM so that one CTA's
-// epilogue overlaps the other's mainloop.
-using CfgMain = GemmCfg<128, 64, 64, 32, 4, 2>;
+// CTA tile 128x64, four consumer warps of 64x32, 3-stage operand ring (72 KB) + 36 KB epilogue staging -> two
+// persistent CTAs per SM, so that one CTA's epilogue overlaps the other's mainloop.
+using CfgMain = GemmCfg<128, 64, 64, 32, 3, 2>;
 
 template <class C, bool TN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& gs, const decomp_epilogue_t& ep,
@@ -90,12 +90,15 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& 
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(gemm smem)");
     configured = true;
   }
-  const long long ctas = (long long)gs.tiles_m * gs.tiles_n * gs.splits;
-  if (ctas <= 0) return DECOMP_OK;
-  if (ctas > 2147483647LL) {
-    set_error("GEMM grid too large");
+  const long long tiles = (long long)gs.tiles_m * gs.tiles_n * gs.splits;
+  if (tiles <= 0) return DECOMP_OK;
+  if (tiles > 2147483647LL) {
+    set_error("GEMM tile count too large");
     return DECOMP_ERR_INVALID;
   }
+  // persistent grid: MINB CTAs per SM walk the tile list
+  long long ctas = (long long)num_sms() * C::MINB;
+  if (ctas > tiles) ctas = tiles;
   kern<<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, gs, ep, partial, skip_if);
   return check_cuda(cudaGetLastError(), "gemm launch");
 }
@@ -172,7 +175,17 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
         set_error("PROX epilogue with check needs latch and scratch");
         return DECOMP_ERR_INVALID;
       }
-      return launch<C, false, DECOMP_EPI_PROX>(ta, tb, gs, *epi, nullptr, skip_if, st);
+      switch (epi->shrink) {
+        case DECOMP_SHRINK_REAL:
+          return launch<C, false, EPI_PROX_REAL>(ta, tb, gs, *epi, nullptr, skip_if, st);
+        case DECOMP_SHRINK_COMPLEX:
+          return launch<C, false, EPI_PROX_COMPLEX>(ta, tb, gs, *epi, nullptr, skip_if, st);
+        case DECOMP_SHRINK_POSITIVE:
+          return launch<C, false, EPI_PROX_POSITIVE>(ta, tb, gs, *epi, nullptr, skip_if, st);
+        default:
+          set_error("decomp_gemm_nt_f64: unknown shrink kind %d", epi->shrink);
+          return DECOMP_ERR_INVALID;
+      }
     case DECOMP_EPI_KL_RATIO:
       return launch<C, false, DECOMP_EPI_KL_RATIO>(ta, tb, gs, *epi, nullptr, skip_if, st);
     default:
