@@ -65,6 +65,7 @@ struct GemmCfg {
   static_assert(WM % 16 == 0 && WN % 16 == 0, "warp tile must be a multiple of 16 (TN sub-boxes)");
   static_assert(BM % 16 == 0 && BN % 16 == 0, "CTA tile must be a multiple of 16");
   static_assert(EPI_PAIRS % (CONS_THREADS * EPI_BATCH) == 0, "epilogue sweep must divide evenly");
+  static_assert(BN / 2 == 32, "the epilogue sweep maps one warp to one staged row");
   static_assert(RING_BYTES % 1024 == 0, "staging buffer must stay 16-byte aligned behind the ring");
 };
 
@@ -107,6 +108,22 @@ struct EpiIn {
 template <int KIND>
 struct Epilogue {
   static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
+
+  // L2 prefetch of one tile row of the epilogue operands ([col, col + cols) of `row`), issued when the tile's
+  // mainloop starts so that the sweep after it finds them in L2
+  static __device__ __forceinline__ void prefetch_row(const decomp_epilogue_t& ep, long long row, long long col,
+                                                      int cols) {
+    const uint32_t bytes = (uint32_t)(cols & ~1) * 8u;
+    if (bytes == 0) return;
+    if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
+      bulk_prefetch_l2(ep.x + row * ep.ldx + col, bytes);
+      bulk_prefetch_l2(ep.other + row * ep.ldother + col, bytes);
+    } else if constexpr (kProx) {
+      bulk_prefetch_l2(ep.x + row * ep.ldx + col, bytes);
+      bulk_prefetch_l2(ep.other + row * ep.ldother + col, bytes);
+      bulk_prefetch_l2(ep.prev + row * ep.ldprev + col, bytes);
+    }
+  }
 
   static __device__ __forceinline__ void load(const decomp_epilogue_t& ep, long long row, long long col, bool two,
                                               EpiIn& in) {
@@ -336,6 +353,15 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
     const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
 
+    if constexpr (Epilogue<EPI>::kProx || EPI == DECOMP_EPI_MU_NUM || EPI == DECOMP_EPI_MU_DEN) {
+      static_assert(C::BM == C::THREADS, "one epilogue-operand row per thread");
+      const long long prow = (long long)t.m0 + threadIdx.x;
+      if (prow < gs.M) {
+        const long long rem = gs.N - t.n0;
+        Epilogue<EPI>::prefetch_row(ep, prow, t.n0, rem < C::BN ? (int)rem : C::BN);
+      }
+    }
+
     double acc[C::MI][C::NJ][2];
 #pragma unroll
     for (int i = 0; i < C::MI; ++i)
@@ -397,28 +423,40 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       __syncthreads();
       const long long row0 = (long long)t.m0 + h * C::EPI_ROWS;
+      // thread -> (row r_in + 4 e, column pair c2) of the staged half tile: a warp covers one 512-byte row
+      const int r_in = threadIdx.x >> 5, c2 = threadIdx.x & 31;
+      const long long col = (long long)t.n0 + 2 * c2;
+      constexpr int ROW_STEP = C::CONS_THREADS / (C::BN / 2);
+      const bool full = row0 + C::EPI_ROWS <= gs.M && (long long)t.n0 + C::BN <= gs.N;
+      if (full) {
+        // interior tile: no predicates, every load of a batch is issued before the first store
 #pragma unroll 1
-      for (int base = threadIdx.x; base < C::EPI_PAIRS; base += C::CONS_THREADS * C::EPI_BATCH) {
-        EpiIn in[C::EPI_BATCH];
-        double2 v[C::EPI_BATCH];
-        bool ok[C::EPI_BATCH], two[C::EPI_BATCH];
-        long long row[C::EPI_BATCH], col[C::EPI_BATCH];
+        for (int r = r_in; r < C::EPI_ROWS; r += ROW_STEP * C::EPI_BATCH) {
+          EpiIn in[C::EPI_BATCH];
+          double2 v[C::EPI_BATCH];
 #pragma unroll
-        for (int b = 0; b < C::EPI_BATCH; ++b) {
-          const int p = base + b * C::CONS_THREADS;
-          const int r = p / (C::BN / 2), c2 = p % (C::BN / 2);
-          row[b] = row0 + r;
-          col[b] = (long long)t.n0 + 2 * c2;
-          ok[b] = row[b] < gs.M && col[b] < gs.N;
-          two[b] = col[b] + 1 < gs.N;
-          v[b] = *reinterpret_cast<const double2*>(epi_buf + r * C::EPI_PITCH + 2 * c2);
-          if (ok[b]) Epilogue<EPI>::load(ep, row[b], col[b], two[b], in[b]);
+          for (int b = 0; b < C::EPI_BATCH; ++b) {
+            Epilogue<EPI>::load(ep, row0 + r + ROW_STEP * b, col, true, in[b]);
+            v[b] = *reinterpret_cast<const double2*>(epi_buf + (r + ROW_STEP * b) * C::EPI_PITCH + 2 * c2);
+          }
+#pragma unroll
+          for (int b = 0; b < C::EPI_BATCH; ++b)
+            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row0 + r + ROW_STEP * b, col, true, v[b].x,
+                                             v[b].y, in[b], step);
         }
-#pragma unroll
-        for (int b = 0; b < C::EPI_BATCH; ++b)
-          if (ok[b])
-            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row[b], col[b], two[b], v[b].x, v[b].y,
-                                             in[b], step);
+      } else {
+        // edge tile: rows beyond M / columns beyond N are masked off, an odd last column is handled alone
+        const bool col_ok = col < gs.N, two = col + 1 < gs.N;
+#pragma unroll 1
+        for (int r = r_in; r < C::EPI_ROWS; r += ROW_STEP) {
+          const long long row = row0 + r;
+          if (row < gs.M && col_ok) {
+            EpiIn in;
+            Epilogue<EPI>::load(ep, row, col, two, in);
+            const double2 v = *reinterpret_cast<const double2*>(epi_buf + r * C::EPI_PITCH + 2 * c2);
+            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row, col, two, v.x, v.y, in, step);
+          }
+        }
       }
     }
   }
