@@ -109,22 +109,6 @@ template <int KIND>
 struct Epilogue {
   static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
 
-  // L2 prefetch of one tile row of the epilogue operands ([col, col + cols) of `row`), issued when the tile's
-  // mainloop starts so that the sweep after it finds them in L2
-  static __device__ __forceinline__ void prefetch_row(const decomp_epilogue_t& ep, long long row, long long col,
-                                                      int cols) {
-    const uint32_t bytes = (uint32_t)(cols & ~1) * 8u;
-    if (bytes == 0) return;
-    if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
-      bulk_prefetch_l2(ep.x + row * ep.ldx + col, bytes);
-      bulk_prefetch_l2(ep.other + row * ep.ldother + col, bytes);
-    } else if constexpr (kProx) {
-      bulk_prefetch_l2(ep.x + row * ep.ldx + col, bytes);
-      bulk_prefetch_l2(ep.other + row * ep.ldother + col, bytes);
-      bulk_prefetch_l2(ep.prev + row * ep.ldprev + col, bytes);
-    }
-  }
-
   static __device__ __forceinline__ void load(const decomp_epilogue_t& ep, long long row, long long col, bool two,
                                               EpiIn& in) {
     if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
@@ -352,15 +336,6 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
     const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
-
-    if constexpr (Epilogue<EPI>::kProx || EPI == DECOMP_EPI_MU_NUM || EPI == DECOMP_EPI_MU_DEN) {
-      static_assert(C::BM == C::THREADS, "one epilogue-operand row per thread");
-      const long long prow = (long long)t.m0 + threadIdx.x;
-      if (prow < gs.M) {
-        const long long rem = gs.N - t.n0;
-        Epilogue<EPI>::prefetch_row(ep, prow, t.n0, rem < C::BN ? (int)rem : C::BN);
-      }
-    }
 
     double acc[C::MI][C::NJ][2];
 #pragma unroll

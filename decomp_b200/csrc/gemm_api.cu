@@ -1,6 +1,7 @@
 // C-ABI entry points of the FP64 GEMM family (see include/decomp_b200.h).
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -97,7 +98,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& 
     return DECOMP_ERR_INVALID;
   }
   // persistent grid: MINB CTAs per SM walk the tile list
-  long long ctas = (long long)num_sms() * C::MINB;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("DECOMP_GEMM_CTAS_PER_SM");   // tuning aid; default = the occupancy the kernel is built for
+    per_sm = (e != nullptr && atoi(e) > 0 && atoi(e) <= C::MINB) ? atoi(e) : C::MINB;
+  }
+  long long ctas = (long long)num_sms() * per_sm;
   if (ctas > tiles) ctas = tiles;
   kern<<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, gs, ep, partial, skip_if);
   return check_cuda(cudaGetLastError(), "gemm launch");
