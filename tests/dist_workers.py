@@ -1,0 +1,102 @@
+"""Worker functions for the multi-process tests (spawned by torch.multiprocessing)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _init(rank, world, port, backend):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    if backend == 'nccl':
+        torch.cuda.set_device(rank)
+        dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+
+
+def shard(a, rank, world):
+    """Contiguous row block of rank `rank` (the last rank takes the remainder)."""
+    n = a.shape[0]
+    per = n // world
+    lo = rank * per
+    hi = n if rank == world - 1 else lo + per
+    return a[lo:hi]
+
+
+# --------------------------------------------------------------------------------------- CPU / gloo
+def cpu_host_logic(rank, world, port, out):
+    """(1) padded-statistic all-reduce helper, (2) MIN-all-reduce convergence latch, (3) the exchange scheme of the
+    sharded NMF sweep (local x update, all-reduced x^T y and x^T x, replicated D update) equals the single-process
+    oracle."""
+    _init(rank, world, port, 'gloo')
+    from decomp_b200 import nmf
+    import golden_cases as gc
+    from oracle import decomp_oracle as orc
+    res = {}
+
+    base = torch.arange(24, dtype=torch.float64).reshape(4, 6) * (rank + 1)
+    view = base[:, :5]                                     # row-padded (non-contiguous) statistic
+    nmf._allreduce2d(view, dist.group.WORLD)
+    expect = torch.arange(24, dtype=torch.float64).reshape(4, 6)[:, :5] * sum(range(1, world + 1))
+    res['allreduce2d'] = bool(torch.equal(view, expect)) and float(base[0, 5]) == 5.0 * (rank + 1)
+
+    latch = torch.tensor([7 if rank == 0 else 0], dtype=torch.int32)
+    dist.all_reduce(latch, op=dist.ReduceOp.MIN)
+    both = torch.tensor([7], dtype=torch.int32)
+    dist.all_reduce(both, op=dist.ReduceOp.MIN)
+    res['latch'] = int(latch.item()) == 0 and int(both.item()) == 7
+
+    y, D0, _ = gc._nmf_data(203, 31, 5, 2)
+    yl = shard(y, rank, world)
+    D = orc.unit_rows(D0)
+    x = np.ones((yl.shape[0], D.shape[0]))
+    for _ in range(15):
+        G = D.dot(D.T)
+        x = x * np.maximum(yl.dot(D.T), 0.0) / np.maximum(x.dot(G), orc.EPS)
+        T = torch.from_numpy(x.T.dot(yl))
+        S = torch.from_numpy(x.T.dot(x))
+        dist.all_reduce(T)
+        dist.all_reduce(S)
+        D = orc.unit_rows(D * np.maximum(T.numpy(), 0.0) / np.maximum(S.numpy().dot(D), orc.EPS))
+    _, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=16)
+    res['nmf_D'] = float(np.max(np.abs(D - D_ref)) / np.max(np.abs(D_ref)))
+    res['nmf_x'] = float(np.max(np.abs(x - shard(x_ref, rank, world))) / np.max(np.abs(x_ref)))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------- GPU / nccl
+def gpu_sharded_solves(rank, world, port, out):
+    """Sharded NMF (unmasked, masked) and sharded Lasso (tol > 0: global convergence decision) against the oracle."""
+    _init(rank, world, port, 'nccl')
+    from decomp_b200 import lasso, nmf
+    import golden_cases as gc
+    from oracle import decomp_oracle as orc
+    res = {}
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    y, D0, mask = gc._nmf_data(1501, 130, 24, 5)
+    for name, m in (('nmf', None), ('nmf_mask', mask)):
+        it, D, x = nmf.solve(shard(y, rank, world), D0.copy(), tol=1e-4, maxiter=400,
+                             mask=None if m is None else shard(m, rank, world), group=dist.group.WORLD)
+        it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=1e-4, maxiter=400, mask=m)
+        res[name] = (it, it0, rel(D, D_ref), rel(x, shard(x_ref, rank, world)))
+
+    A, yl, maskl, _ = gc._lasso_data((901,), 24, 40, 3)
+    for name, m in (('lasso', None), ('lasso_mask', maskl)):
+        it, x = lasso.solve_fastpath(shard(yl, rank, world), A, 0.05, None, 1e-6, 1000, 'fista', None,
+                                     mask=None if m is None else shard(m, rank, world), group=dist.group.WORLD)
+        it0, x_ref = orc.lasso(yl, A, 0.05, tol=1e-6, method='fista', maxiter=1000, mask=m)
+        res[name] = (it, it0, rel(x, shard(x_ref, rank, world)))
+    out[rank] = res
+    dist.destroy_process_group()
