@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG, 'lib', 'libdecomp_b200.so')
 
 EPI_STORE, EPI_STORE_MASK, EPI_MU_NUM, EPI_MU_DEN, EPI_PROX, EPI_KL_RATIO = range(6)
 SHRINK_REAL, SHRINK_COMPLEX, SHRINK_POSITIVE = range(3)
+EPI_FLAG_COLVEC_IS_THRESHOLD = 1
 
 c_dp = ctypes.c_void_p
 c_i64 = ctypes.c_int64
@@ -32,7 +33,7 @@ class Epilogue(ctypes.Structure):
         ('colvec', c_dp), ('colvec2', c_dp), ('rowvec', c_dp), ('step', c_dp),
         ('momentum', ctypes.c_double),
         ('latch', c_dp), ('scratch', c_dp),
-        ('latch_value', c_i32), ('reserved', c_i32),
+        ('latch_value', c_i32), ('flags', c_i32),
     ]
 
 

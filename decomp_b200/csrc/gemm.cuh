@@ -1,18 +1,20 @@
 // FP64 tensor-core GEMM for sm_100a, persistent and warp-specialised:
 //
-//   * grid = (CTAs per SM) x (SM count); every CTA walks the tile list with stride gridDim.x
+//   * grid = one CTA per SM; every CTA walks the tile list with stride gridDim.x
+//   * 8 MMA warps (warp tile 32x32 of the 128x64 CTA tile) run DMMA.8x8x4 out of conflict-free swizzled
+//     LDS.64 reads.  Two MMA warps per SM sub-partition are what saturates the FP64 tensor pipe (one warp per
+//     sub-partition reaches ~71 % of it, measured)
 //   * operand k-blocks stream through a shared-memory ring filled by TMA (cp.async.bulk.tensor, 128-byte
-//     swizzle) and guarded by full/empty mbarriers; one elected thread refills the stage that was consumed one
-//     k-block earlier, and the ring keeps running across tile boundaries, so the next tile's operands arrive
-//     while the current tile's epilogue is still executing.  There is deliberately no dedicated producer warp:
-//     4 warps per CTA x 2 CTAs = 2 warps per SM sub-partition leaves 255 registers per thread (a fifth warp
-//     would cap it at 168 and spill the 128 accumulator registers in the epilogue)
-//   * four warps run DMMA.8x8x4 out of conflict-free swizzled LDS.64 reads
-//   * epilogue: the accumulators are staged through a padded shared-memory buffer (half a tile at a time) and the
-//     consumer warps then sweep it row-contiguously (512-byte rows, 16 bytes per lane), loading the epilogue
-//     operands of four elements per thread before the first store; the fused update (MU ratio, mask, ISTA/FISTA
-//     proximal step + momentum + convergence test) runs in that sweep
-//   * two CTAs per SM, so one CTA's epilogue overlaps the other's mainloop on the DMMA pipe
+//     swizzle) and guarded by full/empty mbarriers; one elected MMA thread refills the stage that was consumed
+//     one k-block earlier, and the ring keeps running across tile boundaries
+//   * 4 epilogue warps own all global-memory traffic of the fused update: when a tile's mainloop ends the MMA
+//     warps park the accumulators in one of two padded shared-memory staging buffers and immediately start the
+//     next tile; the epilogue warps sweep the staged tile row-contiguously (one warp = one 512-byte row, 16
+//     bytes per lane), issue all operand loads of a batch before its first store, and apply the fused update (MU
+//     ratio, mask, ISTA/FISTA proximal step + momentum + convergence test).  The memory-bound epilogue of tile t
+//     therefore runs under the DMMA mainloop of tile t+1 instead of stalling it
+//   * 12 warps = 3 per sub-partition -> 168 registers per thread: enough for the 64 accumulator registers of a
+//     32x32 warp tile and for the epilogue batches, no spills
 //
 //   NT: acc[m][n] = sum_k A[m][k] B[n][k]   both operands K-contiguous   (y.dot(d.T), x.dot(G), ...)
 //   TN: acc[m][n] = sum_k A[k][m] B[k][n]   both operands M/N-contiguous (x.T.dot(y), contraction over samples)
@@ -44,29 +46,30 @@ struct GemmGeom {
   long long ld_partial;  // TN: leading dimension of one partial slab (even)
 };
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int NBUF_, int EPI_WARPS_, int EPI_BATCH_>
 struct GemmCfg {
-  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, NBUF = NBUF_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
-  static constexpr int NCONS = WARPS_M * WARPS_N;
-  static constexpr int CONS_THREADS = NCONS * 32;
-  static constexpr int THREADS = NCONS * 32;
+  static constexpr int MMA_WARPS = WARPS_M * WARPS_N, EPI_WARPS = EPI_WARPS_;
+  static constexpr int MMA_THREADS = MMA_WARPS * 32, EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = MMA_THREADS + EPI_THREADS;
   static constexpr int MI = WM / 8, NJ = WN / 8;
   static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  // epilogue staging: WM rows of the tile at a time, row pitch BN + 8 doubles (pitch = 64 bytes mod 128, so that
-  // the 8 rows x 64 bytes a warp stores per instruction fall into 4 conflict-free wavefronts)
-  static constexpr int EPI_ROWS = WM, EPI_PITCH = BN + 8;
-  static constexpr int EPI_BYTES = EPI_ROWS * EPI_PITCH * 8;
-  static constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 2 * STAGES * 8;
-  static constexpr int EPI_BATCH = 4;
-  static constexpr int EPI_PAIRS = EPI_ROWS * (BN / 2);
+  // accumulator staging: whole tile, row pitch BN + 8 doubles (pitch = 64 bytes mod 128, so that the 8 rows x
+  // 64 bytes a warp stores per instruction fall into 4 conflict-free wavefronts)
+  static constexpr int EPI_PITCH = BN + 8;
+  static constexpr int BUF_BYTES = BM * EPI_PITCH * 8;
+  static constexpr int NUM_BARRIERS = 2 * STAGES + 2 * NBUF;
+  static constexpr int SMEM_BYTES = RING_BYTES + NBUF * BUF_BYTES + NUM_BARRIERS * 8;
+  static constexpr int EPI_BATCH = EPI_BATCH_;
+  static constexpr int ROW_STEP = EPI_THREADS / (BN / 2);      // rows covered by one pass of the epilogue warps
   static_assert(WM % 16 == 0 && WN % 16 == 0, "warp tile must be a multiple of 16 (TN sub-boxes)");
   static_assert(BM % 16 == 0 && BN % 16 == 0, "CTA tile must be a multiple of 16");
-  static_assert(EPI_PAIRS % (CONS_THREADS * EPI_BATCH) == 0, "epilogue sweep must divide evenly");
   static_assert(BN / 2 == 32, "the epilogue sweep maps one warp to one staged row");
-  static_assert(RING_BYTES % 1024 == 0, "staging buffer must stay 16-byte aligned behind the ring");
+  static_assert(BM % (ROW_STEP * EPI_BATCH) == 0, "epilogue sweep must divide evenly");
+  static_assert(RING_BYTES % 1024 == 0 && BUF_BYTES % 16 == 0, "staging buffers must stay 16-byte aligned");
 };
 
 // --------------------------------------------------------------------------------------------------
@@ -100,34 +103,57 @@ __device__ __forceinline__ void st_pair(double* p, double a, double b, bool two)
   }
 }
 
+// ---- bit-level helpers: the same results as the floating-point forms without touching the FP64 pipe
+// max(v, 0) that keeps NaN (like numpy's maximum): negative and not NaN  <=>  0x80000000 <= hi <= 0xfff00000
+__device__ __forceinline__ double max_zero(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  return (hi - 0x80000000u) <= 0x7ff00000u ? 0.0 : v;
+}
+// mag * sign(s) for mag >= 0 (or NaN): sign(0) = 0 gives 0 either way because mag is then max(-t, 0) = 0
+__device__ __forceinline__ double with_sign_of(double mag, double s) {
+  return __hiloint2double(__double2hiint(mag) | (__double2hiint(s) & 0x80000000), __double2loint(mag));
+}
+__device__ __forceinline__ unsigned long long abs_bits(double v) {
+  return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
 struct EpiIn {
   Pair p0, p1, p2;
-  double rowfac;
 };
+
+__device__ __forceinline__ Pair ld_pair16(const double* p) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  Pair r;
+  r.a = v.x;
+  r.b = v.y;
+  return r;
+}
 
 template <int KIND>
 struct Epilogue {
   static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
+  static constexpr bool kLoads = KIND != DECOMP_EPI_STORE && KIND != EPI_PARTIAL;
 
-  static __device__ __forceinline__ void load(const decomp_epilogue_t& ep, long long row, long long col, bool two,
-                                              EpiIn& in) {
+  // Issues the global loads of one column pair.  (row, col) has been clamped into the matrix by the caller, so
+  // the loads are unconditional 16-byte accesses (the even row pitch keeps an odd last column in bounds); what
+  // is out of range is discarded in apply().
+  static __device__ __forceinline__ void load(const decomp_epilogue_t& ep, long long row, long long col, EpiIn& in) {
     if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
       if (ep.cwidth == 2) {
         in.p0.a = in.p0.b = ep.mask[row * ep.ldmask + (col >> 1)];
       } else {
-        in.p0 = ld_pair(ep.mask + row * ep.ldmask + col, two);
+        in.p0 = ld_pair16(ep.mask + row * ep.ldmask + col);
       }
     } else if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
-      in.p0 = ld_pair(ep.x + row * ep.ldx + col, two);
-      in.p1 = ld_pair(ep.other + row * ep.ldother + col, two);
+      in.p0 = ld_pair16(ep.x + row * ep.ldx + col);
+      in.p1 = ld_pair16(ep.other + row * ep.ldother + col);
     } else if constexpr (KIND == DECOMP_EPI_KL_RATIO) {
-      in.p0 = ld_pair(ep.other + row * ep.ldother + col, two);
-      if (ep.mask != nullptr) in.p1 = ld_pair(ep.mask + row * ep.ldmask + col, two);
+      in.p0 = ld_pair16(ep.other + row * ep.ldother + col);
+      if (ep.mask != nullptr) in.p1 = ld_pair16(ep.mask + row * ep.ldmask + col);
     } else if constexpr (kProx) {
-      in.p0 = ld_pair(ep.x + row * ep.ldx + col, two);
-      in.p1 = ld_pair(ep.other + row * ep.ldother + col, two);
-      in.p2 = ld_pair(ep.prev + row * ep.ldprev + col, two);
-      in.rowfac = ep.rowvec != nullptr ? ep.rowvec[row] : 1.0;
+      in.p0 = ld_pair16(ep.x + row * ep.ldx + col);
+      in.p1 = ld_pair16(ep.other + row * ep.ldother + col);
+      in.p2 = ld_pair16(ep.prev + row * ep.ldprev + col);
     }
   }
 
@@ -160,56 +186,68 @@ struct Epilogue {
       }
       st_pair(ep.out + row * ep.ldo + col, y0 / (v0 + kEps), y1 / (v1 + kEps), two);
     } else if constexpr (kProx) {
+      // Scalar FP64 instructions share the DMMA pipe and cost the MMA warps a tensor slot each (measured: ~16
+      // pipe cycles per warp instruction while DMMAs are in flight), so this update is written with the
+      // minimum of them -- 5 per element: abs / max(.,0) / sign / the convergence comparison are bit operations.
       // z = w + step * (yAt - w.G)   (lasso.py:245-246)
       const double z0 = in.p0.a + step * (in.p1.a - v0);
       const double z1 = in.p0.b + step * (in.p1.b - v1);
-      // threshold step * alpha (lasso.py:287); under a full mask alpha carries the per-problem mask count (:163).
-      // The per-column vectors are a few kB and stay in L1.
-      double a0, a1, tol0 = 0.0, tol1 = 0.0;
+      // threshold step * alpha (lasso.py:287): colvec holds it ready-made (flag bit 0) or alpha, in which case
+      // it is formed here; under a full mask alpha carries the per-problem mask count (lasso.py:163).
+      double t0, t1;
+      unsigned long long tolb0 = 0ull, tolb1 = 0ull;
       if constexpr (KIND == EPI_PROX_COMPLEX) {
-        a0 = a1 = __ldg(ep.colvec + (col >> 1));
-        if (ep.check) tol0 = __ldg(ep.colvec2 + (col >> 1));
+        t0 = t1 = __ldg(ep.colvec + (col >> 1));
+        if (ep.check) tolb0 = (unsigned long long)__double_as_longlong(__ldg(ep.colvec2 + (col >> 1)));
       } else {
-        a0 = __ldg(ep.colvec + col);
-        a1 = two ? __ldg(ep.colvec + col + 1) : 0.0;
+        const double2 a = __ldg(reinterpret_cast<const double2*>(ep.colvec + col));   // colvec is padded to even
+        t0 = a.x;
+        t1 = a.y;
         if (ep.check) {
-          tol0 = __ldg(ep.colvec2 + col);
-          tol1 = two ? __ldg(ep.colvec2 + col + 1) : 0.0;
+          const double2 tl = __ldg(reinterpret_cast<const double2*>(ep.colvec2 + col));
+          tolb0 = (unsigned long long)__double_as_longlong(tl.x);
+          tolb1 = (unsigned long long)__double_as_longlong(tl.y);
         }
       }
-      const double t0 = ep.rowvec != nullptr ? step * (a0 * in.rowfac) : step * a0;
-      const double t1 = ep.rowvec != nullptr ? step * (a1 * in.rowfac) : step * a1;
-      double x0, x1;
+      if (ep.rowvec != nullptr) {
+        const double rowfac = __ldg(ep.rowvec + row);
+        t0 = step * (t0 * rowfac);
+        t1 = step * (t1 * rowfac);
+      } else if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) {
+        t0 = step * t0;
+        t1 = step * t1;
+      }
+      double x0, x1, d0, d1;
       bool bad = false;
       if constexpr (KIND == EPI_PROX_COMPLEX) {
         // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
         const double r = hypot(z0, z1);
         const double den = r + kEps;
-        const double mag = fmax(r - t0, 0.0);
+        const double mag = max_zero(r - t0);
         x0 = mag * (z0 / den);
         x1 = mag * (z1 / den);
-        if (ep.check) bad = !(hypot(x0 - in.p2.a, x1 - in.p2.b) - tol0 < 0.0);
+        d0 = x0 - in.p2.a;
+        d1 = x1 - in.p2.b;
+        if (ep.check) bad = !(abs_bits(hypot(d0, d1)) < tolb0);
       } else {
         if constexpr (KIND == EPI_PROX_POSITIVE) {
-          x0 = fmax(z0 - t0, 0.0);   // lasso.py:228-241
-          x1 = fmax(z1 - t1, 0.0);
+          x0 = max_zero(z0 - t0);   // lasso.py:228-241
+          x1 = max_zero(z1 - t1);
         } else {
-          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
-          const double s0 = (z0 > 0.0) ? 1.0 : ((z0 < 0.0) ? -1.0 : z0);
-          const double s1 = (z1 > 0.0) ? 1.0 : ((z1 < 0.0) ? -1.0 : z1);
-          x0 = fmax(fabs(z0) - t0, 0.0) * s0;
-          x1 = fmax(fabs(z1) - t1, 0.0) * s1;
+          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207); the product with +-1 / 0 is a sign transfer
+          x0 = with_sign_of(max_zero(fabs(z0) - t0), z0);
+          x1 = with_sign_of(max_zero(fabs(z1) - t1), z1);
         }
-        if (ep.check) {
-          bad = !(fabs(x0 - in.p2.a) - tol0 < 0.0);
-          if (two) bad = bad || !(fabs(x1 - in.p2.b) - tol1 < 0.0);
-        }
+        d0 = x0 - in.p2.a;
+        d1 = x1 - in.p2.b;
+        // |d| - tol < 0  <=>  |d| < tol; for non-negative doubles that is the order of their bit patterns, and a
+        // NaN compares "not smaller" exactly as in the reference's max(...) < 0
+        if (ep.check) bad = !(abs_bits(d0) < tolb0) || (two && !(abs_bits(d1) < tolb1));
       }
       st_pair(ep.out + row * ep.ldo + col, x0, x1, two);
       if (ep.out2 != nullptr) {
         // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
-        st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * (x0 - in.p2.a), x1 + ep.momentum * (x1 - in.p2.b),
-                two);
+        st_pair(ep.out2 + row * ep.ldo2 + col, x0 + ep.momentum * d0, x1 + ep.momentum * d1, two);
       }
       return bad;
     }
@@ -239,199 +277,246 @@ __device__ __forceinline__ TileInfo tile_info(const GemmGeom& gs, int tiles_mn, 
 // The kernel
 // --------------------------------------------------------------------------------------------------
 template <class C, bool TN, int EPI>
-__global__ void __launch_bounds__(C::THREADS, C::MINB)
+__global__ void __launch_bounds__(C::THREADS, 1)
 gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmGeom gs,
                 const decomp_epilogue_t ep, double* __restrict__ partial, const int* __restrict__ skip_if) {
   if (skip_if != nullptr && *skip_if != 0) return;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  double* epi_buf = reinterpret_cast<double*>(smem + C::RING_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES + C::EPI_BYTES);
+  double* stage_buf = reinterpret_cast<double*>(smem + C::RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES + C::NBUF * C::BUF_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* staged_bar = empty_bar + C::STAGES;    // MMA warps -> epilogue warps: accumulators parked
+  uint64_t* drained_bar = staged_bar + C::NBUF;    // epilogue warps -> MMA warps: staging buffer free again
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = gs.tiles_m * gs.tiles_n;
   const int tiles_total = tiles_mn * gs.splits;
-  const bool elected = threadIdx.x == 0;
 
-  // ---- producer cursor (meaningful in the elected thread only): next k-block to request
-  int p_tile = blockIdx.x, p_i = 0, p_stage = 0;
-  uint32_t p_phase = 0;      // parity of the `empty` completion the next refill of p_stage has to wait for
-  bool p_wait = false;       // false while the ring is being filled for the first time
-  TileInfo p_t = tile_info(gs, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
-
-  auto produce_one = [&]() {
-    // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
-    while (p_tile < tiles_total && p_i >= p_t.nkb) {
-      p_tile += gridDim.x;
-      p_i = 0;
-      if (p_tile < tiles_total) p_t = tile_info(gs, tiles_mn, p_tile, C::BM, C::BN);
-    }
-    if (p_tile >= tiles_total) return;
-    if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
-    mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
-    unsigned char* sa = smem + p_stage * C::STAGE_BYTES;
-    unsigned char* sb = sa + C::A_BYTES;
-    const int k0 = (p_t.kb0 + p_i) * BK;
-    if constexpr (!TN) {
-      tma_load_2d(sa, &tmA, &full_bar[p_stage], k0, p_t.m0);
-      tma_load_2d(sb, &tmB, &full_bar[p_stage], k0, p_t.n0);
-    } else {
-#pragma unroll
-      for (int b = 0; b < C::BM / 16; ++b) tma_load_2d(sa + b * 2048, &tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);
-#pragma unroll
-      for (int b = 0; b < C::BN / 16; ++b) tma_load_2d(sb + b * 2048, &tmB, &full_bar[p_stage], p_t.n0 + 16 * b, k0);
-    }
-    ++p_i;
-    if (++p_stage == C::STAGES) {
-      p_stage = 0;
-      if (p_wait) p_phase ^= 1u;
-      p_wait = true;
-    }
-  };
-
-  if (elected) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], C::NCONS);
+      mbar_init(&empty_bar[s], C::MMA_WARPS);
+    }
+    for (int b = 0; b < C::NBUF; ++b) {
+      mbar_init(&staged_bar[b], C::MMA_WARPS);
+      mbar_init(&drained_bar[b], C::EPI_WARPS);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   __syncthreads();
-  if (elected) {
-#pragma unroll 1
-    for (int s = 0; s < C::STAGES; ++s) produce_one();   // fill the ring
-  }
 
   bool violated = false;
-  const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
-  const int g = lane >> 2, q = lane & 3;
 
-  // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
-  int offA[4], offB[4];
-  if constexpr (!TN) {
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
-      offA[s4] = (wm * C::WM + g) * 128 + o;
-      offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
-    }
-  } else {
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-      const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
-      // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
-      offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-      offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-    }
-  }
-  double step = 0.0;
-  if constexpr (Epilogue<EPI>::kProx) step = *ep.step;
+  if (warp < C::MMA_WARPS) {
+    // ================================================================ MMA warps (+ elected TMA producer)
+    const bool elected = threadIdx.x == 0;
 
-  int s = 0;
-  uint32_t ph = 0;
-  bool first = true;   // no refill after the very first k-block: the ring was filled STAGES deep
+    // producer cursor (meaningful in the elected thread only): next k-block to request
+    int p_tile = blockIdx.x, p_i = 0, p_stage = 0;
+    uint32_t p_phase = 0;      // parity of the `empty` completion the next refill of p_stage has to wait for
+    bool p_wait = false;       // false while the ring is being filled for the first time
+    TileInfo p_t = tile_info(gs, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
+
+    auto produce_one = [&]() {
+      while (p_tile < tiles_total && p_i >= p_t.nkb) {
+        p_tile += gridDim.x;
+        p_i = 0;
+        if (p_tile < tiles_total) p_t = tile_info(gs, tiles_mn, p_tile, C::BM, C::BN);
+      }
+      if (p_tile >= tiles_total) return;
+      if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
+      mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
+      unsigned char* sa = smem + p_stage * C::STAGE_BYTES;
+      unsigned char* sb = sa + C::A_BYTES;
+      const int k0 = (p_t.kb0 + p_i) * BK;
+      if constexpr (!TN) {
+        tma_load_2d(sa, &tmA, &full_bar[p_stage], k0, p_t.m0);
+        tma_load_2d(sb, &tmB, &full_bar[p_stage], k0, p_t.n0);
+      } else {
+#pragma unroll
+        for (int b = 0; b < C::BM / 16; ++b)
+          tma_load_2d(sa + b * 2048, &tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);
+#pragma unroll
+        for (int b = 0; b < C::BN / 16; ++b)
+          tma_load_2d(sb + b * 2048, &tmB, &full_bar[p_stage], p_t.n0 + 16 * b, k0);
+      }
+      ++p_i;
+      if (++p_stage == C::STAGES) {
+        p_stage = 0;
+        if (p_wait) p_phase ^= 1u;
+        p_wait = true;
+      }
+    };
+
+    if (elected) {
 #pragma unroll 1
-  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-    const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
+      for (int s = 0; s < C::STAGES; ++s) produce_one();   // fill the ring
+    }
 
-    double acc[C::MI][C::NJ][2];
-#pragma unroll
-    for (int i = 0; i < C::MI; ++i)
-#pragma unroll
-      for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
+    const int g = lane >> 2, q = lane & 3;
 
-#pragma unroll 1
-    for (int it = 0; it < t.nkb; ++it) {
-      mbar_wait(&full_bar[s], ph);
-      const unsigned char* st = smem + s * C::STAGE_BYTES;
+    // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
+    int offA[4], offB[4];
+    if constexpr (!TN) {
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
-        double a[C::MI], b[C::NJ];
-        if constexpr (!TN) {
-#pragma unroll
-          for (int i = 0; i < C::MI; ++i) a[i] = *reinterpret_cast<const double*>(st + offA[s4] + i * 1024);
-#pragma unroll
-          for (int j = 0; j < C::NJ; ++j) b[j] = *reinterpret_cast<const double*>(st + offB[s4] + j * 1024);
-        } else {
-          const int kx = 2 * q + (s4 & 1);  // kk & 7
-#pragma unroll
-          for (int i = 0; i < C::MI; ++i)
-            a[i] = *reinterpret_cast<const double*>(st + offA[s4] + (i >> 1) * 2048 +
-                                                    (((4 * (i & 1) + (g >> 1)) ^ kx) << 4));
-#pragma unroll
-          for (int j = 0; j < C::NJ; ++j)
-            b[j] = *reinterpret_cast<const double*>(st + offB[s4] + (j >> 1) * 2048 +
-                                                    (((4 * (j & 1) + (g >> 1)) ^ kx) << 4));
-        }
-#pragma unroll
-        for (int i = 0; i < C::MI; ++i)
-#pragma unroll
-          for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
+        offA[s4] = (wm * C::WM + g) * 128 + o;
+        offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      // refill the stage consumed one k-block ago (prefetch distance STAGES - 1)
-      if (elected && !first) produce_one();
-      first = false;
-      if (++s == C::STAGES) {
-        s = 0;
-        ph ^= 1u;
+    } else {
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
+        // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
+        offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
+        offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
       }
     }
 
-    // -------------------------------------------------------------- epilogue through shared memory
-    double* pbase = nullptr;
-    if constexpr (EPI == EPI_PARTIAL) pbase = partial + (long long)t.z * gs.M * gs.ld_partial;
+    int s = 0;
+    uint32_t ph = 0;
+    bool first = true;   // no refill after the very first k-block: the ring was filled STAGES deep
+    int buf = 0;
+    uint32_t buf_phase = 0;   // parity of the `drained` completion to wait for before re-using `buf`
+    bool buf_wait = false;    // false until every staging buffer has been used once
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
+
+      double acc[C::MI][C::NJ][2];
 #pragma unroll
-    for (int h = 0; h < C::WARPS_M; ++h) {
-      __syncthreads();  // the previous sweep has finished reading the staging buffer
-      if (wm == h) {
+      for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-        for (int i = 0; i < C::MI; ++i)
+        for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll 1
+      for (int it = 0; it < t.nkb; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        const unsigned char* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < C::NJ; ++j)
-            *reinterpret_cast<double2*>(epi_buf + (g + 8 * i) * C::EPI_PITCH + wn * C::WN + 8 * j + 2 * q) =
-                make_double2(acc[i][j][0], acc[i][j][1]);
+        for (int s4 = 0; s4 < 4; ++s4) {
+          double a[C::MI], b[C::NJ];
+          if constexpr (!TN) {
+#pragma unroll
+            for (int i = 0; i < C::MI; ++i) a[i] = *reinterpret_cast<const double*>(st + offA[s4] + i * 1024);
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j) b[j] = *reinterpret_cast<const double*>(st + offB[s4] + j * 1024);
+          } else {
+            const int kx = 2 * q + (s4 & 1);  // kk & 7
+#pragma unroll
+            for (int i = 0; i < C::MI; ++i)
+              a[i] = *reinterpret_cast<const double*>(st + offA[s4] + (i >> 1) * 2048 +
+                                                      (((4 * (i & 1) + (g >> 1)) ^ kx) << 4));
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j)
+              b[j] = *reinterpret_cast<const double*>(st + offB[s4] + (j >> 1) * 2048 +
+                                                      (((4 * (j & 1) + (g >> 1)) ^ kx) << 4));
+          }
+#pragma unroll
+          for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        // refill the stage consumed one k-block ago (prefetch distance STAGES - 1)
+        if (elected && !first) produce_one();
+        first = false;
+        if (++s == C::STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      __syncthreads();
-      const long long row0 = (long long)t.m0 + h * C::EPI_ROWS;
-      // thread -> (row r_in + 4 e, column pair c2) of the staged half tile: a warp covers one 512-byte row
-      const int r_in = threadIdx.x >> 5, c2 = threadIdx.x & 31;
-      const long long col = (long long)t.n0 + 2 * c2;
-      constexpr int ROW_STEP = C::CONS_THREADS / (C::BN / 2);
-      const bool full = row0 + C::EPI_ROWS <= gs.M && (long long)t.n0 + C::BN <= gs.N;
-      if (full) {
-        // interior tile: no predicates, every load of a batch is issued before the first store
-#pragma unroll 1
-        for (int r = r_in; r < C::EPI_ROWS; r += ROW_STEP * C::EPI_BATCH) {
-          EpiIn in[C::EPI_BATCH];
-          double2 v[C::EPI_BATCH];
+
+      // park the accumulators for the epilogue warps and move on
+      if (buf_wait) mbar_wait(&drained_bar[buf], buf_phase);
+      double* sb = stage_buf + buf * (C::BUF_BYTES / 8);
 #pragma unroll
-          for (int b = 0; b < C::EPI_BATCH; ++b) {
-            Epilogue<EPI>::load(ep, row0 + r + ROW_STEP * b, col, true, in[b]);
-            v[b] = *reinterpret_cast<const double2*>(epi_buf + (r + ROW_STEP * b) * C::EPI_PITCH + 2 * c2);
-          }
+      for (int i = 0; i < C::MI; ++i)
 #pragma unroll
-          for (int b = 0; b < C::EPI_BATCH; ++b)
-            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row0 + r + ROW_STEP * b, col, true, v[b].x,
-                                             v[b].y, in[b], step);
+        for (int j = 0; j < C::NJ; ++j)
+          *reinterpret_cast<double2*>(sb + (wm * C::WM + g + 8 * i) * C::EPI_PITCH + wn * C::WN + 8 * j + 2 * q) =
+              make_double2(acc[i][j][0], acc[i][j][1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&staged_bar[buf]);   // release: the stores above are visible to the waiters
+      if (++buf == C::NBUF) {
+        buf = 0;
+        if (buf_wait) buf_phase ^= 1u;
+        buf_wait = true;
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps
+    // A tile is swept in BM / (ROW_STEP * EPI_BATCH) batches of EPI_BATCH column pairs per thread; all operand
+    // loads of a batch are issued before its first store.
+    const int e = threadIdx.x - C::MMA_THREADS;
+    const int r_in = e >> 5, c2 = e & 31;   // thread -> (row r_in + ROW_STEP j, column pair c2): a warp covers one row
+    constexpr int NBATCH = C::BM / (C::ROW_STEP * C::EPI_BATCH);
+    double step = 0.0;
+    if constexpr (Epilogue<EPI>::kProx) step = *ep.step;
+
+    struct Where {
+      long long row0, col, colc;   // first row of the tile, this thread's column, the column clamped into [0, N-2]
+      bool col_ok, two;
+    };
+    auto locate = [&](const TileInfo& t) {
+      Where w;
+      w.row0 = t.m0;
+      w.col = (long long)t.n0 + 2 * c2;
+      w.col_ok = w.col < gs.N;
+      w.two = w.col + 1 < gs.N;
+      long long cmax = (gs.N - 1) & ~1LL;    // last even column: a 16-byte load there stays inside the even pitch
+      w.colc = w.col < cmax ? w.col : cmax;
+      return w;
+    };
+    auto issue = [&](const Where& w, int batch, EpiIn (&in)[C::EPI_BATCH]) {
+      if constexpr (Epilogue<EPI>::kLoads) {
+#pragma unroll
+        for (int b = 0; b < C::EPI_BATCH; ++b) {
+          long long row = w.row0 + r_in + C::ROW_STEP * (batch * C::EPI_BATCH + b);
+          if (row > gs.M - 1) row = gs.M - 1;
+          Epilogue<EPI>::load(ep, row, w.colc, in[b]);
         }
-      } else {
-        // edge tile: rows beyond M / columns beyond N are masked off, an odd last column is handled alone
-        const bool col_ok = col < gs.N, two = col + 1 < gs.N;
+      }
+    };
+    auto finish = [&](const Where& w, int batch, const EpiIn (&in)[C::EPI_BATCH], const double* sb, double* pbase) {
+#pragma unroll
+      for (int b = 0; b < C::EPI_BATCH; ++b) {
+        const int r = r_in + C::ROW_STEP * (batch * C::EPI_BATCH + b);
+        const long long row = w.row0 + r;
+        const double2 v = *reinterpret_cast<const double2*>(sb + r * C::EPI_PITCH + 2 * c2);
+        if (row < gs.M && w.col_ok)
+          violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row, w.col, w.two, v.x, v.y, in[b], step);
+      }
+    };
+
+    int buf = 0;
+    uint32_t buf_phase = 0;
 #pragma unroll 1
-        for (int r = r_in; r < C::EPI_ROWS; r += ROW_STEP) {
-          const long long row = row0 + r;
-          if (row < gs.M && col_ok) {
-            EpiIn in;
-            Epilogue<EPI>::load(ep, row, col, two, in);
-            const double2 v = *reinterpret_cast<const double2*>(epi_buf + r * C::EPI_PITCH + 2 * c2);
-            violated |= Epilogue<EPI>::apply(ep, pbase, gs.ld_partial, row, col, two, v.x, v.y, in, step);
-          }
-        }
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
+      const Where w = locate(t);
+      double* pbase = nullptr;
+      if constexpr (EPI == EPI_PARTIAL) pbase = partial + (long long)t.z * gs.M * gs.ld_partial;
+      const double* sb = stage_buf + buf * (C::BUF_BYTES / 8);
+      EpiIn in[C::EPI_BATCH];
+      issue(w, 0, in);                                     // operand loads do not depend on the accumulators
+      mbar_wait(&staged_bar[buf], buf_phase);              // accumulators of this tile are parked
+#pragma unroll 1
+      for (int batch = 0; batch < NBATCH; ++batch) {
+        if (batch > 0) issue(w, batch, in);
+        finish(w, batch, in, sb, pbase);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&drained_bar[buf]);
+      if (++buf == C::NBUF) {
+        buf = 0;
+        buf_phase ^= 1u;
       }
     }
   }

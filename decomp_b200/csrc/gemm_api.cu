@@ -77,9 +77,9 @@ int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64
   return DECOMP_OK;
 }
 
-// CTA tile 128x64, four consumer warps of 64x32, 3-stage operand ring (72 KB) + 36 KB epilogue staging -> two
-// persistent CTAs per SM, so that one CTA's epilogue overlaps the other's mainloop.
-using CfgMain = GemmCfg<128, 64, 64, 32, 3, 2>;
+// CTA tile 128x64: 8 MMA warps of 32x32, 4 epilogue warps (batches of 4 column pairs per thread), 3-stage operand
+// ring (72 KB) + two 72 KB accumulator staging buffers = 216 KB -> one persistent CTA per SM.
+using CfgMain = GemmCfg<128, 64, 32, 32, 3, 2, 4, 4>;
 
 template <class C, bool TN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& gs, const decomp_epilogue_t& ep,
@@ -97,13 +97,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& 
     set_error("GEMM tile count too large");
     return DECOMP_ERR_INVALID;
   }
-  // persistent grid: MINB CTAs per SM walk the tile list
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    const char* e = getenv("DECOMP_GEMM_CTAS_PER_SM");   // tuning aid; default = the occupancy the kernel is built for
-    per_sm = (e != nullptr && atoi(e) > 0 && atoi(e) <= C::MINB) ? atoi(e) : C::MINB;
-  }
-  long long ctas = (long long)num_sms() * per_sm;
+  long long ctas = num_sms();   // persistent grid: one CTA per SM walks the tile list
   if (ctas > tiles) ctas = tiles;
   kern<<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, gs, ep, partial, skip_if);
   return check_cuda(cudaGetLastError(), "gemm launch");
@@ -118,11 +112,23 @@ static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
   gs->tiles_n = (int)((N + C::BN - 1) / C::BN);
   gs->kblocks_total = (int)((K + BK - 1) / BK);
   const long long tiles = (long long)gs->tiles_m * gs->tiles_n;
-  const long long target = (long long)num_sms() * C::MINB * 4;  // ~4 waves
-  long long splits = tiles > 0 ? (target + tiles - 1) / tiles : 1;
-  const long long max_splits = gs->kblocks_total / 8 > 0 ? gs->kblocks_total / 8 : 1;  // >= 128 rows per split
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // Split the contraction so that the persistent grid (one CTA per SM) is evenly loaded: minimise
+  //   rounds(tiles * splits) * (k-blocks per split + fixed cost of parking / writing one partial tile)
+  // over the split count; >= 128 rows (8 k-blocks) per split.
+  const long long sms = num_sms();
+  const long long max_splits = gs->kblocks_total / 8 > 0 ? gs->kblocks_total / 8 : 1;
+  long long splits = 1;
+  double best = 0.0;
+  for (long long cand = 1; cand <= max_splits && cand <= 4096; ++cand) {
+    const long long per = (gs->kblocks_total + cand - 1) / cand;
+    const long long real = (gs->kblocks_total + per - 1) / per;   // splits that actually get work
+    const long long rounds = (tiles * real + sms - 1) / sms;
+    const double cost = (double)rounds * ((double)per + 6.0);
+    if (cand == 1 || cost < best * 0.999) {
+      best = cost;
+      splits = cand;
+    }
+  }
   gs->kblocks_per_split = (int)((gs->kblocks_total + splits - 1) / splits);
   if (gs->kblocks_per_split < 1) gs->kblocks_per_split = 1;
   gs->splits = (gs->kblocks_total + gs->kblocks_per_split - 1) / gs->kblocks_per_split;

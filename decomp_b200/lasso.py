@@ -188,7 +188,9 @@ class LassoSolver(object):
         else:
             ops.gemm_nt(Anr, AH, ops.epilogue(ops.EPI_STORE, rview(G)))
         self.step = torch.empty(1, dtype=torch.float64, device=dev)
-        ops.gershgorin_step(rview(G), cplx, self.step)
+        # threshold step * alpha (lasso.py:287) is formed once here unless alpha is per problem (full mask)
+        self.thr = None if full_mask else ops.vector(k, dev)
+        ops.gershgorin_step(rview(G), cplx, self.step, alpha_scaled=self.alpha_vec, thr_out=self.thr)
         self.yAh = yAh = empty2d(B, k, cplx, dev)
         if full_mask:
             self.T = T = empty2d(B, f, cplx, dev)                  # also the per-iteration [B, f] temporary
@@ -215,7 +217,9 @@ class LassoSolver(object):
         W, cw, latch = self.W, self.cw, self.latch
         check = self.checks and i % 10 == 0
         epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
-                           other=rview(self.yAh), prev=rview(self.X), colvec=self.alpha_vec, colvec2=self.tol_vec,
+                           other=rview(self.yAh), prev=rview(self.X),
+                           colvec=self.alpha_vec if self.full_mask else self.thr, colvec2=self.tol_vec,
+                           flags=0 if self.full_mask else ops.EPI_FLAG_COLVEC_IS_THRESHOLD,
                            rowvec=self.rowvec, step=self.step, momentum=self.mom[i], shrink=self.shrink,
                            check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
         if self.full_mask:

@@ -135,7 +135,7 @@ class MuSolver(object):
             self.S = empty2d(k, k, False, dev)
         if kl and mask is None:
             self.ones_kf = full2d(k, f, 1.0, False, dev)
-            self.dsum = torch.empty(k, dtype=torch.float64, device=dev)
+            self.dsum = torch.empty(k + (k & 1), dtype=torch.float64, device=dev)[:k]   # even: 16-byte epilogue loads
             self.xsum = torch.empty(k, dtype=torch.float64, device=dev)
 
     def fired(self):

@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (EPI_KL_RATIO, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EPI_STORE_MASK,  # noqa: F401
+from ._lib import (EPI_FLAG_COLVEC_IS_THRESHOLD, EPI_KL_RATIO, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EPI_STORE_MASK,  # noqa: F401
                    SHRINK_COMPLEX, SHRINK_POSITIVE, SHRINK_REAL, Epilogue, ld, ptr, rview)
 from ._device import empty2d
 
@@ -36,7 +36,7 @@ def probe_dmma_tflops():
 
 def epilogue(kind, out, cwidth=1, **kw):
     """Build a decomp_epilogue_t. Keyword tensors: out2, x, other, prev, mask, colvec, colvec2, rowvec, step,
-    latch, scratch; scalars: shrink, check, momentum, latch_value."""
+    latch, scratch; scalars: shrink, check, momentum, latch_value, flags."""
     e = Epilogue()
     e.kind = kind
     e.cwidth = cwidth
@@ -55,6 +55,7 @@ def epilogue(kind, out, cwidth=1, **kw):
             setattr(e, name, t.data_ptr())
     e.momentum = float(kw.get('momentum', 0.0))
     e.latch_value = int(kw.get('latch_value', 0))
+    e.flags = int(kw.get('flags', 0))
     return e
 
 
@@ -157,6 +158,11 @@ def row_sums(A, scale_=1.0, out=None):
     return out
 
 
+def vector(k, device):
+    """[k] float64 vector whose storage is readable up to an even element count (16-byte epilogue loads)."""
+    return torch.zeros(k + (k & 1), dtype=torch.float64, device=device)[:k]
+
+
 def gershgorin_step(G, is_complex, step_out, alpha_scaled=None, thr_out=None):
     cw = 2 if is_complex else 1
     k = G.shape[0]
@@ -222,8 +228,8 @@ def dl_masked_update(S, T, D, D_out, is_complex, workspace):
 
 def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):
     k = s.numel()
-    alpha_out = torch.empty(k, dtype=torch.float64, device=s.device)
-    tol_out = torch.empty(k, dtype=torch.float64, device=s.device)
+    alpha_out = vector(k, s.device)
+    tol_out = vector(k, s.device)
     rc = _lib.lib().decomp_lasso_vectors_f64(_p(s), k, float(alpha), float(tol), float(mult), _p(mult_dev),
                                              _p(alpha_out), _p(tol_out), _lib.stream_ptr())
     _lib.check(rc, 'decomp_lasso_vectors_f64')

@@ -45,6 +45,8 @@ enum decomp_epilogue_kind {
   DECOMP_EPI_KL_RATIO = 5   /* out = other / (acc + eps) [* mask]       (grads.py:142-160) */
 };
 
+#define DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD 1 /* colvec holds step * alpha (lasso.py:287) ready-made */
+
 enum decomp_shrink_kind {
   DECOMP_SHRINK_REAL = 0,    /* lasso.py:192-207 */
   DECOMP_SHRINK_COMPLEX = 1, /* lasso.py:210-225, column pairs are (re, im) */
@@ -68,15 +70,16 @@ typedef struct decomp_epilogue {
   int64_t ldprev;
   const double* mask;        /* STORE_MASK / KL_RATIO: mask [M, N / cwidth] (may be NULL for KL) */
   int64_t ldmask;
-  const double* colvec;      /* PROX: threshold per column  step * alpha_k  [N / cwidth] */
-  const double* colvec2;     /* PROX: tolerance per column  tol * s_k        [N / cwidth] */
+  const double* colvec;      /* PROX: alpha_k per column [N / cwidth] (flags bit 0: already step * alpha_k);
+                                real data: 16-byte aligned and readable up to an even element count */
+  const double* colvec2;     /* PROX: tolerance per column  tol * s_k  [N / cwidth], same layout rule */
   const double* rowvec;      /* PROX (full mask): per-row factor sum_j mask[row, j]; NULL -> 1 */
   const double* step;        /* PROX: device scalar 1 / L */
   double momentum;           /* PROX: (beta - 1) / beta_next, or i / (i + 3), or 0 */
   int32_t* latch;            /* PROX+check: set to `latch_value` by the last CTA if converged */
   int32_t* scratch;          /* PROX+check: two int32 (violation flag, CTA ticket), zero-initialised */
   int32_t latch_value;
-  int32_t reserved;
+  int32_t flags;             /* DECOMP_EPI_FLAG_* */
 } decomp_epilogue_t;
 
 const char* decomp_last_error(void);

@@ -126,8 +126,9 @@ def test_gemm_nt_prox(kind, rowvec):
     rhs = ops.make_rhs(rv(dG), cplx, False)
     dw, dy, dxp = dev(w), dev(yAt), dev(xprev)
     xn, wn = dev(np.zeros_like(w)), dev(np.zeros_like(w))
-    dalpha = torch.from_numpy(alpha).cuda()
-    dtol = torch.from_numpy(tol).cuda()
+    dalpha, dtol = ops.vector(k, 'cuda'), ops.vector(k, 'cuda')     # readable up to an even element count
+    dalpha.copy_(torch.from_numpy(alpha))
+    dtol.copy_(torch.from_numpy(tol))
     drow = torch.from_numpy(rowfac).cuda() if rowvec else None
     dstep = torch.zeros(1, dtype=torch.float64, device='cuda')
     ops.gershgorin_step(rv(dG), cplx, dstep)
