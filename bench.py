@@ -281,7 +281,7 @@ def run_ours(args):
             'roofline': {'bound': 'tensor', 'achieved': flops_launch / t_launch / 1e12, 'peak': dmma_peak,
                          'unit': 'TFLOP/s', 'frac': flops_launch / t_launch / 1e12 / dmma_peak,
                          'traffic': args.traffic_fista,
-                         'kernel': 'gemm_f64_kernel<NT, PROX> (one launch per FISTA iteration)',
+                         'kernel': 'gemm_f64_proxq_kernel (fused GEMM + ISTA/FISTA update, one launch per iteration)',
                          'peak_source': 'FP64 tensor (DMMA.8x8x4) issue rate measured live by '
                                         'decomp_probe_dmma_tflops(); MEASURED_PEAKS.json has no FP64 entry',
                          'algorithmic_flops_per_launch': flops_launch,

@@ -11,7 +11,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, 'lib', 'libdecomp_b200.so')
 
-EPI_STORE, EPI_STORE_MASK, EPI_MU_NUM, EPI_MU_DEN, EPI_PROX, EPI_KL_RATIO = range(6)
+EPI_STORE, EPI_STORE_MASK, EPI_MU_NUM, EPI_MU_DEN, EPI_PROX, EPI_KL_RATIO, EPI_PROXQ = range(7)
 SHRINK_REAL, SHRINK_COMPLEX, SHRINK_POSITIVE = range(3)
 EPI_FLAG_COLVEC_IS_THRESHOLD = 1
 
@@ -66,6 +66,8 @@ def _declare(lib):
     lib.decomp_gather_rows_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_dp, c_i64, c_dp]
     lib.decomp_lasso_vectors_f64.argtypes = [c_dp, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp,
                                              c_dp, c_dp]
+    lib.decomp_lasso_q_f64.argtypes = [c_dp, c_i64, c_i64, c_i32, c_dp, c_dp, c_i64, c_dp]
+    lib.decomp_scale_scalar_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_dp]
     lib.decomp_mu_update_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp, c_dp]
     lib.decomp_max_abs_diff_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i32, ctypes.c_double, c_dp, c_i32,
                                             c_dp, c_dp, c_dp, c_dp]
@@ -83,7 +85,7 @@ EXPORTS = (
     'decomp_last_error', 'decomp_abi_version', 'decomp_probe_dmma_tflops', 'decomp_gemm_nt_f64', 'decomp_gemm_tn_workspace_bytes',
     'decomp_gemm_tn_f64', 'decomp_make_rhs_f64', 'decomp_row_norms_f64', 'decomp_scale_f64', 'decomp_mask_mul_f64',
     'decomp_col_sums_f64', 'decomp_row_sums_f64', 'decomp_gershgorin_step_f64', 'decomp_normalize_rows_f64',
-    'decomp_gather_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',
+    'decomp_gather_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_lasso_q_f64', 'decomp_scale_scalar_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',
     'decomp_dl_sweep_f64', 'decomp_dl_atom_weighted_f64', 'decomp_dl_masked_update_f64',
 )
 

@@ -274,7 +274,182 @@ __device__ __forceinline__ TileInfo tile_info(const GemmGeom& gs, int tiles_mn, 
 }
 
 // --------------------------------------------------------------------------------------------------
-// The kernel
+// Operand pipeline + DMMA mainloop of the 8 MMA warps, shared by both kernels below.
+// --------------------------------------------------------------------------------------------------
+template <class C, bool TN>
+struct MmaPipe {
+  const CUtensorMap* tmA;
+  const CUtensorMap* tmB;
+  const GemmGeom* gs;
+  unsigned char* smem;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  int tiles_mn, tiles_total;
+  bool elected;
+  int lane, wm, wn, g, q;
+  // producer cursor (meaningful in the elected thread only): next k-block to request
+  int p_tile, p_i, p_stage;
+  uint32_t p_phase;   // parity of the `empty` completion the next refill of p_stage has to wait for
+  bool p_wait;        // false while the ring is being filled for the first time
+  TileInfo p_t;
+  // consumer cursor
+  int s;
+  uint32_t ph;
+  bool first;         // no refill after the very first k-block: the ring was filled STAGES deep
+  int offA[4], offB[4];   // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
+
+  __device__ __forceinline__ void init(const CUtensorMap* a, const CUtensorMap* b, const GemmGeom* geom,
+                                       unsigned char* sm, uint64_t* full, uint64_t* empty) {
+    tmA = a;
+    tmB = b;
+    gs = geom;
+    smem = sm;
+    full_bar = full;
+    empty_bar = empty;
+    tiles_mn = geom->tiles_m * geom->tiles_n;
+    tiles_total = tiles_mn * geom->splits;
+    elected = threadIdx.x == 0;
+    const int warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31;
+    wm = warp / C::WARPS_N;
+    wn = warp % C::WARPS_N;
+    g = lane >> 2;
+    q = lane & 3;
+    p_tile = blockIdx.x;
+    p_i = 0;
+    p_stage = 0;
+    p_phase = 0;
+    p_wait = false;
+    p_t = tile_info(*geom, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
+    s = 0;
+    ph = 0;
+    first = true;
+    if constexpr (!TN) {
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
+        offA[s4] = (wm * C::WM + g) * 128 + o;
+        offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
+      }
+    } else {
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
+        // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
+        offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
+        offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
+      }
+    }
+  }
+
+  // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
+  __device__ __forceinline__ void produce_one() {
+    while (p_tile < tiles_total && p_i >= p_t.nkb) {
+      p_tile += gridDim.x;
+      p_i = 0;
+      if (p_tile < tiles_total) p_t = tile_info(*gs, tiles_mn, p_tile, C::BM, C::BN);
+    }
+    if (p_tile >= tiles_total) return;
+    if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
+    mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
+    unsigned char* sa = smem + p_stage * C::STAGE_BYTES;
+    unsigned char* sb = sa + C::A_BYTES;
+    const int k0 = (p_t.kb0 + p_i) * BK;
+    if constexpr (!TN) {
+      tma_load_2d(sa, tmA, &full_bar[p_stage], k0, p_t.m0);
+      tma_load_2d(sb, tmB, &full_bar[p_stage], k0, p_t.n0);
+    } else {
+#pragma unroll
+      for (int b = 0; b < C::BM / 16; ++b) tma_load_2d(sa + b * 2048, tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);
+#pragma unroll
+      for (int b = 0; b < C::BN / 16; ++b) tma_load_2d(sb + b * 2048, tmB, &full_bar[p_stage], p_t.n0 + 16 * b, k0);
+    }
+    ++p_i;
+    if (++p_stage == C::STAGES) {
+      p_stage = 0;
+      if (p_wait) p_phase ^= 1u;
+      p_wait = true;
+    }
+  }
+
+  __device__ __forceinline__ void fill_ring() {
+    if (elected) {
+#pragma unroll 1
+      for (int i = 0; i < C::STAGES; ++i) produce_one();
+    }
+  }
+
+  // acc = sum over the tile's k-blocks; refills the stage consumed one k-block ago (prefetch distance STAGES - 1).
+  // `hook(it)` runs in the elected thread after the refill of k-block `it` (used to trickle other TMA requests in
+  // between the operand refills instead of queueing them in front of the ring).
+  template <class Hook>
+  __device__ __forceinline__ void run(const TileInfo& t, double (&acc)[C::MI][C::NJ][2], Hook hook) {
+#pragma unroll
+    for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+      for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < t.nkb; ++it) {
+      mbar_wait(&full_bar[s], ph);
+      const unsigned char* st = smem + s * C::STAGE_BYTES;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        double a[C::MI], b[C::NJ];
+        if constexpr (!TN) {
+#pragma unroll
+          for (int i = 0; i < C::MI; ++i) a[i] = *reinterpret_cast<const double*>(st + offA[s4] + i * 1024);
+#pragma unroll
+          for (int j = 0; j < C::NJ; ++j) b[j] = *reinterpret_cast<const double*>(st + offB[s4] + j * 1024);
+        } else {
+          const int kx = 2 * q + (s4 & 1);  // kk & 7
+#pragma unroll
+          for (int i = 0; i < C::MI; ++i)
+            a[i] = *reinterpret_cast<const double*>(st + offA[s4] + (i >> 1) * 2048 +
+                                                    (((4 * (i & 1) + (g >> 1)) ^ kx) << 4));
+#pragma unroll
+          for (int j = 0; j < C::NJ; ++j)
+            b[j] = *reinterpret_cast<const double*>(st + offB[s4] + (j >> 1) * 2048 +
+                                                    (((4 * (j & 1) + (g >> 1)) ^ kx) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+          for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+      if (elected) {
+        if (!first) produce_one();
+        hook(it);
+      }
+      first = false;
+      if (++s == C::STAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+  }
+};
+
+// last-CTA-done convergence latch shared by both kernels (lasso.py:293/409): every thread passes its flag
+__device__ __forceinline__ void convergence_latch(const decomp_epilogue_t& ep, bool violated) {
+  const int any = __syncthreads_or(violated ? 1 : 0);
+  if (threadIdx.x == 0) {
+    if (any) atomicOr(&ep.scratch[0], 1);
+    __threadfence();
+    const int ticket = atomicAdd(&ep.scratch[1], 1);
+    if (ticket == (int)gridDim.x - 1) {
+      __threadfence();
+      const int v = atomicOr(&ep.scratch[0], 0);
+      if (v == 0) *ep.latch = ep.latch_value;
+      ep.scratch[0] = 0;
+      ep.scratch[1] = 0;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Generic kernel: 8 MMA warps + 4 epilogue warps, accumulators handed over through shared memory
 // --------------------------------------------------------------------------------------------------
 template <class C, bool TN, int EPI>
 __global__ void __launch_bounds__(C::THREADS, 1)
@@ -312,126 +487,19 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp < C::MMA_WARPS) {
     // ================================================================ MMA warps (+ elected TMA producer)
-    const bool elected = threadIdx.x == 0;
+    MmaPipe<C, TN> pipe;
+    pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
+    pipe.fill_ring();
+    const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
 
-    // producer cursor (meaningful in the elected thread only): next k-block to request
-    int p_tile = blockIdx.x, p_i = 0, p_stage = 0;
-    uint32_t p_phase = 0;      // parity of the `empty` completion the next refill of p_stage has to wait for
-    bool p_wait = false;       // false while the ring is being filled for the first time
-    TileInfo p_t = tile_info(gs, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
-
-    auto produce_one = [&]() {
-      while (p_tile < tiles_total && p_i >= p_t.nkb) {
-        p_tile += gridDim.x;
-        p_i = 0;
-        if (p_tile < tiles_total) p_t = tile_info(gs, tiles_mn, p_tile, C::BM, C::BN);
-      }
-      if (p_tile >= tiles_total) return;
-      if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
-      mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
-      unsigned char* sa = smem + p_stage * C::STAGE_BYTES;
-      unsigned char* sb = sa + C::A_BYTES;
-      const int k0 = (p_t.kb0 + p_i) * BK;
-      if constexpr (!TN) {
-        tma_load_2d(sa, &tmA, &full_bar[p_stage], k0, p_t.m0);
-        tma_load_2d(sb, &tmB, &full_bar[p_stage], k0, p_t.n0);
-      } else {
-#pragma unroll
-        for (int b = 0; b < C::BM / 16; ++b)
-          tma_load_2d(sa + b * 2048, &tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);
-#pragma unroll
-        for (int b = 0; b < C::BN / 16; ++b)
-          tma_load_2d(sb + b * 2048, &tmB, &full_bar[p_stage], p_t.n0 + 16 * b, k0);
-      }
-      ++p_i;
-      if (++p_stage == C::STAGES) {
-        p_stage = 0;
-        if (p_wait) p_phase ^= 1u;
-        p_wait = true;
-      }
-    };
-
-    if (elected) {
-#pragma unroll 1
-      for (int s = 0; s < C::STAGES; ++s) produce_one();   // fill the ring
-    }
-
-    const int wm = warp / C::WARPS_N, wn = warp % C::WARPS_N;
-    const int g = lane >> 2, q = lane & 3;
-
-    // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
-    int offA[4], offB[4];
-    if constexpr (!TN) {
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
-        offA[s4] = (wm * C::WM + g) * 128 + o;
-        offB[s4] = C::A_BYTES + (wn * C::WN + g) * 128 + o;
-      }
-    } else {
-#pragma unroll
-      for (int s4 = 0; s4 < 4; ++s4) {
-        const int kk = 2 * q + (s4 & 1) + 8 * (s4 >> 1);
-        // the (i & 1) dependent part of the swizzle is added in the loop (chunk = 4*(i&1) + (g>>1))
-        offA[s4] = (wm * C::WM / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-        offB[s4] = C::A_BYTES + (wn * C::WN / 16) * 2048 + kk * 128 + ((g & 1) << 3);
-      }
-    }
-
-    int s = 0;
-    uint32_t ph = 0;
-    bool first = true;   // no refill after the very first k-block: the ring was filled STAGES deep
     int buf = 0;
     uint32_t buf_phase = 0;   // parity of the `drained` completion to wait for before re-using `buf`
     bool buf_wait = false;    // false until every staging buffer has been used once
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
-
       double acc[C::MI][C::NJ][2];
-#pragma unroll
-      for (int i = 0; i < C::MI; ++i)
-#pragma unroll
-        for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-#pragma unroll 1
-      for (int it = 0; it < t.nkb; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        const unsigned char* st = smem + s * C::STAGE_BYTES;
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {
-          double a[C::MI], b[C::NJ];
-          if constexpr (!TN) {
-#pragma unroll
-            for (int i = 0; i < C::MI; ++i) a[i] = *reinterpret_cast<const double*>(st + offA[s4] + i * 1024);
-#pragma unroll
-            for (int j = 0; j < C::NJ; ++j) b[j] = *reinterpret_cast<const double*>(st + offB[s4] + j * 1024);
-          } else {
-            const int kx = 2 * q + (s4 & 1);  // kk & 7
-#pragma unroll
-            for (int i = 0; i < C::MI; ++i)
-              a[i] = *reinterpret_cast<const double*>(st + offA[s4] + (i >> 1) * 2048 +
-                                                      (((4 * (i & 1) + (g >> 1)) ^ kx) << 4));
-#pragma unroll
-            for (int j = 0; j < C::NJ; ++j)
-              b[j] = *reinterpret_cast<const double*>(st + offB[s4] + (j >> 1) * 2048 +
-                                                      (((4 * (j & 1) + (g >> 1)) ^ kx) << 4));
-          }
-#pragma unroll
-          for (int i = 0; i < C::MI; ++i)
-#pragma unroll
-            for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-        // refill the stage consumed one k-block ago (prefetch distance STAGES - 1)
-        if (elected && !first) produce_one();
-        first = false;
-        if (++s == C::STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
-      }
+      pipe.run(t, acc, [](int) {});
 
       // park the accumulators for the epilogue warps and move on
       if (buf_wait) mbar_wait(&drained_bar[buf], buf_phase);
@@ -522,23 +590,200 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   if constexpr (Epilogue<EPI>::kProx) {
-    // convergence latch (lasso.py:293/409): the last CTA to finish decides for the whole batch
-    if (ep.check) {
-      const int any = __syncthreads_or(violated ? 1 : 0);
-      if (threadIdx.x == 0) {
-        if (any) atomicOr(&ep.scratch[0], 1);
-        __threadfence();
-        const int ticket = atomicAdd(&ep.scratch[1], 1);
-        if (ticket == (int)gridDim.x - 1) {
-          __threadfence();
-          const int v = atomicOr(&ep.scratch[0], 0);
-          if (v == 0) *ep.latch = ep.latch_value;
-          ep.scratch[0] = 0;
-          ep.scratch[1] = 0;
+    if (ep.check) convergence_latch(ep, violated);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Unmasked ISTA / FISTA iteration in ONE launch, accumulators never leave the registers:
+//     z = c + w Q,   Q = I - G / L,  c = (y A^H) / L        (= w + (yAh - w G) / L, lasso.py:245-246)
+//     x_new = shrink(z, alpha / L);   w_next = x_new + momentum (x_new - x_prev)
+// 8 MMA warps, one CTA per SM.  The two epilogue operand tiles (c and x_prev, 64 KB each) are brought into
+// shared memory by TMA while the tile's mainloop runs (128-byte swizzle, so that the fragment-layout reads are
+// conflict free), and when the mainloop ends every warp updates its own 32x32 fragment and stores x_new and
+// w_next straight from registers.  All scalar FP64 work of a tile therefore happens in one short burst in which
+// no DMMA is in flight, instead of trickling through the shared FP64/DMMA pipe under the next tile's mainloop.
+// --------------------------------------------------------------------------------------------------
+template <class C>
+struct ProxqSmem {
+  static constexpr int OPND_BYTES = C::BM * C::BN * 8;
+  static constexpr int BOX_BYTES = C::BM * 128;          // one TMA box: BM rows x 16 doubles, 128-byte swizzle
+  static constexpr int SMEM_BYTES = C::RING_BYTES + 2 * OPND_BYTES + (2 * C::STAGES + 1) * 8;
+};
+
+template <class C, int EPI>
+__global__ void __launch_bounds__(C::MMA_THREADS, 1)
+gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
+                      const GemmGeom gs, const decomp_epilogue_t ep, const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;
+  using S = ProxqSmem<C>;
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* opnd_c = smem + C::RING_BYTES;
+  unsigned char* opnd_p = opnd_c + S::OPND_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(opnd_p + S::OPND_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* opnd_bar = empty_bar + C::STAGES;
+
+  const int tiles_mn = gs.tiles_m * gs.tiles_n;
+  const int tiles_total = tiles_mn * gs.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], C::MMA_WARPS);
+    }
+    mbar_init(opnd_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmP);
+  }
+  __syncthreads();
+
+  // The operand tiles of a tile are requested box by box (16 KB each) between the ring refills of that tile's own
+  // mainloop, so that they never queue in front of the GEMM operands (elected thread only).
+  constexpr int NBOX = C::BN / 16;
+  auto request_box = [&](const TileInfo& t, int b) {
+    if (b == 0) mbar_arrive_expect_tx(opnd_bar, 2 * S::OPND_BYTES);
+    if (b < NBOX) {
+      tma_load_2d(opnd_c + b * S::BOX_BYTES, &tmC, opnd_bar, t.n0 + 16 * b, t.m0);
+    } else {
+      tma_load_2d(opnd_p + (b - NBOX) * S::BOX_BYTES, &tmP, opnd_bar, t.n0 + 16 * (b - NBOX), t.m0);
+    }
+  };
+
+  MmaPipe<C, false> pipe;
+  pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
+  pipe.fill_ring();
+  const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
+
+  double step = 0.0;
+  if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) step = *ep.step;
+  bool violated = false;
+  uint32_t opnd_phase = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
+    double acc[C::MI][C::NJ][2];
+    // the previous tile's update has released the operand buffers (__syncthreads at the end of the loop body)
+    pipe.run(t, acc, [&](int it) {
+      if (it < 2 * NBOX) request_box(t, it);
+    });
+    if (pipe.elected) {
+      for (int b = t.nkb < 0 ? 0 : t.nkb; b < 2 * NBOX; ++b) request_box(t, b);   // short contractions: the rest
+    }
+
+    mbar_wait(opnd_bar, opnd_phase);
+    opnd_phase ^= 1u;
+
+    // per-column vectors of this lane's NJ column pairs: threshold step * alpha (lasso.py:287) and tolerance
+    // tol * s as bit patterns (lasso.py:130); columns beyond N get harmless zeros and are never stored
+    const long long col_lane = (long long)t.n0 + wn * C::WN + 2 * q;
+    double thr0[C::NJ], thr1[C::NJ];
+    unsigned long long tolb0[C::NJ], tolb1[C::NJ];
+#pragma unroll
+    for (int j = 0; j < C::NJ; ++j) {
+      const long long col = col_lane + 8 * j;
+      thr0[j] = thr1[j] = 0.0;
+      tolb0[j] = tolb1[j] = 0ull;
+      if (col < gs.N) {
+        if constexpr (EPI == EPI_PROX_COMPLEX) {
+          thr0[j] = thr1[j] = __ldg(ep.colvec + (col >> 1));
+          if (ep.check) tolb0[j] = (unsigned long long)__double_as_longlong(__ldg(ep.colvec2 + (col >> 1)));
+        } else {
+          const double2 a = __ldg(reinterpret_cast<const double2*>(ep.colvec + col));   // padded to even
+          thr0[j] = a.x;
+          thr1[j] = a.y;
+          if (ep.check) {
+            const double2 tl = __ldg(reinterpret_cast<const double2*>(ep.colvec2 + col));
+            tolb0[j] = (unsigned long long)__double_as_longlong(tl.x);
+            tolb1[j] = (unsigned long long)__double_as_longlong(tl.y);
+          }
+        }
+        if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) {
+          thr0[j] = step * thr0[j];
+          thr1[j] = step * thr1[j];
         }
       }
     }
+
+    // fragment walk: row r = wm*WM + g + 8 i (so r & 7 == g), column c = wn*WN + 8 j + 2 q inside the tile
+    const long long row_lane = (long long)t.m0 + wm * C::WM + g;
+    const int c_lane = wn * C::WN + 2 * q;
+    const unsigned char* sc = opnd_c + (wm * C::WM + g) * 128;
+    const unsigned char* sp = opnd_p + (wm * C::WM + g) * 128;
+    double* po = ep.out + row_lane * ep.ldo + col_lane;
+    double* pw = ep.out2 != nullptr ? ep.out2 + row_lane * ep.ldo2 + col_lane : nullptr;
+    const bool interior = (long long)t.m0 + C::BM <= gs.M && (long long)t.n0 + C::BN <= gs.N;
+    const double mom = ep.momentum;
+
+    auto update = [&](int i, int j, bool store, bool two) {
+      const int c = c_lane + 8 * j;
+      const int off = (c >> 4) * S::BOX_BYTES + i * 1024 + ((((c & 15) >> 1) ^ g) << 4);
+      const double2 cc = *reinterpret_cast<const double2*>(sc + off);
+      const double2 pp = *reinterpret_cast<const double2*>(sp + off);
+      const double z0 = acc[i][j][0] + cc.x;
+      const double z1 = acc[i][j][1] + cc.y;
+      double x0, x1, d0, d1;
+      bool bad = false;
+      if constexpr (EPI == EPI_PROX_COMPLEX) {
+        // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
+        const double rr = hypot(z0, z1);
+        const double den = rr + kEps;
+        const double mag = max_zero(rr - thr0[j]);
+        x0 = mag * (z0 / den);
+        x1 = mag * (z1 / den);
+        d0 = x0 - pp.x;
+        d1 = x1 - pp.y;
+        if (ep.check) bad = !(abs_bits(hypot(d0, d1)) < tolb0[j]);
+      } else {
+        if constexpr (EPI == EPI_PROX_POSITIVE) {
+          x0 = max_zero(z0 - thr0[j]);   // lasso.py:228-241
+          x1 = max_zero(z1 - thr1[j]);
+        } else {
+          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
+          x0 = with_sign_of(max_zero(fabs(z0) - thr0[j]), z0);
+          x1 = with_sign_of(max_zero(fabs(z1) - thr1[j]), z1);
+        }
+        d0 = x0 - pp.x;
+        d1 = x1 - pp.y;
+        if (ep.check) bad = !(abs_bits(d0) < tolb0[j]) || (two && !(abs_bits(d1) < tolb1[j]));
+      }
+      if (store) {
+        violated |= bad;
+        st_pair(po + 8 * j, x0, x1, two);
+        // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
+        if (pw != nullptr) st_pair(pw + 8 * j, x0 + mom * d0, x1 + mom * d1, two);
+      }
+    };
+
+    if (interior) {
+#pragma unroll
+      for (int i = 0; i < C::MI; ++i) {
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) update(i, j, true, true);
+        po += 8 * ep.ldo;
+        if (pw != nullptr) pw += 8 * ep.ldo2;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < C::MI; ++i) {
+        const bool row_ok = row_lane + 8 * i < gs.M;
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) {
+          const long long col = col_lane + 8 * j;
+          update(i, j, row_ok && col < gs.N, col + 1 < gs.N);
+        }
+        po += 8 * ep.ldo;
+        if (pw != nullptr) pw += 8 * ep.ldo2;
+      }
+    }
+    __syncthreads();   // every warp is done with the operand tiles before the next tile's requests overwrite them
   }
+  if (ep.check) convergence_latch(ep, violated);
 }
 
 // out = [beta * out +] sum_z partial[z]   (fixed summation order -> bitwise reproducible)

@@ -80,6 +80,8 @@ int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64
 // CTA tile 128x64: 8 MMA warps of 32x32, 4 epilogue warps (batches of 4 column pairs per thread), 3-stage operand
 // ring (72 KB) + two 72 KB accumulator staging buffers = 216 KB -> one persistent CTA per SM.
 using CfgMain = GemmCfg<128, 64, 32, 32, 3, 2, 4, 4>;
+// the fused ISTA/FISTA kernel has no accumulator staging: 4-stage ring (96 KB) + two 64 KB operand tiles
+using CfgProxq = GemmCfg<128, 64, 32, 32, 4, 2, 4, 4>;
 
 template <class C, bool TN, int EPI>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& gs, const decomp_epilogue_t& ep,
@@ -101,6 +103,24 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmGeom& 
   if (ctas > tiles) ctas = tiles;
   kern<<<(unsigned)ctas, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, gs, ep, partial, skip_if);
   return check_cuda(cudaGetLastError(), "gemm launch");
+}
+
+template <class C, int EPI>
+static int launch_proxq(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tp,
+                        const GemmGeom& gs, const decomp_epilogue_t& ep, const int32_t* skip_if, cudaStream_t stream) {
+  auto kern = gemm_f64_proxq_kernel<C, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ProxqSmem<C>::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(proxq smem)");
+    configured = true;
+  }
+  const long long tiles = (long long)gs.tiles_m * gs.tiles_n;
+  if (tiles <= 0) return DECOMP_OK;
+  long long ctas = num_sms();
+  if (ctas > tiles) ctas = tiles;
+  kern<<<(unsigned)ctas, C::MMA_THREADS, ProxqSmem<C>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, gs, ep, skip_if);
+  return check_cuda(cudaGetLastError(), "proxq launch");
 }
 
 static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
@@ -200,6 +220,33 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
       }
     case DECOMP_EPI_KL_RATIO:
       return launch<C, false, DECOMP_EPI_KL_RATIO>(ta, tb, gs, *epi, nullptr, skip_if, st);
+    case DECOMP_EPI_PROXQ: {
+      if (epi->check && (epi->latch == nullptr || epi->scratch == nullptr)) {
+        set_error("PROXQ epilogue with check needs latch and scratch");
+        return DECOMP_ERR_INVALID;
+      }
+      if (epi->other == nullptr || epi->prev == nullptr || epi->out == nullptr || epi->colvec == nullptr ||
+          (!(epi->flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD) && epi->step == nullptr)) {
+        set_error("PROXQ epilogue needs out, other, prev, colvec (and step unless colvec is the threshold)");
+        return DECOMP_ERR_INVALID;
+      }
+      CUtensorMap tc, tp;
+      rc = make_tensor_map(&tc, epi->other, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldother, 16, C::BM);
+      if (rc != DECOMP_OK) return rc;
+      rc = make_tensor_map(&tp, epi->prev, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldprev, 16, C::BM);
+      if (rc != DECOMP_OK) return rc;
+      switch (epi->shrink) {
+        case DECOMP_SHRINK_REAL:
+          return launch_proxq<CfgProxq, EPI_PROX_REAL>(ta, tb, tc, tp, gs, *epi, skip_if, st);
+        case DECOMP_SHRINK_COMPLEX:
+          return launch_proxq<CfgProxq, EPI_PROX_COMPLEX>(ta, tb, tc, tp, gs, *epi, skip_if, st);
+        case DECOMP_SHRINK_POSITIVE:
+          return launch_proxq<CfgProxq, EPI_PROX_POSITIVE>(ta, tb, tc, tp, gs, *epi, skip_if, st);
+        default:
+          set_error("decomp_gemm_nt_f64: unknown shrink kind %d", epi->shrink);
+          return DECOMP_ERR_INVALID;
+      }
+    }
     default:
       set_error("decomp_gemm_nt_f64: unknown epilogue kind %d", epi->kind);
       return DECOMP_ERR_INVALID;

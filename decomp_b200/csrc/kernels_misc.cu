@@ -351,6 +351,32 @@ __global__ void lasso_vectors_kernel(const double* __restrict__ s, int k, double
   }
 }
 
+// ------------------------------------------------------------------------------------ folded gradient step
+// Q = I - step * G (complex: interleaved pairs), the right-hand operand that turns  w + step * (yAh - w G)  into
+// step * yAh + w Q  (lasso.py:245-246 re-associated; exact in real arithmetic)
+__global__ void lasso_q_kernel(const double* __restrict__ G, long long ldg, int k, int cw,
+                               const double* __restrict__ step, double* __restrict__ Q, long long ldq) {
+  const double st = *step;
+  const long long total = (long long)k * k * cw;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long i = idx / (k * cw), c = idx % (k * cw);
+    const bool diag_re = (c == i * cw);
+    Q[i * ldq + c] = (diag_re ? 1.0 : 0.0) - st * G[i * ldg + c];
+  }
+}
+
+__global__ void scale_scalar_kernel(const double* __restrict__ A, long long lda, long long rows, long long cols,
+                                    const double* __restrict__ scalar, double* __restrict__ out, long long ldo) {
+  const double sc = *scalar;
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx % cols;
+    out[r * ldo + c] = sc * A[r * lda + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------ elementwise MU ratio
 // out = x * max(num, 0) / max(den, eps)                                (grads.py:84,93)
 __global__ void mu_update_kernel(const double* __restrict__ x, long long ldx, const double* __restrict__ num,
@@ -585,6 +611,24 @@ int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double to
   lasso_vectors_kernel<<<grid_for(k, 256), 256, 0, as_stream(stream)>>>(s, (int)k, alpha, tol, mult, mult_dev,
                                                                        alpha_out, tol_out);
   DCP_CHECK_LAUNCH("lasso_vectors");
+  return DECOMP_OK;
+}
+
+int decomp_lasso_q_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex, const double* step, double* Q,
+                       int64_t ldq, void* stream) {
+  if (k <= 0) return DECOMP_OK;
+  const int cw = is_complex ? 2 : 1;
+  lasso_q_kernel<<<grid_for(k * k * cw, 256), 256, 0, as_stream(stream)>>>(G, ldg, (int)k, cw, step, Q, ldq);
+  DCP_CHECK_LAUNCH("lasso_q");
+  return DECOMP_OK;
+}
+
+int decomp_scale_scalar_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, const double* scalar_dev,
+                            double* out, int64_t ldo, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  scale_scalar_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(A, lda, rows, cols, scalar_dev, out,
+                                                                                ldo);
+  DCP_CHECK_LAUNCH("scale_scalar");
   return DECOMP_OK;
 }
 

@@ -199,7 +199,11 @@ class LassoSolver(object):
             self.A_rhs = ops.make_rhs(Anr, cplx, False)            # NT operand of  w . A
         else:
             ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
-            self.G_rhs = ops.make_rhs(rview(G), cplx, False)       # NT operand of  w . G
+            # fold the gradient step into the operands:  w + (yAh - w G)/L  =  yAh/L + w (I - G/L)
+            Q = empty2d(k, k, cplx, dev)
+            ops.lasso_q(rview(G), cplx, self.step, rview(Q))
+            self.Q_rhs = ops.make_rhs(rview(Q), cplx, False)       # NT operand of  w . Q
+            ops.scale_scalar(rview(yAh), self.step, rview(yAh))    # yAh <- yAh / L
 
         # ---- iteration state
         self.checks = checks = tol > 0.0
@@ -216,18 +220,23 @@ class LassoSolver(object):
     def _launch(self, i, out_x):
         W, cw, latch = self.W, self.cw, self.latch
         check = self.checks and i % 10 == 0
+        if not self.full_mask:
+            epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), other=rview(self.yAh),
+                               prev=rview(self.X), colvec=self.thr, colvec2=self.tol_vec,
+                               flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, momentum=self.mom[i], shrink=self.shrink,
+                               check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
+            ops.gemm_nt(rview(W[i % 2]), self.Q_rhs, epi, skip=latch)
+            if check and self.group is not None:
+                torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            return
         epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
                            other=rview(self.yAh), prev=rview(self.X),
-                           colvec=self.alpha_vec if self.full_mask else self.thr, colvec2=self.tol_vec,
-                           flags=0 if self.full_mask else ops.EPI_FLAG_COLVEC_IS_THRESHOLD,
+                           colvec=self.alpha_vec, colvec2=self.tol_vec,
                            rowvec=self.rowvec, step=self.step, momentum=self.mom[i], shrink=self.shrink,
                            check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
-        if self.full_mask:
-            ops.gemm_nt(rview(W[i % 2]), self.A_rhs,
-                        ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
-            ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
-        else:
-            ops.gemm_nt(rview(W[i % 2]), self.G_rhs, epi, skip=latch)
+        ops.gemm_nt(rview(W[i % 2]), self.A_rhs,
+                    ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
+        ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
         if check and self.group is not None:
             # the latch fires only if every shard passed the test (reference: one max over the whole batch)
             torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)

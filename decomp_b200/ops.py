@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (EPI_FLAG_COLVEC_IS_THRESHOLD, EPI_KL_RATIO, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EPI_STORE_MASK,  # noqa: F401
+from ._lib import (EPI_FLAG_COLVEC_IS_THRESHOLD, EPI_KL_RATIO, EPI_PROXQ, EPI_MU_DEN, EPI_MU_NUM, EPI_PROX, EPI_STORE, EPI_STORE_MASK,  # noqa: F401
                    SHRINK_COMPLEX, SHRINK_POSITIVE, SHRINK_REAL, Epilogue, ld, ptr, rview)
 from ._device import empty2d
 
@@ -235,6 +235,25 @@ def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):
     _lib.check(rc, 'decomp_lasso_vectors_f64')
     _count(1)
     return alpha_out, tol_out
+
+
+def lasso_q(G, is_complex, step, Q):
+    """Q = I - step * G (real views of [k, k] matrices; step is a device scalar)."""
+    k = G.shape[0]
+    rc = _lib.lib().decomp_lasso_q_f64(_p(G), ld(G), k, int(is_complex), _p(step), _p(Q), ld(Q), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_lasso_q_f64')
+    _count(1)
+    return Q
+
+
+def scale_scalar(A, scalar_dev, out):
+    """out = scalar * A with the scalar read from device memory."""
+    rows, cols = A.shape
+    rc = _lib.lib().decomp_scale_scalar_f64(_p(A), ld(A), rows, cols, _p(scalar_dev), _p(out), ld(out),
+                                            _lib.stream_ptr())
+    _lib.check(rc, 'decomp_scale_scalar_f64')
+    _count(1)
+    return out
 
 
 def mu_update(x, num, den, out, skip=None):

@@ -42,7 +42,11 @@ enum decomp_epilogue_kind {
   DECOMP_EPI_MU_NUM = 2,    /* out = x * max(acc,0) / max(other,eps)    (grads.py:84,93: acc is the positive part) */
   DECOMP_EPI_MU_DEN = 3,    /* out = x * max(other,0) / max(acc,eps)    (acc is the negative part) */
   DECOMP_EPI_PROX = 4,      /* ISTA/FISTA step, see decomp_epilogue_t   (lasso.py:244-271, 405-414) */
-  DECOMP_EPI_KL_RATIO = 5   /* out = other / (acc + eps) [* mask]       (grads.py:142-160) */
+  DECOMP_EPI_KL_RATIO = 5,  /* out = other / (acc + eps) [* mask]       (grads.py:142-160) */
+  DECOMP_EPI_PROXQ = 6      /* unmasked ISTA/FISTA step with the gradient step folded into the GEMM operand:
+                               B = (I - G/L)^T, other = (y A^H)/L  ->  z = other + acc = w + (yAh - w G)/L, then as
+                               PROX.  Needs flags = DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD or `step`; `x` is unused;
+                               `other` and `prev` follow the GEMM operand alignment contract (TMA). */
 };
 
 #define DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD 1 /* colvec holds step * alpha (lasso.py:287) ready-made */
@@ -152,6 +156,12 @@ int decomp_gather_rows_f64(const double* in, int64_t ldi, const int64_t* index, 
  * device scalar mult_dev when that is non-NULL (sum of a 1-D mask)   (lasso.py:129-130, 136-138) */
 int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double tol, double mult, const double* mult_dev,
                              double* alpha_out, double* tol_out, void* stream);
+/* Q = I - (*step) * G for a [k,k] (complex: interleaved) Gram matrix and out = (*scalar_dev) * A: the operands of
+ * DECOMP_EPI_PROXQ, i.e. lasso.py:245-246  w + (yAh - w G)/L  written as  yAh/L + w (I - G/L). */
+int decomp_lasso_q_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex, const double* step, double* Q,
+                       int64_t ldq, void* stream);
+int decomp_scale_scalar_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, const double* scalar_dev,
+                            double* out, int64_t ldo, void* stream);
 /* out = x * max(num, 0) / max(den, eps), elementwise (masked D update, grads.py:93 with :122-125) */
 int decomp_mu_update_f64(const double* x, int64_t ldx, const double* num, int64_t ldn, const double* den, int64_t ldd,
                          int64_t rows, int64_t cols, double* out, int64_t ldo, const int32_t* skip_if, void* stream);

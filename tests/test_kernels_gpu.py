@@ -159,6 +159,69 @@ def test_gemm_nt_prox(kind, rowvec):
     assert float(xn.abs().max().item()) == 0.0
 
 
+@pytest.mark.parametrize('kind', ['real', 'positive', 'complex'])
+@pytest.mark.parametrize('Bn,k', [(203, 23), (1000, 96), (129, 5)])
+def test_gemm_nt_proxq(kind, Bn, k):
+    """The fused unmasked ISTA/FISTA launch: z = c + w Q with Q = I - step G, c = step yAh (lasso.py:245-246)."""
+    from decomp_b200 import ops
+    rng = np.random.RandomState(Bn + k)
+    cplx = kind == 'complex'
+    cw = 2 if cplx else 1
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    A = randn(k, k + 9)
+    G = A.dot(np.conj(A.T))
+    w, yAt, xprev = randn(Bn, k), randn(Bn, k) * 5, randn(Bn, k)
+    alpha = np.abs(rng.randn(k)) * 0.5
+    tol = np.full(k, 1e-3)
+    step = 1.0 / np.max(np.sum(np.abs(G), axis=0))
+    xn_ref, wn_ref, viol = _prox_ref(w, G, yAt, xprev, step, alpha, tol, 0.37, kind)
+
+    dG = dev(G)
+    dstep = torch.zeros(1, dtype=torch.float64, device='cuda')
+    dalpha, dtol, dthr = ops.vector(k, 'cuda'), ops.vector(k, 'cuda'), ops.vector(k, 'cuda')
+    dalpha.copy_(torch.from_numpy(alpha))
+    dtol.copy_(torch.from_numpy(tol))
+    ops.gershgorin_step(rv(dG), cplx, dstep, alpha_scaled=dalpha, thr_out=dthr)
+    Q = dev(np.zeros_like(G))
+    ops.lasso_q(rv(dG), cplx, dstep, rv(Q))
+    close(host(Q), np.eye(k) - step * G)
+    rhs = ops.make_rhs(rv(Q), cplx, False)
+    dc = dev(yAt)
+    ops.scale_scalar(rv(dc), dstep, rv(dc))
+    close(host(dc), step * yAt)
+    dw, dxp = dev(w), dev(xprev)
+    xn, wn = dev(np.zeros_like(w)), dev(np.zeros_like(w))
+    latch = torch.zeros(1, dtype=torch.int32, device='cuda')
+    scratch = torch.zeros(2, dtype=torch.int32, device='cuda')
+    shrink = {'real': ops.SHRINK_REAL, 'positive': ops.SHRINK_POSITIVE, 'complex': ops.SHRINK_COMPLEX}[kind]
+
+    def epi(out, prev, momentum):
+        return ops.epilogue(ops.EPI_PROXQ, rv(out), cwidth=cw, out2=rv(wn), other=rv(dc), prev=rv(prev), colvec=dthr,
+                            colvec2=dtol, flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, momentum=momentum, shrink=shrink,
+                            check=True, latch=latch, scratch=scratch, latch_value=7)
+
+    ops.gemm_nt(rv(dw), rhs, epi(xn, dxp, 0.37))
+    torch.cuda.synchronize()
+    close(host(xn), xn_ref, 1e-11)
+    close(host(wn), wn_ref, 1e-11)
+    assert viol and int(latch.item()) == 0 and scratch.tolist() == [0, 0]
+    # in place on the previous iterate (how the solver runs it), then the converged case fires the latch
+    dxp_inplace = dev(xprev)
+    ops.gemm_nt(rv(dw), rhs, epi(dxp_inplace, dxp_inplace, 0.37))
+    close(host(dxp_inplace), xn_ref, 1e-11)
+    dxp2 = dev(host(xn))
+    ops.gemm_nt(rv(dw), rhs, epi(xn, dxp2, 0.0))
+    torch.cuda.synchronize()
+    assert int(latch.item()) == 7
+    xn.zero_()
+    ops.gemm_nt(rv(dw), rhs, epi(xn, dxp2, 0.0), skip=latch)
+    torch.cuda.synchronize()
+    assert float(xn.abs().max().item()) == 0.0
+
+
 @pytest.mark.parametrize('K,M,N', [(1, 1, 1), (37, 5, 9), (5000, 20, 200), (4099, 130, 70), (20000, 256, 64)])
 def test_gemm_tn(K, M, N):
     from decomp_b200 import ops

@@ -30,6 +30,8 @@ cases = {
  'PROX x=A operand (as FISTA)': E(ops.EPI_PROX, out, out2=out2, x=A, other=other, prev=prev, colvec=colvec, colvec2=colvec, step=step, momentum=0.3),
  'PROX in place (out=prev)': E(ops.EPI_PROX, prev, out2=out2, x=A, other=other, prev=prev, colvec=colvec, colvec2=colvec, step=step, momentum=0.3),
 }
+thr = ops.vector(N, dev); thr.copy_(colvec * 0.1)
+cases['PROXQ (2 TMA tiles, 2 st)'] = E(ops.EPI_PROXQ, prev, out2=out2, other=other, prev=prev, colvec=thr, colvec2=colvec, flags=1, momentum=0.3)
 for name, epi in cases.items():
     ms = timeit(lambda: ops.gemm_nt(A, B, epi))
     print('%-32s %.3f ms' % (name, ms))
