@@ -8,4 +8,4 @@ arithmetic runs in hand-written CUDA kernels reached through the C ABI of
 __version__ = '0.1.0'
 
 from . import utils  # noqa: F401,E402
-from . import lasso, nmf, dictionary_learning  # noqa: F401,E402
+from . import lasso, nmf, dictionary_learning, nnls  # noqa: F401,E402

@@ -165,3 +165,10 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in src.replace('the numpy oracle', ''), os.path.join(dirpath, f)
+
+
+def test_nnls_wrapper_keeps_the_reference_quirk():
+    from decomp_b200 import nnls
+    rng = np.random.RandomState(0)
+    with pytest.raises(ValueError):
+        nnls.solve(rng.randn(11, 10), rng.randn(5, 10), 0.1)          # default 'ista_pos' -> 'ista_pos_pos'

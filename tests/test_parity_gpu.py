@@ -168,3 +168,13 @@ def test_inputs_are_not_mutated():
     nmf.solve(y, D, x=x0, tol=0.0, maxiter=5, mask=mask)
     assert np.array_equal(y, case['y']) and np.array_equal(D, case['D']) and np.array_equal(mask, case['mask'])
     assert np.array_equal(x0, np.ones_like(x0))
+
+
+def test_nnls_wrapper():
+    """decomp/nnls.py:4-7 appends '_pos'; equals the golden of lasso.solve(method='fista_pos')."""
+    from decomp_b200 import nnls
+    case = gc.lasso_cases()['pmat_fista_pos_nomask']
+    g = load('lasso_pmat_fista_pos_nomask')
+    it, x = nnls.solve(case['y'], case['A'], case['alpha'], tol=case['tol'], method='fista', maxiter=case['maxiter'])
+    assert it == int(g['it'])
+    assert_close(x, g['x'], what='x')
