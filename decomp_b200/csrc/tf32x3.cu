@@ -1,0 +1,445 @@
+// TF32-split ("3xTF32") path of the unmasked ISTA/FISTA iteration on the 5th-generation tensor cores.
+//
+//   z = c + w Q           w = w_hi + w_lo, Q = Q_hi + Q_lo   (TF32 pieces: 11 + 11 significant bits)
+//   w Q ~= w_lo Q_hi + w_hi Q_lo + w_hi Q_hi                  (three tcgen05.mma kind::tf32 per k-step, FP32
+//                                                              accumulators in tensor memory)
+//
+// Kernel 1, tf32x3_gemm_kernel: warp-specialised, persistent, one CTA per SM.
+//   warp 0   TMA producer: per 32-wide k-block the [128, 32] tiles of w_hi / w_lo and the [N, 32] tiles of Q_hi /
+//            Q_lo (FP32 in memory, already TF32-valued) land in shared memory in the 128-byte-swizzled K-major
+//            layout that the UMMA shared-memory descriptors describe (2-stage ring, mbarrier full/empty)
+//   warp 1   MMA issuer: one elected thread issues 3 x 4 tcgen05.mma (M = 128, N <= 256, K = 8) per k-block into
+//            one of two TMEM accumulators (2 x N columns) and commits to the ring's `empty` barrier / the
+//            accumulator's `full` barrier
+//   warp 2   allocates / frees the tensor memory
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> FP32 row-major P (each thread owns one
+//            output row, 128 contiguous bytes per chunk), then release the accumulator
+// Kernel 2, proxq_apply_kernel: the FP64 part of the iteration as one coalesced streaming pass
+//   z = c + P;  x_new = shrink(z, thr);  w_next = x_new + momentum (x_new - x_prev) -> written directly as the
+//   TF32 pair (w_hi, w_lo) the next GEMM reads; convergence test + last-CTA latch as in the FP64 kernels.
+// Per iteration: GEMM reads 2 x 4 B and writes 4 B per element, the pass reads 4 + 8 + 8 B and writes 8 + 4 + 4 B:
+// 48 B per element against 40 B for the fused FP64 launch, but nothing is bound by the FP64 tensor pipe any more.
+#include <cudaTypedefs.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace dcp {
+
+constexpr double kEpsT = 1.0e-15;
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_tf32(double v, float& hi, float& lo) {
+  hi = to_tf32(__double2float_rn(v));
+  lo = to_tf32(__double2float_rn(v - (double)hi));
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b32 r;\nelect.sync r|p, 0xffffffff;\nselp.b32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ split kernels
+__global__ void split_tf32_kernel(const double* __restrict__ A, long long lda, long long rows, long long cols,
+                                  float* __restrict__ hi, float* __restrict__ lo, long long ldh) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx % cols;
+    float h, l;
+    split_tf32(A[r * lda + c], h, l);
+    hi[r * ldh + c] = h;
+    lo[r * ldh + c] = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM
+constexpr int TBM = 128, TBK = 32, TSTAGES = 2, TNMAX = 256;
+constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KB
+constexpr int TB_BYTES = TNMAX * TBK * 4;        // 32 KB
+constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;   // 96 KB
+constexpr int TSMEM_BYTES = TSTAGES * TSTAGE_BYTES + 16 * 8;
+
+__global__ void __launch_bounds__(256, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   float* __restrict__ P, long long ldp, int M, int N, int K, const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TSTAGES * TSTAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TSTAGES;
+  uint64_t* acc_full = empty_bar + TSTAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (M + TBM - 1) / TBM;
+  const int nkb = (K + TBK - 1) / TBK;
+  // two accumulators of N columns each; allocation is a power of two >= 32 columns
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * N)) cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes = 2u * TA_BYTES + 2u * (uint32_t)N * TBK * 4u;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = tile * TBM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          unsigned char* st = smem + s * TSTAGE_BYTES;
+          const int k0 = kb * TBK;
+          tma_load_2d(st, &tmAh, &full_bar[s], k0, m0);
+          tma_load_2d(st + TA_BYTES, &tmAl, &full_bar[s], k0, m0);
+          tma_load_2d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, 0);
+          tma_load_2d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, 0);
+          if (++s == TSTAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_ph ^ 1u);   // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + s * TSTAGE_BYTES);
+          const uint32_t a_lo = a_hi + TA_BYTES;
+          const uint32_t b_hi = a_hi + 2 * TA_BYTES;
+          const uint32_t b_lo = b_hi + TB_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) {
+            const uint32_t off = (uint32_t)k * 32u;   // 8 TF32 = 32 bytes along K inside the swizzle atom
+            const uint64_t dah = umma_desc_k_sw128(a_hi + off), dal = umma_desc_k_sw128(a_lo + off);
+            const uint64_t dbh = umma_desc_k_sw128(b_hi + off), dbl = umma_desc_k_sw128(b_lo + off);
+            umma_tf32(tmem_d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          tc_commit(&empty_bar[s]);                      // smem stage is free once these MMAs have read it
+          if (kb == nkb - 1) tc_commit(&acc_full[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == TSTAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> P
+    const int e = warp - 4;                 // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * TBM + e * 32 + lane;
+      mbar_wait(&acc_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * N);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (row < M) {
+          float4* dst = reinterpret_cast<float4*>(P + row * ldp + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ FP64 pass
+__device__ __forceinline__ double max_zero_t(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  return (hi - 0x80000000u) <= 0x7ff00000u ? 0.0 : v;
+}
+__device__ __forceinline__ double with_sign_of_t(double mag, double s) {
+  return __hiloint2double(__double2hiint(mag) | (__double2hiint(s) & 0x80000000), __double2loint(mag));
+}
+
+// one thread = one column pair; grid-stride over rows * N/2 pairs, row-contiguous
+template <int SHRINK>
+__global__ void __launch_bounds__(256)
+proxq_apply_kernel(const float* __restrict__ P, long long ldp, const decomp_epilogue_t ep, float* __restrict__ w_hi,
+                   float* __restrict__ w_lo, long long ldw, long long M, long long N,
+                   const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;
+  const long long pairs = N / 2;
+  const long long total = M * pairs;
+  bool violated = false;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / pairs, col = (idx % pairs) * 2;
+    const float2 p = *reinterpret_cast<const float2*>(P + row * ldp + col);
+    const double2 c = *reinterpret_cast<const double2*>(ep.other + row * ep.ldother + col);
+    const double2 xp = *reinterpret_cast<const double2*>(ep.prev + row * ep.ldprev + col);
+    const double z0 = c.x + (double)p.x, z1 = c.y + (double)p.y;
+    double t0, t1, tol0 = 0.0, tol1 = 0.0;
+    if (SHRINK == DECOMP_SHRINK_COMPLEX) {
+      t0 = t1 = __ldg(ep.colvec + (col >> 1));
+      if (ep.check) tol0 = __ldg(ep.colvec2 + (col >> 1));
+    } else {
+      t0 = __ldg(ep.colvec + col);
+      t1 = __ldg(ep.colvec + col + 1);
+      if (ep.check) {
+        tol0 = __ldg(ep.colvec2 + col);
+        tol1 = __ldg(ep.colvec2 + col + 1);
+      }
+    }
+    double x0, x1;
+    if (SHRINK == DECOMP_SHRINK_COMPLEX) {
+      const double r = hypot(z0, z1);
+      const double den = r + kEpsT;
+      const double mag = max_zero_t(r - t0);
+      x0 = mag * (z0 / den);
+      x1 = mag * (z1 / den);
+      if (ep.check) violated |= !(hypot(x0 - xp.x, x1 - xp.y) - tol0 < 0.0);
+    } else {
+      if (SHRINK == DECOMP_SHRINK_POSITIVE) {
+        x0 = max_zero_t(z0 - t0);
+        x1 = max_zero_t(z1 - t1);
+      } else {
+        x0 = with_sign_of_t(max_zero_t(fabs(z0) - t0), z0);
+        x1 = with_sign_of_t(max_zero_t(fabs(z1) - t1), z1);
+      }
+      if (ep.check) violated |= !(fabs(x0 - xp.x) - tol0 < 0.0) || !(fabs(x1 - xp.y) - tol1 < 0.0);
+    }
+    *reinterpret_cast<double2*>(ep.out + row * ep.ldo + col) = make_double2(x0, x1);
+    const double w0 = x0 + ep.momentum * (x0 - xp.x), w1 = x1 + ep.momentum * (x1 - xp.y);
+    float h0, l0, h1, l1;
+    split_tf32(w0, h0, l0);
+    split_tf32(w1, h1, l1);
+    *reinterpret_cast<float2*>(w_hi + row * ldw + col) = make_float2(h0, h1);
+    *reinterpret_cast<float2*>(w_lo + row * ldw + col) = make_float2(l0, l1);
+  }
+  if (ep.check) {
+    const int any = __syncthreads_or(violated ? 1 : 0);
+    if (threadIdx.x == 0) {
+      if (any) atomicOr(&ep.scratch[0], 1);
+      __threadfence();
+      const int ticket = atomicAdd(&ep.scratch[1], 1);
+      if (ticket == (int)gridDim.x - 1) {
+        __threadfence();
+        const int v = atomicOr(&ep.scratch[0], 0);
+        if (v == 0) *ep.latch = ep.latch_value;
+        ep.scratch[0] = 0;
+        ep.scratch[1] = 0;
+      }
+    }
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// FP32 [outer, inner] row-major tensor map, box {32 floats = 128 bytes, box_outer rows}, 128-byte swizzle
+static int make_map_f32(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                        uint32_t box_outer) {
+  auto enc = encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DECOMP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld & 3u) != 0) {
+    set_error("TF32 GEMM operand must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
+    return DECOMP_ERR_INVALID;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_outer};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32) failed with CUresult %d", (int)r);
+    return DECOMP_ERR_CUDA;
+  }
+  return DECOMP_OK;
+}
+
+}  // namespace dcp
+
+using namespace dcp;
+
+extern "C" {
+
+int decomp_split_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldh,
+                          void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  long long b = (rows * cols + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  split_tf32_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(A, lda, rows, cols, hi, lo, ldh);
+  DCP_CHECK_LAUNCH("split_tf32");
+  return DECOMP_OK;
+}
+
+int decomp_gemm_nt_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
+                          int64_t ldb, int64_t M, int64_t N, int64_t K, float* P, int64_t ldp, const int32_t* skip_if,
+                          void* stream) {
+  if (M <= 0) return DECOMP_OK;
+  if (N <= 0 || N > TNMAX || (N % 32) != 0 || K <= 0 || (ldp & 3) != 0) {
+    set_error("decomp_gemm_nt_tf32x3: needs 32 <= N <= 256, N %% 32 == 0, K > 0, ldp %% 4 == 0 (N=%lld K=%lld)",
+              (long long)N, (long long)K);
+    return DECOMP_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tah, tal, tbh, tbl;
+  int rc = make_map_f32(&tah, A_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)N);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)N);
+  if (rc != DECOMP_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 smem)");
+    configured = true;
+  }
+  long long tiles = (M + TBM - 1) / TBM;
+  long long ctas = num_sms();
+  if (ctas > tiles) ctas = tiles;
+  tf32x3_gemm_kernel<<<(unsigned)ctas, 256, TSMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, P, ldp, (int)M, (int)N,
+                                                                             (int)K, skip_if);
+  return check_cuda(cudaGetLastError(), "tf32x3 gemm launch");
+}
+
+int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
+                           int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream) {
+  if (M <= 0 || N <= 0) return DECOMP_OK;
+  if (epi == nullptr || (N & 1) || epi->other == nullptr || epi->prev == nullptr || epi->out == nullptr ||
+      epi->colvec == nullptr || (ldp & 1) || (ldw & 1) || (epi->check && (epi->latch == nullptr || epi->scratch == nullptr))) {
+    set_error("decomp_proxq_apply_f64: invalid argument");
+    return DECOMP_ERR_INVALID;
+  }
+  long long b = (M * (N / 2) + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (b > cap) b = cap;
+  cudaStream_t st = as_stream(stream);
+  switch (epi->shrink) {
+    case DECOMP_SHRINK_REAL:
+      proxq_apply_kernel<DECOMP_SHRINK_REAL><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
+      break;
+    case DECOMP_SHRINK_COMPLEX:
+      proxq_apply_kernel<DECOMP_SHRINK_COMPLEX><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
+      break;
+    case DECOMP_SHRINK_POSITIVE:
+      proxq_apply_kernel<DECOMP_SHRINK_POSITIVE><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
+      break;
+    default:
+      set_error("decomp_proxq_apply_f64: unknown shrink kind %d", epi->shrink);
+      return DECOMP_ERR_INVALID;
+  }
+  return check_cuda(cudaGetLastError(), "proxq_apply launch");
+}
+
+}  // extern "C"

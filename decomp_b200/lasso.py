@@ -36,13 +36,17 @@ DEVICE_RULES = ('ista', 'fista', 'acc_ista')
 POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
 
 
-def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=None, **kwargs):
+def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=None, precision='fp64', **kwargs):
     """Solve the batched Lasso problem; see the module docstring. Returns ``(it, x)``.
 
     Arguments are numpy arrays (result: numpy) or CUDA torch tensors (result: torch, no host copy).
     ``method``: 'ista' | 'fista' | 'acc_ista', optionally suffixed '_pos' for non-negative x.
     The reference's sequential / inverse-based methods ('cd', 'parallel_cd', 'admm') are outside the
     hot path and raise ``NotImplementedError``.
+
+    ``precision`` (not in the reference): 'fp64' (default; matches the numpy path to ~1e-13) or 'tf32x3' -- the
+    unmasked iteration's GEMM on the tcgen05 tensor cores with operands split into two TF32 pieces and FP32
+    accumulation (the update itself stays FP64); agrees with the FP64 path to ~1e-5 relative on x.
     """
     array_kind(y, A, x, mask)
     # x = None means zeros(y.shape[:-1] + (k,), y.dtype) (lasso.py:73-74); they are created on the device
@@ -62,10 +66,11 @@ def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=Non
     if method not in AVAILABLE_METHODS + AVAILABLE_NNLS_METHODS:
         raise ValueError('Available methods are {0:s}. Given {1:s}'.format(str(AVAILABLE_METHODS), method))
     assert np_dtype(A).kind != 'c' or method[-4:] != '_pos'
-    return solve_fastpath(y, A, alpha, x, tol, maxiter, method, None, mask=mask, **kwargs)
+    return solve_fastpath(y, A, alpha, x, tol, maxiter, method, None, mask=mask, precision=precision, **kwargs)
 
 
-def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, group=None, **kwargs):
+def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, group=None, precision='fp64',
+                   **kwargs):
     """Assertion-free entry (reference: decomp/lasso.py:97-189). ``xp`` is accepted and ignored.
 
     ``group``: optional ``torch.distributed`` process group; the batch rows given to this rank are its
@@ -95,7 +100,8 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
     if mask is not None:
         m2 = to_device1d(mask, device) if mask.ndim == 1 else to_device2d(flatten_rows(mask), device, copy=False)
 
-    state = lasso_device(y2, A2, float(alpha), x2, float(tol), int(maxiter), rule, positive, m2, group=group)
+    state = lasso_device(y2, A2, float(alpha), x2, float(tol), int(maxiter), rule, positive, m2, group=group,
+                         precision=precision)
     it = state.iterations()
     res = to_host(state.result, y, out_dtype)
     return it, res.reshape(batch_shape + (k,))
@@ -128,11 +134,11 @@ def _momentum_schedule(rule, maxiter):
     return out
 
 
-def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None):
+def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None, precision='fp64'):
     """Enqueue a whole solve on the current stream. All arguments are device tensors ([B, f], [k, f],
     [B, k] or None for zeros; mask None, [f] or [B, f]). Nothing is synchronised unless the latch has to
     be polled (``tol > 0`` and more than POLL_EVERY iterations). Returns a ``LassoState``."""
-    solver = LassoSolver(y, A, alpha, x, tol, maxiter, rule, positive, mask=mask, group=group)
+    solver = LassoSolver(y, A, alpha, x, tol, maxiter, rule, positive, mask=mask, group=group, precision=precision)
     solver.iterate(0, solver.n_inplace)
     return solver.finish(out)
 
@@ -141,8 +147,11 @@ class LassoSolver(object):
     """One batched Lasso solve, split into set-up / iterations / read-out so that callers (and bench.py) can
     enqueue exactly the iterations they want. Every method only enqueues work on the current stream."""
 
-    def __init__(self, y, A, alpha, x, tol, maxiter, rule, positive, mask=None, group=None):
+    def __init__(self, y, A, alpha, x, tol, maxiter, rule, positive, mask=None, group=None, precision='fp64'):
         dev = y.device
+        if precision not in ('fp64', 'tf32x3'):
+            raise ValueError("precision must be 'fp64' or 'tf32x3', given " + str(precision))
+        self.tf32 = precision == 'tf32x3'
         self.cplx = cplx = A.is_complex()
         self.cw = cw = 2 if cplx else 1
         self.B, self.f = B, f = y.shape
@@ -204,13 +213,24 @@ class LassoSolver(object):
             ops.lasso_q(rview(G), cplx, self.step, rview(Q))
             self.Q_rhs = ops.make_rhs(rview(Q), cplx, False)       # NT operand of  w . Q
             ops.scale_scalar(rview(yAh), self.step, rview(yAh))    # yAh <- yAh / L
+        if self.tf32:
+            n_real = k * cw
+            if full_mask or n_real % 32 != 0 or n_real > 256:
+                raise NotImplementedError("precision='tf32x3' covers the unmasked iteration with k (2k for complex "
+                                          "data) a multiple of 32 up to 256; use precision='fp64'")
+            self.Q_hi, self.Q_lo = ops.split_tf32(self.Q_rhs)
+            self.P = ops.empty_f32(B, n_real, dev)
 
         # ---- iteration state
         self.checks = checks = tol > 0.0
         self.latch = torch.zeros(1, dtype=torch.int32, device=dev) if checks else None
         self.scratch = torch.zeros(2, dtype=torch.int32, device=dev) if checks else None
-        self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
-        self.W[0].copy_(X)
+        if self.tf32:
+            self.W_hi, self.W_lo = ops.split_tf32(rview(X))        # w0 = x0 as a TF32 pair, updated in place
+            self.W = [X, X]
+        else:
+            self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
+            self.W[0].copy_(X)
         self.mom = _momentum_schedule(rule, maxiter)
         # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
         # matters if it is a checking one, and then only when the check passes.
@@ -220,6 +240,16 @@ class LassoSolver(object):
     def _launch(self, i, out_x):
         W, cw, latch = self.W, self.cw, self.latch
         check = self.checks and i % 10 == 0
+        if self.tf32:
+            epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, other=rview(self.yAh), prev=rview(self.X),
+                               colvec=self.thr, colvec2=self.tol_vec, flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD,
+                               momentum=self.mom[i], shrink=self.shrink, check=check, latch=latch,
+                               scratch=self.scratch, latch_value=i + 1)
+            ops.gemm_nt_tf32x3(self.W_hi, self.W_lo, self.Q_hi, self.Q_lo, self.P, skip=latch)
+            ops.proxq_apply(self.P, epi, self.W_hi, self.W_lo, skip=latch)
+            if check and self.group is not None:
+                torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            return
         if not self.full_mask:
             epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), other=rview(self.yAh),
                                prev=rview(self.X), colvec=self.thr, colvec2=self.tol_vec,

@@ -274,3 +274,41 @@ def max_abs_diff(A, B, is_complex, result, scratch, tol=0.0, latch=None, latch_v
     _lib.check(rc, 'decomp_max_abs_diff_f64')
     _count(1)
     return result
+
+
+# ------------------------------------------------------------------------------------- TF32-split path
+def empty_f32(rows, cols, device):
+    """[rows, cols] float32 buffer with a row pitch that is a multiple of 4 floats (TMA: 16-byte rows)."""
+    pitch = (cols + 3) // 4 * 4
+    return torch.empty((max(rows, 1), max(pitch, 4)), dtype=torch.float32, device=device)[:rows, :cols]
+
+
+def split_tf32(A, hi=None, lo=None):
+    """A (float64 real view) ~= hi + lo with TF32-valued float32 pieces."""
+    rows, cols = A.shape
+    if hi is None:
+        hi, lo = empty_f32(rows, cols, A.device), empty_f32(rows, cols, A.device)
+    rc = _lib.lib().decomp_split_tf32_f64(_p(A), ld(A), rows, cols, _p(hi), _p(lo), ld(hi), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_split_tf32_f64')
+    _count(1)
+    return hi, lo
+
+
+def gemm_nt_tf32x3(A_hi, A_lo, B_hi, B_lo, P, skip=None):
+    """P = A . B^T in split TF32 on the tcgen05 tensor cores (A [M, K], B [N, K], P [M, N] float32)."""
+    M, K = A_hi.shape
+    N = B_hi.shape[0]
+    rc = _lib.lib().decomp_gemm_nt_tf32x3(_p(A_hi), _p(A_lo), ld(A_hi), _p(B_hi), _p(B_lo), ld(B_hi), M, N, K, _p(P),
+                                          ld(P), _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_nt_tf32x3')
+    _count(1)
+    return P
+
+
+def proxq_apply(P, epi, w_hi, w_lo, skip=None):
+    """FP64 threshold / momentum / convergence pass after gemm_nt_tf32x3; writes w_next as (w_hi, w_lo)."""
+    M, N = P.shape
+    rc = _lib.lib().decomp_proxq_apply_f64(_p(P), ld(P), ctypes.byref(epi), _p(w_hi), _p(w_lo), ld(w_hi), M, N,
+                                           _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_proxq_apply_f64')
+    _count(1)

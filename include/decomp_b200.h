@@ -171,6 +171,22 @@ int decomp_max_abs_diff_f64(const double* A, int64_t lda, const double* B, int64
                             int32_t is_complex, double tol, int32_t* tol_latch, int32_t latch_value, double* result,
                             int32_t* scratch, const int32_t* skip_if, void* stream);
 
+/* ---- TF32-split ("3xTF32") variant of the unmasked ISTA/FISTA iteration (tcgen05 tensor cores, FP32 accumulate) ----
+ * Not bit-compatible with the FP64 path: products carry ~22 significant bits (see DESIGN.md for the tolerance).
+ * hi/lo: FP32 arrays holding TF32-valued pieces, v ~= hi + lo; row pitch `ldh` in floats, multiple of 4. */
+int decomp_split_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldh,
+                          void* stream);
+/* P[M,N] (FP32, row-major) = A_lo.B_hi^T + A_hi.B_lo^T + A_hi.B_hi^T; A_* [M,K], B_* [N,K] K-contiguous FP32.
+ * 32 <= N <= 256, N % 32 == 0.  Replaces xp.tensordot(x0, AAt) of lasso.py:245 (with B = (I - G/L)^T). */
+int decomp_gemm_nt_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
+                          int64_t ldb, int64_t M, int64_t N, int64_t K, float* P, int64_t ldp, const int32_t* skip_if,
+                          void* stream);
+/* The FP64 part of the iteration in one streaming pass (lasso.py:192-256, 405-414 with z = other + P):
+ * uses epi->{out, other, prev, colvec (= step*alpha), colvec2, momentum, shrink, check, latch, scratch, latch_value};
+ * w_next is written as the TF32 pair (w_hi, w_lo) the next decomp_gemm_nt_tf32x3 reads. */
+int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
+                           int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream);
+
 /* ---- dictionary-learning basis update ------------------------------------------------- */
 /* Gauss-Seidel atom sweep, dictionary_learning.py:154-159:
  *   for a in 0..k-1: u = (T[a] - S[a].D) / (S[a][a] + eps) + D[a];  D[a] = u / sqrt(max(|u|^2, 1))
