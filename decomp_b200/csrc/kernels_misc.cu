@@ -377,6 +377,18 @@ __global__ void scale_scalar_kernel(const double* __restrict__ A, long long lda,
   }
 }
 
+// ------------------------------------------------------------------------------------ out = a * X + b * Y
+__global__ void axpby_kernel(double a, const double* __restrict__ X, long long ldx, double b,
+                             const double* __restrict__ Y, long long ldy, long long rows, long long cols,
+                             double* __restrict__ out, long long ldo) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx % cols;
+    out[r * ldo + c] = a * X[r * ldx + c] + b * Y[r * ldy + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------ elementwise MU ratio
 // out = x * max(num, 0) / max(den, eps)                                (grads.py:84,93)
 __global__ void mu_update_kernel(const double* __restrict__ x, long long ldx, const double* __restrict__ num,
@@ -611,6 +623,14 @@ int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double to
   lasso_vectors_kernel<<<grid_for(k, 256), 256, 0, as_stream(stream)>>>(s, (int)k, alpha, tol, mult, mult_dev,
                                                                        alpha_out, tol_out);
   DCP_CHECK_LAUNCH("lasso_vectors");
+  return DECOMP_OK;
+}
+
+int decomp_axpby_f64(double a, const double* X, int64_t ldx, double b, const double* Y, int64_t ldy, int64_t rows,
+                     int64_t cols, double* out, int64_t ldo, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  axpby_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(a, X, ldx, b, Y, ldy, rows, cols, out, ldo);
+  DCP_CHECK_LAUNCH("axpby");
   return DECOMP_OK;
 }
 

@@ -30,8 +30,13 @@ from .utils import assertion
 
 
 def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='block_cd', lasso_method='cd',
-          lasso_iter=10, lasso_tol=1.0e-5, mask=None, random_seed=None):
+          lasso_iter=10, lasso_tol=1.0e-5, mask=None, random_seed=None, group=None):
     """Learn the dictionary ``D`` and the codes ``x``; see the module docstring.
+
+    ``group`` (not in the reference): optional ``torch.distributed`` process group.  The algorithm is sequential
+    across minibatches, so the ranks share each minibatch: every rank passes the SAME arrays and seed, codes its
+    own block of rows of each minibatch, the new codes are exchanged, the sufficient statistics are all-reduced and
+    the atom update is replicated.  Every rank returns the same ``(it, D, x)``.
 
     ``lasso_method`` must be one of the device rules ('ista', 'fista', 'acc_ista', optionally '_pos'); the
     reference's default 'cd' is a sequential reference-purpose method outside the hot path.
@@ -72,7 +77,7 @@ def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method=
     xd = to_device2d(x, device, copy=True)
     rng = np.random.RandomState(random_seed)
     it, Dd, xd = block_cd_device(yd, Dd, float(alpha), xd, float(tol), int(minibatch), int(maxiter), rule, positive,
-                                 int(lasso_iter), float(lasso_tol), md, rng)
+                                 int(lasso_iter), float(lasso_tol), md, rng, group=group)
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
@@ -99,7 +104,8 @@ class _ShuffledRows(object):
         return self.cur[r * step:(r + 1) * step]
 
 
-def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, lasso_iter, lasso_tol, mask, rng):
+def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, lasso_iter, lasso_tol, mask, rng,
+                    group=None):
     """``solve_cd`` / ``solve_cd_mask`` on device tensors. Returns ``(it, D, x)`` with x in the caller's row order."""
     dev = y.device
     n, f = y.shape
@@ -127,6 +133,14 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
     else:
         S = zeros2d(k, k, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
+    dist = torch.distributed if group is not None else None
+    if dist is not None:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        lo, hi = rank * minibatch // world, (rank + 1) * minibatch // world     # this rank's rows of a minibatch
+        S_part = torch.zeros_like(S)            # local statistics before the all-reduce
+        T_part = zeros2d(k, f, cplx, dev)
+    else:
+        lo, hi = 0, minibatch
     result = torch.zeros(2, dtype=torch.float64, device=dev)
     scratch = torch.zeros(1, dtype=torch.int32, device=dev)
     checks = tol > 0.0
@@ -150,22 +164,45 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
             for r in range(n // minibatch):                                    # tail rows are skipped
                 y_mb, x_mb = ys.rows(r, minibatch), xs.rows(r, minibatch)
                 m_mb = ms.rows(r, minibatch) if masked else None
-                lasso_device(y_mb, D, alpha, x_mb, lasso_tol, lasso_iter, rule, positive, m_mb, out=x_mb)
+                if dist is None:
+                    lasso_device(y_mb, D, alpha, x_mb, lasso_tol, lasso_iter, rule, positive, m_mb, out=x_mb)
+                else:
+                    # code this rank's rows, then make the whole minibatch's codes known everywhere
+                    x_own = x_mb[lo:hi]
+                    lasso_device(y_mb[lo:hi], D, alpha, x_own, lasso_tol, lasso_iter, rule, positive,
+                                 m_mb[lo:hi] if masked else None, out=x_own, group=group)
+                    x_mb[:lo].zero_()
+                    x_mb[hi:].zero_()
+                    _allreduce(x_mb, group)
 
                 theta = count * minibatch + 1.0                                # equation (11), :143-144
                 beta = (theta - minibatch) / theta
-                xr = rview(x_mb)
+                # statistics over this rank's rows (all rows without a group); with a group the partial sums are
+                # all-reduced and folded in as  S <- beta S + sum_ranks(partial)
+                xr = rview(x_mb[lo:hi])
+                rows = hi - lo
+                S_dst, T_dst = (S, T) if dist is None else (S_part, T_part)
+                comb = stat_combine if dist is None else stat_combine - 1       # accumulate / overwrite
                 if not masked:
-                    ops.gemm_tn(xr, xr, rview(S), combine=stat_combine, beta=beta, workspace=ws)       # :151
-                    ops.gemm_tn(xr, rview(y_mb), rview(T), combine=stat_combine, beta=beta, workspace=ws)
+                    ops.gemm_tn(xr, xr, rview(S_dst), combine=comb, beta=beta, workspace=ws)           # :151
+                    ops.gemm_tn(xr, rview(y_mb[lo:hi]), rview(T_dst), combine=comb, beta=beta, workspace=ws)
+                else:
+                    for a in range(k):                                                                 # :210-213
+                        ops.dl_atom_weighted(xr, cplx, a, rview(W[:rows]))
+                        ops.gemm_tn(m_mb[lo:hi], rview(W[:rows]), S_dst[a], combine=1 if dist is None else 0,
+                                    beta=beta, workspace=ws)
+                    ops.mask_mul(rview(y_mb[lo:hi]), m_mb[lo:hi], rview(YM[:rows]), cwidth=cw)
+                    ops.gemm_tn(xr, rview(YM[:rows]), rview(T_dst), combine=comb, beta=beta, workspace=ws)  # :214
+                if dist is not None:
+                    _allreduce(S_part, group)
+                    _allreduce(T_part, group)
+                    S2, P2 = (S.view(k * f, k * cw), S_part.view(k * f, k * cw)) if masked else (rview(S), rview(S_part))
+                    ops.axpby(beta, S2, 1.0, P2, S2)
+                    ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
+                if not masked:
                     Dn.copy_(D)
                     ops.dl_sweep(rview(S), rview(T), rview(Dn), cplx)                                  # :154-159
                 else:
-                    for a in range(k):                                                                 # :210-213
-                        ops.dl_atom_weighted(xr, cplx, a, rview(W))
-                        ops.gemm_tn(m_mb, rview(W), S[a], combine=1, beta=beta, workspace=ws)
-                    ops.mask_mul(rview(y_mb), m_mb, rview(YM), cwidth=cw)
-                    ops.gemm_tn(xr, rview(YM), rview(T), combine=stat_combine, beta=beta, workspace=ws)  # :214
                     ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)                # :216-222
                 if checks:
                     ops.max_abs_diff(rview(D), rview(Dn), cplx, result, scratch)
@@ -176,3 +213,13 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
         except KeyboardInterrupt:
             return it, D, restored_x()
     return maxiter, D, restored_x()
+
+
+def _allreduce(t, group):
+    """Sum over the ranks, in place, also for row-padded (non-contiguous) buffers."""
+    if t.is_contiguous():
+        torch.distributed.all_reduce(t, group=group)
+    else:
+        flat = t.contiguous()
+        torch.distributed.all_reduce(flat, group=group)
+        t.copy_(flat)

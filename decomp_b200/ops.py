@@ -237,6 +237,16 @@ def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):
     return alpha_out, tol_out
 
 
+def axpby(a, X, b, Y, out):
+    """out = a * X + b * Y (real views)."""
+    rows, cols = X.shape
+    rc = _lib.lib().decomp_axpby_f64(float(a), _p(X), ld(X), float(b), _p(Y), ld(Y), rows, cols, _p(out), ld(out),
+                                     _lib.stream_ptr())
+    _lib.check(rc, 'decomp_axpby_f64')
+    _count(1)
+    return out
+
+
 def lasso_q(G, is_complex, step, Q):
     """Q = I - step * G (real views of [k, k] matrices; step is a device scalar)."""
     k = G.shape[0]

@@ -156,6 +156,10 @@ int decomp_gather_rows_f64(const double* in, int64_t ldi, const int64_t* index, 
  * device scalar mult_dev when that is non-NULL (sum of a 1-D mask)   (lasso.py:129-130, 136-138) */
 int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double tol, double mult, const double* mult_dev,
                              double* alpha_out, double* tol_out, void* stream);
+/* out = a * X + b * Y elementwise (A = beta*A + sum over ranks of the local statistics, dictionary_learning.py:151-152,
+ * when the minibatch rows are sharded over GPUs) */
+int decomp_axpby_f64(double a, const double* X, int64_t ldx, double b, const double* Y, int64_t ldy, int64_t rows,
+                     int64_t cols, double* out, int64_t ldo, void* stream);
 /* Q = I - (*step) * G for a [k,k] (complex: interleaved) Gram matrix and out = (*scalar_dev) * A: the operands of
  * DECOMP_EPI_PROXQ, i.e. lasso.py:245-246  w + (yAh - w G)/L  written as  yAh/L + w (I - G/L). */
 int decomp_lasso_q_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex, const double* step, double* Q,

@@ -73,6 +73,31 @@ def cpu_host_logic(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def gpu_sharded_dictionary_learning(rank, world, port, out):
+    """Dictionary learning with each minibatch's rows shared between the ranks (replicated inputs) vs the oracle."""
+    _init(rank, world, port, 'nccl')
+    from decomp_b200 import dictionary_learning
+    import golden_cases as gc
+    from oracle import decomp_oracle as orc
+    res = {}
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    for cplx in (False, True):
+        y, D0, mask = gc._dl_data(230, 33, 12, 9, cplx)
+        for masked in (False, True):
+            yy = y * mask if masked else y
+            kw = dict(tol=0.0, minibatch=63, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
+                      mask=mask if masked else None, random_seed=4)
+            it, D, x = dictionary_learning.solve(yy, D0.copy(), 0.05, group=dist.group.WORLD, **kw)
+            it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, **kw)
+            res['dl_%s_%s' % ('c' if cplx else 'f', 'mask' if masked else 'nomask')] = (it, it0, rel(D, D_ref),
+                                                                                        rel(x, x_ref))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------- GPU / nccl
 def gpu_sharded_solves(rank, world, port, out):
     """Sharded NMF (unmasked, masked) and sharded Lasso (tol > 0: global convergence decision) against the oracle."""

@@ -37,3 +37,13 @@ def test_world_size_2_nccl_sharded_solves():
         for name in ('lasso', 'lasso_mask'):
             it, it0, ex = res[name]
             assert it == it0 and ex < 1e-10, (rank, name, res[name])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_world_size_2_nccl_dictionary_learning():
+    out = _spawn(dist_workers.gpu_sharded_dictionary_learning, 2)
+    assert set(out) == {0, 1}
+    for rank, res in out.items():
+        for name, (it, it0, eD, ex) in res.items():
+            assert it == it0 and eD < 1e-9 and ex < 1e-9, (rank, name, it, it0, eD, ex)
