@@ -389,6 +389,21 @@ __global__ void axpby_kernel(double a, const double* __restrict__ X, long long l
   }
 }
 
+// ------------------------------------------------------------------------------------ SVRMU basis step
+// out = max(D * ((1 - alpha) + alpha * P / max(Q, eps)), 0)            (nmf_methods/kasai.py:75-77)
+__global__ void svrmu_update_kernel(const double* __restrict__ D, long long ldd, const double* __restrict__ P,
+                                    long long ldp, const double* __restrict__ Q, long long ldq, double alpha,
+                                    long long rows, long long cols, double* __restrict__ out, long long ldo) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx % cols;
+    const double ratio = __ddiv_rn(__dmul_rn(alpha, P[r * ldp + c]), fmax(Q[r * ldq + c], kEps));
+    const double v = __dmul_rn(D[r * ldd + c], __dadd_rn(1.0 - alpha, ratio));
+    out[r * ldo + c] = fmax(v, 0.0);
+  }
+}
+
 // ------------------------------------------------------------------------------------ elementwise MU ratio
 // out = x * max(num, 0) / max(den, eps)                                (grads.py:84,93)
 __global__ void mu_update_kernel(const double* __restrict__ x, long long ldx, const double* __restrict__ num,
@@ -623,6 +638,15 @@ int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double to
   lasso_vectors_kernel<<<grid_for(k, 256), 256, 0, as_stream(stream)>>>(s, (int)k, alpha, tol, mult, mult_dev,
                                                                        alpha_out, tol_out);
   DCP_CHECK_LAUNCH("lasso_vectors");
+  return DECOMP_OK;
+}
+
+int decomp_svrmu_update_f64(const double* D, int64_t ldd, const double* P, int64_t ldp, const double* Q, int64_t ldq,
+                            double alpha, int64_t rows, int64_t cols, double* out, int64_t ldo, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  svrmu_update_kernel<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(D, ldd, P, ldp, Q, ldq, alpha, rows,
+                                                                                cols, out, ldo);
+  DCP_CHECK_LAUNCH("svrmu_update");
   return DECOMP_OK;
 }
 

@@ -60,21 +60,18 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
     if likelihood in ['kl']:
         assertion.assert_nonnegative(y)
 
-    if minibatch is not None:
-        raise NotImplementedError('NMF with {} algorithm is not yet implemented.'.format(method)
-                                  if method not in MINIBATCH_METHODS else
-                                  'minibatch NMF ({}) is outside the B200 hot path; use minibatch=None, '
-                                  "method='mu'.".format(method))
-    if method != 'mu':
-        raise NotImplementedError('Batch-NMF with {} algorithm is not yet implemented.'.format(method))
-    if kwargs:
-        raise TypeError('solve() got unexpected keyword arguments ' + str(sorted(kwargs)))
     if likelihood in ('l2', 'gaussian'):
         kl = False
     elif likelihood in ('kl', 'poisson'):
         kl = True
     else:
         raise NotImplementedError('Likelihood {} is not implemented for nmf'.format(likelihood))
+    if minibatch is not None:
+        return _solve_minibatch(y, D, x, tol, minibatch, maxiter, method, kl, mask, random_seed, group, kwargs)
+    if method != 'mu':
+        raise NotImplementedError('Batch-NMF with {} algorithm is not yet implemented.'.format(method))
+    if kwargs:
+        raise TypeError('solve() got unexpected keyword arguments ' + str(sorted(kwargs)))
 
     device = require_cuda()
     out_dtype = np_dtype(y)
@@ -83,6 +80,32 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
     Dd = to_device2d(D, device, copy=True)
     xd = to_device2d(x, device, copy=True)       # updated in place: always our own copy
     it, Dd, xd = mu_device(yd, Dd, xd, float(tol), int(maxiter), kl, md, group=group)
+    return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
+
+
+def _solve_minibatch(y, D, x, tol, minibatch, maxiter, method, kl, mask, random_seed, group, kwargs):
+    """decomp/nmf.py:82-111: the stochastic drivers (serizel.py, kasai.py) on row blocks of shuffled data."""
+    from . import nmf_minibatch
+    if method not in MINIBATCH_METHODS:
+        raise NotImplementedError('NMF with {} algorithm is not yet implemented.'.format(method))
+    if group is not None:
+        raise NotImplementedError('minibatch NMF runs on one GPU')
+    allowed = ('forget_rate',) if method.endswith('g-mu') else ('alpha', 'beta')
+    for key in kwargs:
+        if key not in allowed:
+            raise TypeError("solve() got an unexpected keyword argument '%s'" % key)
+    if y.shape[0] < minibatch:                                        # utils/data.py:79-82
+        raise ValueError('Minibatch size should be smaller than the total size. Given {} < {}'.format(
+            y.shape[0], minibatch))
+    device = require_cuda()
+    out_dtype = np_dtype(y)
+    yd = to_device2d(y, device, copy=False)
+    md = to_device2d(mask, device, copy=False) if mask is not None else None
+    Dd = to_device2d(D, device, copy=True)
+    xd = to_device2d(x, device, copy=True)
+    rng = np.random.RandomState(random_seed)
+    it, Dd, xd = nmf_minibatch.solve_device(yd, Dd, xd, float(tol), int(minibatch), int(maxiter), method, kl, md, rng,
+                                            **kwargs)
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 

@@ -247,6 +247,16 @@ def axpby(a, X, b, Y, out):
     return out
 
 
+def svrmu_update(D, P, Q, alpha, out):
+    """out = max(D * ((1 - alpha) + alpha * P / max(Q, eps)), 0)."""
+    rows, cols = D.shape
+    rc = _lib.lib().decomp_svrmu_update_f64(_p(D), ld(D), _p(P), ld(P), _p(Q), ld(Q), float(alpha), rows, cols, _p(out),
+                                            ld(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_svrmu_update_f64')
+    _count(1)
+    return out
+
+
 def lasso_q(G, is_complex, step, Q):
     """Q = I - step * G (real views of [k, k] matrices; step is a device scalar)."""
     k = G.shape[0]

@@ -160,6 +160,10 @@ int decomp_lasso_vectors_f64(const double* s, int64_t k, double alpha, double to
  * when the minibatch rows are sharded over GPUs) */
 int decomp_axpby_f64(double a, const double* X, int64_t ldx, double b, const double* Y, int64_t ldy, int64_t rows,
                      int64_t cols, double* out, int64_t ldo, void* stream);
+/* out = max(D * ((1 - alpha) + alpha * P / max(Q, eps)), 0): the variance-reduced basis step of
+ * nmf_methods/kasai.py:75-77 (minibatch NMF, "next" row of the scope table) */
+int decomp_svrmu_update_f64(const double* D, int64_t ldd, const double* P, int64_t ldp, const double* Q, int64_t ldq,
+                            double alpha, int64_t rows, int64_t cols, double* out, int64_t ldo, void* stream);
 /* Q = I - (*step) * G for a [k,k] (complex: interleaved) Gram matrix and out = (*scalar_dev) * A: the operands of
  * DECOMP_EPI_PROXQ, i.e. lasso.py:245-246  w + (yAh - w G)/L  written as  yAh/L + w (I - G/L). */
 int decomp_lasso_q_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex, const double* step, double* Q,

@@ -127,6 +127,112 @@ def nmf_mu(y, D, x=None, tol=1.0e-3, maxiter=1000, likelihood='l2', mask=None):
 
 
 # --------------------------------------------------------------------------------------
+# NMF, minibatch multiplicative updates (decomp/nmf.py:82-111 -> nmf_methods/serizel.py, kasai.py)
+# --------------------------------------------------------------------------------------
+def _mu_step(v, pos, neg):
+    return v * np.maximum(pos, 0.0) / np.maximum(neg, EPS)
+
+
+def nmf_minibatch(y, D, x=None, tol=1.0e-3, minibatch=10, maxiter=1000, method='asg-mu', likelihood='l2', mask=None,
+                  random_seed=None, forget_rate=0.5, alpha=1.0, beta=0.5):
+    """Minibatch NMF drivers of the reference, with its quirks: 'gsg-mu' runs the 'asg-mu' loop
+    (serizel.py:23-25), and on convergence the *previous* D is returned (serizel.py:58, kasai.py:81)."""
+    kl = likelihood in ('kl', 'poisson')
+    if x is None:
+        x = np.ones((y.shape[0], D.shape[0]), dtype=y.dtype)
+    D = unit_rows(D)                                              # nmf.py:70
+    ys, xs = _Rows(y, minibatch), _Rows(x, minibatch)
+    ms = _Rows(mask, minibatch) if mask is not None else None
+    rng = np.random.RandomState(random_seed)
+    order = np.arange(len(y))
+    n_loop = len(y) // minibatch
+
+    def permute():
+        rng.shuffle(order)
+        ys.permute(order)
+        xs.permute(order)
+        if ms is not None:
+            ms.permute(order)
+
+    def batches():
+        mc = ms.chunks() if ms is not None else None
+        for y_mb, x_mb in zip(ys.chunks(), xs.chunks()):
+            yield y_mb, x_mb, (next(mc) if mc is not None else None)
+
+    def update_x(y_mb, x_mb, m_mb, D):
+        pos, neg = _mu_parts_x(y_mb, x_mb, D, m_mb, kl)
+        x_mb[:] = _mu_step(x_mb, pos, neg)
+
+    if method in ('asg-mu', 'gsg-mu'):                            # serizel.py:36-61
+        for it in range(1, maxiter):
+            permute()
+            for y_mb, x_mb, m_mb in batches():
+                update_x(y_mb, x_mb, m_mb, D)
+                pos, neg = _mu_parts_d(y_mb, x_mb, D, m_mb, kl)
+                D_new = unit_rows(_mu_step(D, pos, neg))
+                if np.max(np.abs(D - D_new)) < tol:
+                    return it, D, xs.restored()
+                D = D_new
+        return maxiter, D, xs.restored()
+
+    if method in ('asag-mu', 'gsag-mu'):                          # serizel.py:92-165
+        every_batch = method == 'asag-mu'
+        for it in range(1, maxiter):
+            permute()
+            pos_sum, neg_sum = np.zeros_like(D), np.zeros_like(D)
+            for y_mb, x_mb, m_mb in batches():
+                update_x(y_mb, x_mb, m_mb, D)
+                pos, neg = _mu_parts_d(y_mb, x_mb, D, m_mb, kl)
+                pos_sum = (1.0 - forget_rate) * pos_sum + forget_rate * pos
+                neg_sum = (1.0 - forget_rate) * neg_sum + forget_rate * neg
+                if every_batch:
+                    D_new = unit_rows(_mu_step(D, pos_sum, neg_sum))
+                    if np.max(np.abs(D - D_new)) < tol:
+                        return it, D, xs.restored()
+                    D = D_new
+            if not every_batch:
+                D_new = unit_rows(_mu_step(D, pos_sum, neg_sum))
+                if np.max(np.abs(D - D_new)) < tol:
+                    return it, D, xs.restored()
+                D = D_new
+        return maxiter, D, xs.restored()
+
+    if method in ('svrmu', 'svrmu-acc'):                          # kasai.py:10-88
+        if method == 'svrmu':
+            inner = 1
+        else:
+            F, K = D.shape
+            N = x.shape[0]
+            inner = int(np.maximum(beta * F * (3 * K + 2 * N) / (3 * F * N + 2 * K), 1.0))
+        permute()                                                  # once, before the first epoch
+        pos_prev = np.zeros((n_loop,) + D.shape, dtype=D.dtype)
+        neg_prev = np.zeros((n_loop,) + D.shape, dtype=D.dtype)
+        for it in range(1, maxiter):
+            pos_full, neg_full = np.zeros_like(D), np.zeros_like(D)
+            for y_mb, x_mb, m_mb in batches():
+                pos, neg = _mu_parts_d(y_mb, x_mb, D, m_mb, kl)
+                pos_full += pos
+                neg_full += neg
+            pos_full /= n_loop
+            neg_full /= n_loop
+            for b, (y_mb, x_mb, m_mb) in enumerate(batches()):
+                for _ in range(inner):
+                    update_x(y_mb, x_mb, m_mb, D)
+                pos, neg = _mu_parts_d(y_mb, x_mb, D, m_mb, kl)
+                P = pos + neg_prev[b] + pos_full
+                Q = neg + pos_prev[b] + neg_full
+                D_new = D * ((1.0 - alpha) + alpha * P / np.maximum(Q, EPS))
+                D_new = unit_rows(np.maximum(D_new, 0.0))
+                if np.max(np.abs(D - D_new)) < tol:
+                    return it, D, xs.restored()
+                D = D_new
+                pos_prev[b] = pos
+                neg_prev[b] = neg
+        return maxiter, D, xs.restored()
+    raise NotImplementedError('NMF with {} algorithm is not yet implemented.'.format(method))
+
+
+# --------------------------------------------------------------------------------------
 # batched Lasso: ISTA / FISTA / accelerated ISTA, optional non-negativity and masks
 # --------------------------------------------------------------------------------------
 def _batch_mean(mask):

@@ -45,6 +45,31 @@ def nmf_cases():
     return cases
 
 
+def nmf_minibatch_cases():
+    """Minibatch NMF drivers (/root/reference/tests/test_nmf.py:105-152 uses the same data recipe)."""
+    cases = OrderedDict()
+    y, D0, mask = _nmf_data(101, 20, 3, 0, 'l2')
+    ykl, D0kl, _ = _nmf_data(101, 20, 3, 0, 'kl')
+    for method in ('asg-mu', 'gsg-mu', 'asag-mu', 'gsag-mu', 'svrmu', 'svrmu-acc'):
+        tag = method.replace('-', '_')
+        cases['%s_l2' % tag] = dict(y=y, D=D0, mask=None, tol=0.0, maxiter=8, minibatch=10, method=method,
+                                    likelihood='l2', random_seed=0)
+        cases['%s_l2_mask' % tag] = dict(y=y, D=D0, mask=mask, tol=0.0, maxiter=8, minibatch=10, method=method,
+                                         likelihood='l2', random_seed=1)
+    cases['asg_mu_kl_mask'] = dict(y=ykl, D=D0kl, mask=mask, tol=0.0, maxiter=6, minibatch=25, method='asg-mu',
+                                   likelihood='kl', random_seed=2)
+    cases['svrmu_kl'] = dict(y=ykl, D=D0kl, mask=None, tol=0.0, maxiter=6, minibatch=25, method='svrmu',
+                             likelihood='kl', random_seed=2)
+    cases['asag_mu_conv'] = dict(y=y, D=D0, mask=None, tol=1.0e-3, maxiter=400, minibatch=20, method='asag-mu',
+                                 likelihood='l2', random_seed=3)
+    y2, D02, mask2 = _nmf_data(257, 67, 7, 3, 'l2')
+    cases['gsag_mu_ragged_mask'] = dict(y=y2, D=D02, mask=mask2, tol=0.0, maxiter=5, minibatch=50, method='gsag-mu',
+                                        likelihood='l2', random_seed=4)
+    cases['svrmu_acc_ragged'] = dict(y=y2, D=D02, mask=None, tol=0.0, maxiter=5, minibatch=50, method='svrmu-acc',
+                                     likelihood='l2', random_seed=4)
+    return cases
+
+
 # ------------------------------------------------------------------------------- Lasso
 def _lasso_data(batch_shape, k, f, seed, complex_=False, dtype=None, positive=False):
     """/root/reference/tests/test_lasso.py:143-150, 223-250 (vector / matrix / tensor set-ups)."""

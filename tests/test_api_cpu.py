@@ -118,7 +118,11 @@ def test_nmf_validation_errors():
     with pytest.raises(AssertionError):
         nmf.solve(-y, D, likelihood='kl')
     with pytest.raises(NotImplementedError):
-        nmf.solve(y, D, method='svrmu', minibatch=5)
+        nmf.solve(y, D, method='mu', minibatch=5)                 # 'mu' is a batch method (nmf.py:113)
+    with pytest.raises(ValueError):
+        nmf.solve(y, D, method='svrmu', minibatch=50)             # minibatch > n (utils/data.py:79-82)
+    with pytest.raises(TypeError):
+        nmf.solve(y, D, method='svrmu', minibatch=5, forget_rate=0.5)
     with pytest.raises(NotImplementedError):
         nmf.solve(y, D, method='als')
     with pytest.raises(NotImplementedError):

@@ -51,6 +51,16 @@ def test_nmf(name):
     assert close(D, g['D']) and close(x, g['x'])
 
 
+@pytest.mark.parametrize('name', list(gc.nmf_minibatch_cases().keys()))
+def test_nmf_minibatch(name):
+    case = gc.nmf_minibatch_cases()[name]
+    g = load('nmfmb_' + name)
+    kw = {k: v for k, v in case.items() if k not in ('y', 'D')}
+    it, D, x = orc.nmf_minibatch(case['y'], case['D'].copy(), **kw)
+    assert it == int(g['it'])
+    assert close(D, g['D']) and close(x, g['x'])
+
+
 @pytest.mark.parametrize('name', list(gc.lasso_cases().keys()))
 def test_lasso(name):
     case = gc.lasso_cases()[name]

@@ -49,6 +49,20 @@ def test_nmf_golden(name):
     assert_close(x, g['x'], what='x')
 
 
+@pytest.mark.parametrize('name', list(gc.nmf_minibatch_cases().keys()))
+def test_nmf_minibatch_golden(name):
+    """Stochastic MU drivers (serizel.py, kasai.py) against the unmodified reference."""
+    from decomp_b200 import nmf
+    case = gc.nmf_minibatch_cases()[name]
+    g = load('nmfmb_' + name)
+    it, D, x = nmf.solve(case['y'], case['D'].copy(), tol=case['tol'], minibatch=case['minibatch'],
+                         maxiter=case['maxiter'], method=case['method'], likelihood=case['likelihood'],
+                         mask=case['mask'], random_seed=case['random_seed'])
+    assert it == int(g['it'])
+    assert_close(D, g['D'], rtol=1.0e-9, what='D')
+    assert_close(x, g['x'], rtol=1.0e-9, what='x')
+
+
 # ----------------------------------------------------------------------------------- golden: Lasso
 @pytest.mark.parametrize('name', list(gc.lasso_cases().keys()))
 def test_lasso_golden(name):

@@ -64,6 +64,14 @@ def main():
         np.savez(os.path.join(out_dir, 'nmf_%s.npz' % name), it=it, D=D, x=x)
         print('nmf', name, 'it', it, 'sumD', D.sum(), 'sumx', x.sum())
 
+    # ---- minibatch NMF drivers
+    for name, case in gc.nmf_minibatch_cases().items():
+        it, D, x = ref.nmf.solve(case['y'], case['D'].copy(), x=None, tol=case['tol'], minibatch=case['minibatch'],
+                                 maxiter=case['maxiter'], method=case['method'], likelihood=case['likelihood'],
+                                 mask=case['mask'], random_seed=case['random_seed'])
+        np.savez(os.path.join(out_dir, 'nmfmb_%s.npz' % name), it=it, D=D, x=x)
+        print('nmfmb', name, 'it', it, 'sumD', D.sum(), 'sumx', x.sum())
+
     # ---- Lasso
     for name, case in gc.lasso_cases().items():
         it, x = ref.lasso.solve(case['y'], case['A'], alpha=case['alpha'], tol=case['tol'],
