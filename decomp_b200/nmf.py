@@ -33,8 +33,13 @@ POLL_EVERY = 25
 
 
 def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', likelihood='l2', mask=None,
-          random_seed=None, group=None, **kwargs):
+          random_seed=None, group=None, host_block_rows=None, **kwargs):
     """NMF, see the module docstring. ``likelihood``: 'l2' | 'gaussian' | 'kl' | 'poisson'.
+
+    ``host_block_rows`` (not in the reference; numpy inputs, 'l2' only): out-of-core mode for data larger than the
+    GPU memory.  ``y`` (and ``mask``) stay in host memory, are page-locked in place and streamed through three
+    rotating device buffers of that many rows by a copy stream while the previous block is being processed
+    (the role of the reference's ``AsyncMinibatchData``, utils/data.py:212-313); ``x`` and ``D`` live on the device.
 
     ``group``: optional ``torch.distributed`` process group. Each rank passes its own contiguous block of
     rows of ``y`` / ``x`` / ``mask`` and the same ``D``; per sweep only the [k, f] and [k, k] statistics
@@ -66,6 +71,14 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
         kl = True
     else:
         raise NotImplementedError('Likelihood {} is not implemented for nmf'.format(likelihood))
+    if host_block_rows is not None:
+        if minibatch is not None or method != 'mu' or kl or group is not None or is_torch(y) or kwargs:
+            raise NotImplementedError("host_block_rows streams numpy data through the full-batch 'mu' / 'l2' solver "
+                                      'on one GPU')
+        device = require_cuda()
+        it, Dd, xd = mu_streamed(y, to_device2d(D, device, copy=True), to_device2d(x, device, copy=True), float(tol),
+                                 int(maxiter), mask, int(host_block_rows))
+        return it, to_host(Dd, y, np_dtype(y)), to_host(xd, y, np_dtype(y))
     if minibatch is not None:
         return _solve_minibatch(y, D, x, tol, minibatch, maxiter, method, kl, mask, random_seed, group, kwargs)
     if method != 'mu':
@@ -223,6 +236,121 @@ class MuSolver(object):
         ops.normalize_rows(Draw, Dn, False, True, D_ref=D if self.checks else None, tol=self.tol, latch=latch,
                            latch_value=it, maxdiff=self.maxdiff if self.checks else None, scratch=self.scratch,
                            skip=latch)
+
+
+class _PinnedRows(object):
+    """Host rows page-locked in place (cudaHostRegister) for asynchronous block copies; released on close()."""
+
+    def __init__(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.t = torch.from_numpy(a)
+        self.registered = False
+        if not self.t.is_pinned():
+            rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), self.t.numel() * 8, 0)
+            self.registered = int(rc) == 0
+        self.cols = a.shape[1]
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.t.data_ptr())
+            self.registered = False
+
+
+def mu_streamed(y, D0, X, tol, maxiter, mask, block_rows):
+    """Full-batch 'l2' MU with ``y`` / ``mask`` streamed from host memory in row blocks; ``X`` [n, k] and the
+    dictionary stay on the device.  One H2D pass over ``y`` per sweep: the x update and the statistics of a
+    block are both computed while it is resident.  Returns ``(it, D, X)``."""
+    dev = X.device
+    n, f = y.shape
+    k = D0.shape[0]
+    masked = mask is not None
+    rows = max(1, min(block_rows, n))
+    nblk = (n + rows - 1) // rows
+    hy = _PinnedRows(y)
+    hm = _PinnedRows(mask) if masked else None
+    NB = 3
+    ybuf = [empty2d(rows, f, False, dev) for _ in range(NB)]
+    mbuf = [empty2d(rows, f, False, dev) for _ in range(NB)] if masked else None
+    ready = [torch.cuda.Event() for _ in range(NB)]      # block has arrived in ybuf[i]
+    freed = [torch.cuda.Event() for _ in range(NB)]      # compute has finished with ybuf[i]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    E = ops.epilogue
+
+    Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]
+    ops.normalize_rows(D0, Dbuf[0], False, True)
+    Draw, Dt, POS = empty2d(k, f, False, dev), empty2d(f, k, False, dev), empty2d(k, f, False, dev)
+    NEG = empty2d(rows, k, False, dev)
+    ws = ops.gemm_tn_workspace_for([(k, f, rows), (k, k, rows)], dev)
+    if masked:
+        F, YM, NEGD = empty2d(rows, f, False, dev), empty2d(rows, f, False, dev), empty2d(k, f, False, dev)
+    else:
+        G, S = empty2d(k, k, False, dev), empty2d(k, k, False, dev)
+    result = torch.zeros(2, dtype=torch.float64, device=dev)
+    scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def fetch(b, slot, first_use):
+        r0, r1 = b * rows, min(n, (b + 1) * rows)
+        with torch.cuda.stream(copy_stream):
+            if not first_use:
+                copy_stream.wait_event(freed[slot])
+            ybuf[slot][:r1 - r0].copy_(hy.t[r0:r1], non_blocking=True)
+            if masked:
+                mbuf[slot][:r1 - r0].copy_(hm.t[r0:r1], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    try:
+        issued = 0
+        for it in range(1, maxiter):
+            D, Dn = Dbuf[(it - 1) % 2], Dbuf[it % 2]
+            ops.make_rhs(D, False, False, out=Dt)
+            if not masked:
+                ops.gemm_nt(D, D, E(ops.EPI_STORE, G))
+            for b in range(min(NB - 1, nblk)):                       # prefetch
+                fetch(b, issued % NB, issued < NB)
+                issued += 1
+            base = issued - min(NB - 1, nblk)
+            for b in range(nblk):
+                if b + NB - 1 < nblk:
+                    fetch(b + NB - 1, issued % NB, issued < NB)
+                    issued += 1
+                slot = (base + b) % NB
+                r0, r1 = b * rows, min(n, (b + 1) * rows)
+                r = r1 - r0
+                main.wait_event(ready[slot])
+                yb, xb = ybuf[slot][:r], X[r0:r1]
+                comb, beta = (0, 0.0) if b == 0 else (1, 1.0)        # accumulate the statistics over the blocks
+                if not masked:
+                    ops.gemm_nt(xb, G, E(ops.EPI_STORE, NEG[:r]))
+                    ops.gemm_nt(yb, D, E(ops.EPI_MU_NUM, xb, x=xb, other=NEG[:r]))
+                    ops.gemm_tn(xb, yb, POS, combine=comb, beta=beta, workspace=ws)
+                    ops.gemm_tn(xb, xb, S, combine=comb, beta=beta, workspace=ws)
+                else:
+                    mb = mbuf[slot][:r]
+                    ops.mask_mul(yb, mb, YM[:r])
+                    ops.gemm_nt(xb, Dt, E(ops.EPI_STORE_MASK, F[:r], mask=mb))
+                    ops.gemm_nt(F[:r], D, E(ops.EPI_STORE, NEG[:r]))
+                    ops.gemm_nt(YM[:r], D, E(ops.EPI_MU_NUM, xb, x=xb, other=NEG[:r]))
+                    ops.gemm_nt(xb, Dt, E(ops.EPI_STORE_MASK, F[:r], mask=mb))
+                    ops.gemm_tn(xb, YM[:r], POS, combine=comb, beta=beta, workspace=ws)
+                    ops.gemm_tn(xb, F[:r], NEGD, combine=comb, beta=beta, workspace=ws)
+                freed[slot].record(main)
+            if not masked:
+                ops.gemm_nt(S, Dt, E(ops.EPI_MU_DEN, Draw, x=D, other=POS))
+            else:
+                ops.mu_update(D, POS, NEGD, Draw)
+            ops.normalize_rows(Draw, Dn, False, True)
+            if tol > 0.0:
+                ops.max_abs_diff(D, Dn, False, result, scratch)
+                if float(result[1].item()) < tol:
+                    return it, Dn, X
+        torch.cuda.synchronize(dev)
+        return maxiter, Dbuf[max(maxiter - 1, 0) % 2], X
+    finally:
+        torch.cuda.synchronize(dev)
+        hy.close()
+        if hm is not None:
+            hm.close()
 
 
 def _allreduce2d(t, group):

@@ -192,3 +192,18 @@ def test_nnls_wrapper():
     it, x = nnls.solve(case['y'], case['A'], case['alpha'], tol=case['tol'], method='fista', maxiter=case['maxiter'])
     assert it == int(g['it'])
     assert_close(x, g['x'], what='x')
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_nmf_streamed_from_host_matches_resident(masked):
+    """Out-of-core mode (host-resident y streamed in row blocks) against the oracle."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(1003, 130, 24, 12)
+    m = mask if masked else None
+    it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=1e-4, maxiter=300, mask=m)
+    for block in (128, 400, 5000):
+        it, D, x = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=300, mask=m, host_block_rows=block)
+        assert it == it0
+        assert_close(D, D_ref, what='D')
+        assert_close(x, x_ref, what='x')
