@@ -137,6 +137,26 @@ __global__ void atom_weighted_kernel(const double* __restrict__ X, long long ldx
   }
 }
 
+// S[b][j][a] = conj(S[a][j][b]) for b > a: the masked statistics are Hermitian in (a, b), so only b >= a is
+// accumulated by the GEMMs and the rest is mirrored.  One block per (a, j) row, contiguous reads, strided writes.
+template <bool CPLX>
+__global__ void dl_mirror_kernel(double* __restrict__ S, int k, int f) {
+  constexpr int CW = CPLX ? 2 : 1;
+  const long long row = blockIdx.x;              // a * f + j
+  const int a = (int)(row / f);
+  const long long j = row % f;
+  const double* src = S + row * (long long)k * CW;
+  for (int b = a + 1 + threadIdx.x; b < k; b += blockDim.x) {
+    double* dst = S + (((long long)b * f + j) * k + a) * CW;
+    if (CPLX) {
+      const double2 v = *reinterpret_cast<const double2*>(src + 2 * b);
+      *reinterpret_cast<double2*>(dst) = make_double2(v.x, -v.y);
+    } else {
+      dst[0] = src[b];
+    }
+  }
+}
+
 // Dt[j][b] = D[b][j]  (elements are complex pairs when CPLX)
 template <bool CPLX>
 __global__ void transpose_elems_kernel(const double* __restrict__ D, long long ldd, int k, int f,
@@ -283,6 +303,21 @@ int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int6
   else
     atom_weighted_kernel<false><<<(unsigned)b, 256, 0, as_stream(stream)>>>(X, ldx, rows, (int)k, (int)atom, W, ldw);
   DCP_CHECK_LAUNCH("dl_atom_weighted");
+  return DECOMP_OK;
+}
+
+int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, void* stream) {
+  if (k <= 1 || f <= 0) return DECOMP_OK;
+  const long long blocks = (long long)(k - 1) * f;   // the last atom has nothing to mirror
+  if (blocks > 2147483647LL) {
+    set_error("decomp_dl_mirror_f64: too many rows");
+    return DECOMP_ERR_INVALID;
+  }
+  if (is_complex)
+    dl_mirror_kernel<true><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(S, (int)k, (int)f);
+  else
+    dl_mirror_kernel<false><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(S, (int)k, (int)f);
+  DCP_CHECK_LAUNCH("dl_mirror");
   return DECOMP_OK;
 }
 

@@ -129,7 +129,8 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
         W = empty2d(minibatch, k, cplx, dev)
         YM = empty2d(minibatch, f, cplx, dev)
         Dt_ws = torch.empty(f * k * cw, dtype=torch.float64, device=dev)
-        ws = ops.gemm_tn_workspace_for([(f, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
+        ws = ops.gemm_tn_workspace_for([(f, (k - a) * cw, minibatch) for a in range(k)] +
+                                       [(k * cw, f * cw, minibatch)], dev)
     else:
         S = zeros2d(k, k, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
@@ -187,10 +188,13 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                     ops.gemm_tn(xr, xr, rview(S_dst), combine=comb, beta=beta, workspace=ws)           # :151
                     ops.gemm_tn(xr, rview(y_mb[lo:hi]), rview(T_dst), combine=comb, beta=beta, workspace=ws)
                 else:
+                    # S[a][j][b] = sum_i conj(x_ia) x_ib m_ij is Hermitian in (a, b): accumulate b >= a, mirror the rest
                     for a in range(k):                                                                 # :210-213
-                        ops.dl_atom_weighted(xr, cplx, a, rview(W[:rows]))
-                        ops.gemm_tn(m_mb[lo:hi], rview(W[:rows]), S_dst[a], combine=1 if dist is None else 0,
+                        Wa = rview(W[:rows, :k - a])
+                        ops.dl_atom_weighted(xr[:, a * cw:], cplx, 0, Wa)
+                        ops.gemm_tn(m_mb[lo:hi], Wa, S_dst[a][:, a * cw:], combine=1 if dist is None else 0,
                                     beta=beta, workspace=ws)
+                    ops.dl_mirror(S_dst, k, f, cplx)
                     ops.mask_mul(rview(y_mb[lo:hi]), m_mb[lo:hi], rview(YM[:rows]), cwidth=cw)
                     ops.gemm_tn(xr, rview(YM[:rows]), rview(T_dst), combine=comb, beta=beta, workspace=ws)  # :214
                 if dist is not None:

@@ -216,6 +216,14 @@ def dl_atom_weighted(X, is_complex, atom, W):
     return W
 
 
+def dl_mirror(S, k, f, is_complex):
+    """Fill S[b][j][a] = conj(S[a][j][b]) for b > a (S: contiguous [k, f, k*cw] doubles)."""
+    rc = _lib.lib().decomp_dl_mirror_f64(_p(S), k, f, int(is_complex), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_mirror_f64')
+    _count(1)
+    return S
+
+
 def dl_masked_update(S, T, D, D_out, is_complex, workspace):
     cw = 2 if is_complex else 1
     k, f = D.shape[0], D.shape[1] // cw

@@ -207,6 +207,9 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
  * A = Mask, out = S[a].  Internal layout of S is [k][f][k*cw] doubles (never returned to the user). */
 int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int64_t k, int32_t is_complex,
                                 int64_t atom, double* W, int64_t ldw, void* stream);
+/* S[b][j][a] = conj(S[a][j][b]) for b > a on the [k][f][k*cw] tensor: the statistics of dictionary_learning.py:210-213
+ * are Hermitian in (a, b), so the GEMMs accumulate b >= a only (half the flops) and this fills in the rest. */
+int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, void* stream);
 /* Masked Jacobi atom update, dictionary_learning.py:216-222:
  *   SaD[j] = sum_b S[a][j][b] D[b][j];  Saa = sum_j (S[a][j][a] + eps);  u = (T[a] - SaD)/Saa + D[a];  l2(u)
  * `workspace` holds the transposed dictionary: f * k * cw doubles. */
