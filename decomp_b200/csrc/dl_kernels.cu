@@ -137,6 +137,51 @@ __global__ void atom_weighted_kernel(const double* __restrict__ X, long long ldx
   }
 }
 
+// Pair products of several atoms side by side, so that one full-width GEMM produces the statistics of all of them.
+// Transposed form for the NT GEMM (contraction index contiguous): Xt is the transposed real view of the codes,
+// Xt[b*cw + part][i]; Wt[c*cw + part][i] = (conj(x_i,colA[c]) x_i,colB[c]).part -- coalesced along the rows i.
+template <bool CPLX>
+__global__ void pair_products_t_kernel(const double* __restrict__ Xt, long long ldx, long long rows,
+                                       const int* __restrict__ colA, const int* __restrict__ colB, int width,
+                                       double* __restrict__ Wt, long long ldw) {
+  const int c = blockIdx.y;
+  const int a = __ldg(colA + c), b = __ldg(colB + c);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    if (CPLX) {
+      const double ar = Xt[(2LL * a) * ldx + i], ai = Xt[(2LL * a + 1) * ldx + i];
+      const double br = Xt[(2LL * b) * ldx + i], bi = Xt[(2LL * b + 1) * ldx + i];
+      Wt[(2LL * c) * ldw + i] = ar * br + ai * bi;
+      Wt[(2LL * c + 1) * ldw + i] = ar * bi - ai * br;
+    } else {
+      Wt[(long long)c * ldw + i] = Xt[(long long)a * ldx + i] * Xt[(long long)b * ldx + i];
+    }
+  }
+}
+
+// S[colA[c]][j][colB[c]] = beta * S[...] + P[j][c]
+template <bool CPLX>
+__global__ void scatter_stats_kernel(const double* __restrict__ P, long long ldp, int f, int width,
+                                     const int* __restrict__ colA, const int* __restrict__ colB, int k, double beta,
+                                     double* __restrict__ S) {
+  constexpr int CW = CPLX ? 2 : 1;
+  const long long total = (long long)f * width;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long j = idx / width;
+    const int c = (int)(idx % width);
+    const int a = __ldg(colA + c), b = __ldg(colB + c);
+    double* dst = S + (((long long)a * f + j) * k + b) * CW;
+    const double* src = P + j * ldp + (long long)c * CW;
+    if (CPLX) {
+      const double2 o = *reinterpret_cast<const double2*>(dst);
+      const double2 v = *reinterpret_cast<const double2*>(src);
+      *reinterpret_cast<double2*>(dst) = make_double2(beta * o.x + v.x, beta * o.y + v.y);
+    } else {
+      dst[0] = beta * dst[0] + src[0];
+    }
+  }
+}
+
 // S[b][j][a] = conj(S[a][j][b]) for b > a: the masked statistics are Hermitian in (a, b), so only b >= a is
 // accumulated by the GEMMs and the rest is mirrored.  One block per (a, j) row, contiguous reads, strided writes.
 template <bool CPLX>
@@ -303,6 +348,37 @@ int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int6
   else
     atom_weighted_kernel<false><<<(unsigned)b, 256, 0, as_stream(stream)>>>(X, ldx, rows, (int)k, (int)atom, W, ldw);
   DCP_CHECK_LAUNCH("dl_atom_weighted");
+  return DECOMP_OK;
+}
+
+int decomp_dl_pair_products_t_f64(const double* Xt, int64_t ldx, int64_t rows, int32_t is_complex, const int32_t* colA,
+                                  const int32_t* colB, int64_t width, double* Wt, int64_t ldw, void* stream) {
+  if (rows <= 0 || width <= 0) return DECOMP_OK;
+  long long bx = (rows + 255) / 256;
+  if (bx > 64) bx = 64;
+  dim3 grid((unsigned)bx, (unsigned)width);
+  if (is_complex)
+    pair_products_t_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(Xt, ldx, rows, colA, colB, (int)width, Wt, ldw);
+  else
+    pair_products_t_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(Xt, ldx, rows, colA, colB, (int)width, Wt, ldw);
+  DCP_CHECK_LAUNCH("dl_pair_products_t");
+  return DECOMP_OK;
+}
+
+int decomp_dl_scatter_stats_f64(const double* P, int64_t ldp, int64_t f, int64_t width, int32_t is_complex,
+                                const int32_t* colA, const int32_t* colB, int64_t k, double beta, double* S,
+                                void* stream) {
+  if (f <= 0 || width <= 0) return DECOMP_OK;
+  long long b = (f * width + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (is_complex)
+    scatter_stats_kernel<true><<<(unsigned)b, 256, 0, as_stream(stream)>>>(P, ldp, (int)f, (int)width, colA, colB, (int)k,
+                                                                           beta, S);
+  else
+    scatter_stats_kernel<false><<<(unsigned)b, 256, 0, as_stream(stream)>>>(P, ldp, (int)f, (int)width, colA, colB, (int)k,
+                                                                            beta, S);
+  DCP_CHECK_LAUNCH("dl_scatter_stats");
   return DECOMP_OK;
 }
 

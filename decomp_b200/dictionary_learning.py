@@ -81,6 +81,19 @@ def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method=
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
+PAIR_COLS = 512   # (atom, b) pairs per statistics GEMM: wide enough for full GEMM efficiency
+
+
+def _pair_chunks(k, cap, device):
+    """[(colA, colB)] int32 device vectors listing the pairs (a, b >= a) in row-major order, ~cap pairs each."""
+    a_idx, b_idx = np.triu_indices(k)
+    out = []
+    for s0 in range(0, a_idx.size, cap):
+        out.append((torch.from_numpy(a_idx[s0:s0 + cap].astype(np.int32)).to(device),
+                    torch.from_numpy(b_idx[s0:s0 + cap].astype(np.int32)).to(device)))
+    return out
+
+
 class _ShuffledRows(object):
     """Device rows under the reference's cumulative shuffle (utils/data.py:124-156): two owned buffers are
     used alternately as gather targets; the caller's array is only ever read."""
@@ -126,11 +139,16 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
     T = zeros2d(k, f, cplx, dev)
     if masked:
         S = torch.zeros((k, f, k * cw), dtype=torch.float64, device=dev)      # [k][f][k] (interleaved complex)
-        W = empty2d(minibatch, k, cplx, dev)
         YM = empty2d(minibatch, f, cplx, dev)
         Dt_ws = torch.empty(f * k * cw, dtype=torch.float64, device=dev)
-        ws = ops.gemm_tn_workspace_for([(f, (k - a) * cw, minibatch) for a in range(k)] +
-                                       [(k * cw, f * cw, minibatch)], dev)
+        # the (atom a, b >= a) pairs of the Hermitian half of S, packed into GEMMs of ~PAIR_COLS columns each
+        chunks = _pair_chunks(k, PAIR_COLS, dev)
+        widest = max(c[0].numel() for c in chunks)
+        Wt = empty2d(widest * cw, minibatch, False, dev)     # transposed pair products: contraction index contiguous
+        Xt = empty2d(k * cw, minibatch, False, dev)          # transposed codes and mask of the minibatch
+        Mt = empty2d(f, minibatch, False, dev)
+        Ptmp = empty2d(f, widest, cplx, dev)
+        ws = ops.gemm_tn_workspace_for([(k * cw, f * cw, minibatch)], dev)
     else:
         S = zeros2d(k, k, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
@@ -189,11 +207,15 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                     ops.gemm_tn(xr, rview(y_mb[lo:hi]), rview(T_dst), combine=comb, beta=beta, workspace=ws)
                 else:
                     # S[a][j][b] = sum_i conj(x_ia) x_ib m_ij is Hermitian in (a, b): accumulate b >= a, mirror the rest
-                    for a in range(k):                                                                 # :210-213
-                        Wa = rview(W[:rows, :k - a])
-                        ops.dl_atom_weighted(xr[:, a * cw:], cplx, 0, Wa)
-                        ops.gemm_tn(m_mb[lo:hi], Wa, S_dst[a][:, a * cw:], combine=1 if dist is None else 0,
-                                    beta=beta, workspace=ws)
+                    # as NT GEMMs  mask^T [f, rows] . Wt [pairs, rows]^T  (the NT kernel is the faster one)
+                    ops.make_rhs(xr, False, False, out=Xt[:, :rows])
+                    ops.make_rhs(m_mb[lo:hi], False, False, out=Mt[:, :rows])
+                    for colA, colB in chunks:                                                          # :210-213
+                        wd = colA.numel()
+                        Wc, Pc = Wt[:wd * cw, :rows], rview(Ptmp[:, :wd])
+                        ops.dl_pair_products_t(Xt[:, :rows], cplx, colA, colB, Wc)
+                        ops.gemm_nt(Mt[:, :rows], Wc, ops.epilogue(ops.EPI_STORE, Pc))
+                        ops.dl_scatter_stats(Pc, cplx, colA, colB, k, beta if dist is None else 0.0, S_dst)
                     ops.dl_mirror(S_dst, k, f, cplx)
                     ops.mask_mul(rview(y_mb[lo:hi]), m_mb[lo:hi], rview(YM[:rows]), cwidth=cw)
                     ops.gemm_tn(xr, rview(YM[:rows]), rview(T_dst), combine=comb, beta=beta, workspace=ws)  # :214

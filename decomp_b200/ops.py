@@ -216,6 +216,26 @@ def dl_atom_weighted(X, is_complex, atom, W):
     return W
 
 
+def dl_pair_products_t(Xt, is_complex, colA, colB, Wt):
+    """Wt[c*cw + part, :] = parts of conj(x[:, colA[c]]) * x[:, colB[c]], from the transposed real view Xt of x."""
+    rows, width = Xt.shape[1], colA.numel()
+    rc = _lib.lib().decomp_dl_pair_products_t_f64(_p(Xt), ld(Xt), rows, int(is_complex), _p(colA), _p(colB), width,
+                                                  _p(Wt), ld(Wt), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_pair_products_t_f64')
+    _count(1)
+    return Wt
+
+
+def dl_scatter_stats(P, is_complex, colA, colB, k, beta, S):
+    """S[colA[c], j, colB[c]] = beta * S[...] + P[j, c]  (S: contiguous [k, f, k*cw] doubles)."""
+    f, width = P.shape[0], colA.numel()
+    rc = _lib.lib().decomp_dl_scatter_stats_f64(_p(P), ld(P), f, width, int(is_complex), _p(colA), _p(colB), k,
+                                                float(beta), _p(S), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_scatter_stats_f64')
+    _count(1)
+    return S
+
+
 def dl_mirror(S, k, f, is_complex):
     """Fill S[b][j][a] = conj(S[a][j][b]) for b > a (S: contiguous [k, f, k*cw] doubles)."""
     rc = _lib.lib().decomp_dl_mirror_f64(_p(S), k, f, int(is_complex), _lib.stream_ptr())

@@ -207,6 +207,15 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
  * A = Mask, out = S[a].  Internal layout of S is [k][f][k*cw] doubles (never returned to the user). */
 int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int64_t k, int32_t is_complex,
                                 int64_t atom, double* W, int64_t ldw, void* stream);
+/* Masked statistics of several atoms per GEMM (dictionary_learning.py:210-213): for `width` (atom a, b >= a) pairs
+ * Wt[c*cw + part][i] = (conj(x[i][colA[c]]) x[i][colB[c]]).part, from the transposed real view Xt of the codes
+ * (Xt[b*cw + part][i]); the caller runs the NT GEMM  mask^T[f, rows] . Wt^T -> P [f, width*cw]  and then
+ * S[colA[c]][j][colB[c]] = beta * S[..] + P[j][c].  colA / colB: device int32 vectors. */
+int decomp_dl_pair_products_t_f64(const double* Xt, int64_t ldx, int64_t rows, int32_t is_complex, const int32_t* colA,
+                                  const int32_t* colB, int64_t width, double* Wt, int64_t ldw, void* stream);
+int decomp_dl_scatter_stats_f64(const double* P, int64_t ldp, int64_t f, int64_t width, int32_t is_complex,
+                                const int32_t* colA, const int32_t* colB, int64_t k, double beta, double* S,
+                                void* stream);
 /* S[b][j][a] = conj(S[a][j][b]) for b > a on the [k][f][k*cw] tensor: the statistics of dictionary_learning.py:210-213
  * are Hermitian in (a, b), so the GEMMs accumulate b >= a only (half the flops) and this fills in the rest. */
 int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, void* stream);

@@ -387,3 +387,41 @@ def test_dl_masked_stats_and_update(cplx, k, f, mb):
     ops.dl_masked_update(dS_r, rv(dev(T)), rv(dev(D)), rv(dOut), cplx, ws)
     torch.cuda.synchronize()
     close(host(dOut), Dn, 1e-10)
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('k,f,mb', [(3, 5, 20), (9, 33, 70)])
+def test_dl_packed_masked_stats(cplx, k, f, mb):
+    """Hermitian half of S via transposed pair products + NT GEMM + scatter, then mirrored
+    (dictionary_learning.py:210-213)."""
+    from decomp_b200 import ops
+    from decomp_b200._device import empty2d
+    from decomp_b200.dictionary_learning import _pair_chunks
+    rng = np.random.RandomState(k * f + mb)
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    X = randn(mb, k)
+    mask = np.rint(rng.uniform(0.3, 1, size=(mb, f)))
+    S0 = randn(k, f, k)
+    S0 = 0.5 * (S0 + np.conj(np.transpose(S0, (2, 1, 0))))          # Hermitian in (a, b) like the real statistics
+    beta = 0.3
+    S_ref = beta * S0 + np.tensordot(np.conj(X.T), np.expand_dims(X, -2) * np.expand_dims(mask, -1), axes=1)
+    cw = 2 if cplx else 1
+    dX, dM = dev(X), dev(mask)
+    dS = torch.from_numpy(np.ascontiguousarray(S0)).cuda()
+    dS_r = torch.view_as_real(dS).reshape(k, f, k * 2) if cplx else dS
+    Xt, Mt = empty2d(k * cw, mb, False, 'cuda'), empty2d(f, mb, False, 'cuda')
+    ops.make_rhs(rv(dX), False, False, out=Xt)
+    ops.make_rhs(dM, False, False, out=Mt)
+    for colA, colB in _pair_chunks(k, 7, 'cuda'):
+        wd = colA.numel()
+        Wt = empty2d(wd * cw, mb, False, 'cuda')
+        P = empty2d(f, wd, cplx, 'cuda')
+        ops.dl_pair_products_t(Xt, cplx, colA, colB, Wt)
+        ops.gemm_nt(Mt, Wt, ops.epilogue(ops.EPI_STORE, rv(P)))
+        ops.dl_scatter_stats(rv(P), cplx, colA, colB, k, beta, dS_r)
+    ops.dl_mirror(dS_r, k, f, cplx)
+    torch.cuda.synchronize()
+    close(host(dS), S_ref)

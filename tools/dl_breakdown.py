@@ -42,3 +42,15 @@ timed('masked stats, 16 of 512 atoms', masked_stats)
 Dt_ws = torch.empty(f * k * 2, dtype=torch.float64, device=dev)
 Do = empty2d(k, f, True, dev)
 timed('dl_masked_update (streams 8.6 GB)', lambda: ops.dl_masked_update(Sb, rview(T), rview(D), rview(Do), True, Dt_ws))
+# ---- pieces of the packed masked statistics
+from decomp_b200.dictionary_learning import _pair_chunks
+chunks = _pair_chunks(k, 512, dev)
+colA, colB = chunks[3]
+Xt = empty2d(2 * k, mb, False, dev); Mt = empty2d(f, mb, False, dev)
+Wt = empty2d(1024, mb, False, dev); Pt = empty2d(f, 512, True, dev)
+timed('transpose x', lambda: ops.make_rhs(xr, False, False, out=Xt))
+timed('transpose mask', lambda: ops.make_rhs(mask, False, False, out=Mt))
+timed('pair_products_t (512 pairs)', lambda: ops.dl_pair_products_t(Xt, True, colA, colB, Wt))
+timed('NT gemm f x 1024, K=8192', lambda: ops.gemm_nt(Mt, Wt, ops.epilogue(ops.EPI_STORE, rview(Pt))))
+timed('scatter_stats', lambda: ops.dl_scatter_stats(rview(Pt), True, colA, colB, k, 0.5, Sb))
+timed('mirror', lambda: ops.dl_mirror(Sb, k, f, True))

@@ -20,7 +20,7 @@ for (M, N, K) in [(131072, 256, 4096), (100000, 256, 256), (400000, 256, 256), (
     ms = timeit(lambda: ops.gemm_nt(A, B, ops.epilogue(ops.EPI_STORE, out)))
     print('NT store M=%d N=%d K=%d: %.3f ms %.2f TF/s' % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
     del A, B, out
-for (K, M, N) in [(131072, 256, 4096), (1000000, 256, 256)]:
+for (K, M, N) in [(131072, 256, 4096), (1000000, 256, 256), (8192, 2048, 1024), (8192, 1024, 4096), (8192, 1024, 1024)]:
     A = torch.randn((K, M), dtype=torch.float64, device=dev)
     B = torch.randn((K, N), dtype=torch.float64, device=dev)
     out = empty2d(M, N)
