@@ -81,7 +81,18 @@ def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method=
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
-PAIR_COLS = 512   # (atom, b) pairs per statistics GEMM: wide enough for full GEMM efficiency
+def _pair_cols(f, cw, device):
+    """(atom, b) pairs per statistics GEMM: the [f, pairs*cw] output is cut into 128x64 tiles that a persistent grid
+    of one CTA per SM walks in rounds, so pick the width whose tile count fills whole rounds best."""
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    tiles_m = (f + 127) // 128
+    best, best_eff = 8, 0.0
+    for tiles_n in range(8, 65):
+        tiles = tiles_m * tiles_n
+        eff = tiles / float(-(-tiles // sms) * sms)
+        if eff > best_eff + 1e-9:
+            best, best_eff = tiles_n, eff
+    return best * 64 // cw
 
 
 def _pair_chunks(k, cap, device):
@@ -141,8 +152,8 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
         S = torch.zeros((k, f, k * cw), dtype=torch.float64, device=dev)      # [k][f][k] (interleaved complex)
         YM = empty2d(minibatch, f, cplx, dev)
         Dt_ws = torch.empty(f * k * cw, dtype=torch.float64, device=dev)
-        # the (atom a, b >= a) pairs of the Hermitian half of S, packed into GEMMs of ~PAIR_COLS columns each
-        chunks = _pair_chunks(k, PAIR_COLS, dev)
+        # the (atom a, b >= a) pairs of the Hermitian half of S, packed into wide GEMMs
+        chunks = _pair_chunks(k, _pair_cols(f, cw, dev), dev)
         widest = max(c[0].numel() for c in chunks)
         Wt = empty2d(widest * cw, minibatch, False, dev)     # transposed pair products: contraction index contiguous
         Xt = empty2d(k * cw, minibatch, False, dev)          # transposed codes and mask of the minibatch
