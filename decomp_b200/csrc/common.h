@@ -18,6 +18,11 @@ int num_sms();
 int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64_t outer, uint64_t ld,
                     uint32_t box_inner, uint32_t box_outer);
 
+// TN operand [K rows][W columns] (W % 16 == 0) seen as the 3-D tensor {16, K, W/16}: one box {16, 16, blocks} lands in
+// shared memory as [block][k][16 doubles] with the 128-byte swizzle -- the TN tile layout -- in ONE instruction.
+int make_tensor_map_tn3d(CUtensorMap* map, const double* base, uint64_t width, uint64_t rows, uint64_t ld,
+                         uint32_t blocks);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace dcp

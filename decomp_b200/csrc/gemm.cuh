@@ -44,6 +44,7 @@ struct GemmGeom {
   long long M, N, K;
   int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
   long long ld_partial;  // TN: leading dimension of one partial slab (even)
+  int tn3d;              // TN: operands are described by 3-D tensor maps (one TMA instruction per operand)
 };
 
 template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int NBUF_, int EPI_WARPS_, int EPI_BATCH_>
@@ -358,6 +359,9 @@ struct MmaPipe {
     if constexpr (!TN) {
       tma_load_2d(sa, tmA, &full_bar[p_stage], k0, p_t.m0);
       tma_load_2d(sb, tmB, &full_bar[p_stage], k0, p_t.n0);
+    } else if (gs->tn3d) {
+      tma_load_3d(sa, tmA, &full_bar[p_stage], 0, k0, p_t.m0 / 16);
+      tma_load_3d(sb, tmB, &full_bar[p_stage], 0, k0, p_t.n0 / 16);
     } else {
 #pragma unroll
       for (int b = 0; b < C::BM / 16; ++b) tma_load_2d(sa + b * 2048, tmA, &full_bar[p_stage], p_t.m0 + 16 * b, k0);

@@ -77,6 +77,24 @@ int make_tensor_map(CUtensorMap* map, const double* base, uint64_t inner, uint64
   return DECOMP_OK;
 }
 
+int make_tensor_map_tn3d(CUtensorMap* map, const double* base, uint64_t width, uint64_t rows, uint64_t ld,
+                         uint32_t blocks) {
+  auto enc = get_encode();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DECOMP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld & 1u) != 0 || (width & 15u) != 0) return DECOMP_ERR_INVALID;
+  cuuint64_t gdim[3] = {16, rows, width / 16};
+  cuuint64_t gstride[2] = {ld * sizeof(double), 16 * sizeof(double)};
+  cuuint32_t box[3] = {16, BK, blocks};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DECOMP_OK : DECOMP_ERR_UNSUPPORTED;
+}
+
 // CTA tile 128x64: 8 MMA warps of 32x32, 4 epilogue warps (batches of 4 column pairs per thread), 3-stage operand
 // ring (72 KB) + two 72 KB accumulator staging buffers = 216 KB -> one persistent CTA per SM.
 using CfgMain = GemmCfg<128, 64, 32, 32, 3, 2, 4, 4>;
@@ -192,6 +210,7 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
   gs.kblocks_total = (int)((K + BK - 1) / BK);
   gs.kblocks_per_split = gs.kblocks_total;
   gs.ld_partial = 0;
+  gs.tn3d = 0;
   cudaStream_t st = as_stream(stream);
   switch (epi->kind) {
     case DECOMP_EPI_STORE:
@@ -281,10 +300,24 @@ int decomp_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ld
     return DECOMP_ERR_INVALID;
   }
   CUtensorMap ta, tb;
-  int rc = make_tensor_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, BK);
-  if (rc != DECOMP_OK) return rc;
-  rc = make_tensor_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 16, BK);
-  if (rc != DECOMP_OK) return rc;
+  int rc;
+  // one 3-D TMA instruction per operand and k-block when both widths are multiples of 16, else 16x16 boxes
+  static int allow3d = -1;
+  if (allow3d < 0) {
+    const char* e = getenv("DECOMP_GEMM_TN3D");
+    allow3d = e != nullptr ? atoi(e) : 1;
+  }
+  gs.tn3d = 0;
+  if (allow3d && (M % 16) == 0 && (N % 16) == 0 &&
+      make_tensor_map_tn3d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, C::BM / 16) == DECOMP_OK &&
+      make_tensor_map_tn3d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, C::BN / 16) == DECOMP_OK) {
+    gs.tn3d = 1;
+  } else {
+    rc = make_tensor_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 16, BK);
+    if (rc != DECOMP_OK) return rc;
+    rc = make_tensor_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 16, BK);
+    if (rc != DECOMP_OK) return rc;
+  }
   cudaStream_t st = as_stream(stream);
   decomp_epilogue_t ep;
   memset(&ep, 0, sizeof(ep));
