@@ -343,13 +343,18 @@ struct MmaPipe {
     }
   }
 
-  // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
-  __device__ __forceinline__ void produce_one() {
+  // moves the producer cursor to the next k-block that exists (skips past the end of a tile)
+  __device__ __forceinline__ void advance_cursor() {
     while (p_tile < tiles_total && p_i >= p_t.nkb) {
       p_tile += gridDim.x;
       p_i = 0;
       if (p_tile < tiles_total) p_t = tile_info(*gs, tiles_mn, p_tile, C::BM, C::BN);
     }
+  }
+
+  // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
+  __device__ __forceinline__ void produce_one() {
+    advance_cursor();
     if (p_tile >= tiles_total) return;
     if (p_wait) mbar_wait(&empty_bar[p_stage], p_phase);
     mbar_arrive_expect_tx(&full_bar[p_stage], C::STAGE_BYTES);
@@ -612,11 +617,11 @@ template <class C>
 struct ProxqSmem {
   static constexpr int OPND_BYTES = C::BM * C::BN * 8;
   static constexpr int BOX_BYTES = C::BM * 128;          // one TMA box: BM rows x 16 doubles, 128-byte swizzle
-  static constexpr int SMEM_BYTES = C::RING_BYTES + 2 * OPND_BYTES + (2 * C::STAGES + 1) * 8;
+  static constexpr int SMEM_BYTES = C::RING_BYTES + 2 * OPND_BYTES + (2 * C::STAGES + 2) * 8;
 };
 
 template <class C, int EPI>
-__global__ void __launch_bounds__(C::MMA_THREADS, 1)
+__global__ void __launch_bounds__(C::MMA_THREADS + 128, 1)
 gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP,
                       const GemmGeom gs, const decomp_epilogue_t ep, const int* __restrict__ skip_if) {
@@ -628,7 +633,8 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   unsigned char* opnd_p = opnd_c + S::OPND_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(opnd_p + S::OPND_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* opnd_bar = empty_bar + C::STAGES;
+  uint64_t* opnd_bar = empty_bar + C::STAGES;   // operand tiles of the current tile have landed
+  uint64_t* opnd_free = opnd_bar + 1;            // every MMA warp is done with them
 
   const int tiles_mn = gs.tiles_m * gs.tiles_n;
   const int tiles_total = tiles_mn * gs.splits;
@@ -639,6 +645,7 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&empty_bar[s], C::MMA_WARPS);
     }
     mbar_init(opnd_bar, 1);
+    mbar_init(opnd_free, C::MMA_WARPS);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -659,133 +666,168 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   };
 
-  MmaPipe<C, false> pipe;
-  pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
-  pipe.fill_ring();
-  const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
-
-  double step = 0.0;
-  if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) step = *ep.step;
   bool violated = false;
-  uint32_t opnd_phase = 0;
-#pragma unroll 1
-  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-    const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
-    double acc[C::MI][C::NJ][2];
-    // the previous tile's update has released the operand buffers (__syncthreads at the end of the loop body)
-    pipe.run(t, acc, [&](int it) {
-      if (it < 2 * NBOX) request_box(t, it);
-    });
-    if (pipe.elected) {
-      for (int b = t.nkb < 0 ? 0 : t.nkb; b < 2 * NBOX; ++b) request_box(t, b);   // short contractions: the rest
-    }
-
-    mbar_wait(opnd_bar, opnd_phase);
-    opnd_phase ^= 1u;
-
-    // per-column vectors of this lane's NJ column pairs: threshold step * alpha (lasso.py:287) and tolerance
-    // tol * s as bit patterns (lasso.py:130); columns beyond N get harmless zeros and are never stored
-    const long long col_lane = (long long)t.n0 + wn * C::WN + 2 * q;
-    double thr0[C::NJ], thr1[C::NJ];
-    unsigned long long tolb0[C::NJ], tolb1[C::NJ];
-#pragma unroll
-    for (int j = 0; j < C::NJ; ++j) {
-      const long long col = col_lane + 8 * j;
-      thr0[j] = thr1[j] = 0.0;
-      tolb0[j] = tolb1[j] = 0ull;
-      if (col < gs.N) {
-        if constexpr (EPI == EPI_PROX_COMPLEX) {
-          thr0[j] = thr1[j] = __ldg(ep.colvec + (col >> 1));
-          if (ep.check) tolb0[j] = (unsigned long long)__double_as_longlong(__ldg(ep.colvec2 + (col >> 1)));
-        } else {
-          const double2 a = __ldg(reinterpret_cast<const double2*>(ep.colvec + col));   // padded to even
-          thr0[j] = a.x;
-          thr1[j] = a.y;
-          if (ep.check) {
-            const double2 tl = __ldg(reinterpret_cast<const double2*>(ep.colvec2 + col));
-            tolb0[j] = (unsigned long long)__double_as_longlong(tl.x);
-            tolb1[j] = (unsigned long long)__double_as_longlong(tl.y);
+  if (threadIdx.x >= C::MMA_THREADS) {
+    // ================================================================ producer warp group (one active thread)
+    // A dedicated TMA thread: with the elected-MMA-thread scheme that thread's warp falls behind the other seven
+    // by the time it spends waiting for `empty` slots and issuing copies, and everybody waits for it at the next
+    // refill.  The group gives its registers to the MMA warps (setmaxnreg).
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (threadIdx.x == C::MMA_THREADS) {
+      MmaPipe<C, false> prod;
+      prod.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
+      uint32_t free_phase = 0;
+      bool free_wait = false;       // the operand tiles have not been used yet
+      for (;;) {
+        prod.advance_cursor();
+        if (prod.p_tile >= tiles_total) break;
+        const int i = prod.p_i;
+        const TileInfo t = prod.p_t;
+        prod.produce_one();
+        {
+          // k-block i of that tile is on its way; trickle that tile's operand boxes behind k-blocks STAGES, STAGES+1, ...
+          // (by then the MMA warps have started this tile, i.e. finished the previous tile's update)
+          int b0 = i - C::STAGES, b1 = b0 + 1;
+          if (i == t.nkb - 1) b1 = 2 * NBOX;                    // last k-block: whatever is left
+          if (b0 < 0) b0 = 0;
+          for (int b = b0; b < b1 && b < 2 * NBOX; ++b) {
+            if (b == 0) {
+              if (free_wait) {
+                mbar_wait(opnd_free, free_phase);
+                free_phase ^= 1u;
+              }
+              free_wait = true;
+            }
+            request_box(t, b);
           }
         }
-        if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) {
-          thr0[j] = step * thr0[j];
-          thr1[j] = step * thr1[j];
-        }
       }
     }
+  } else {
+    // ================================================================ MMA warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    MmaPipe<C, false> pipe;
+    pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
+    pipe.elected = false;   // the producer group owns the ring
+    const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
 
-    // fragment walk: row r = wm*WM + g + 8 i (so r & 7 == g), column c = wn*WN + 8 j + 2 q inside the tile
-    const long long row_lane = (long long)t.m0 + wm * C::WM + g;
-    const int c_lane = wn * C::WN + 2 * q;
-    const unsigned char* sc = opnd_c + (wm * C::WM + g) * 128;
-    const unsigned char* sp = opnd_p + (wm * C::WM + g) * 128;
-    double* po = ep.out + row_lane * ep.ldo + col_lane;
-    double* pw = ep.out2 != nullptr ? ep.out2 + row_lane * ep.ldo2 + col_lane : nullptr;
-    const bool interior = (long long)t.m0 + C::BM <= gs.M && (long long)t.n0 + C::BN <= gs.N;
-    const double mom = ep.momentum;
+    double step = 0.0;
+    if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) step = *ep.step;
+    uint32_t opnd_phase = 0;
+  #pragma unroll 1
+    for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+      const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
+      double acc[C::MI][C::NJ][2];
+        pipe.run(t, acc, [](int) {});
 
-    auto update = [&](int i, int j, bool store, bool two) {
-      const int c = c_lane + 8 * j;
-      const int off = (c >> 4) * S::BOX_BYTES + i * 1024 + ((((c & 15) >> 1) ^ g) << 4);
-      const double2 cc = *reinterpret_cast<const double2*>(sc + off);
-      const double2 pp = *reinterpret_cast<const double2*>(sp + off);
-      const double z0 = acc[i][j][0] + cc.x;
-      const double z1 = acc[i][j][1] + cc.y;
-      double x0, x1, d0, d1;
-      bool bad = false;
-      if constexpr (EPI == EPI_PROX_COMPLEX) {
-        // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
-        const double rr = hypot(z0, z1);
-        const double den = rr + kEps;
-        const double mag = max_zero(rr - thr0[j]);
-        x0 = mag * (z0 / den);
-        x1 = mag * (z1 / den);
-        d0 = x0 - pp.x;
-        d1 = x1 - pp.y;
-        if (ep.check) bad = !(abs_bits(hypot(d0, d1)) < tolb0[j]);
-      } else {
-        if constexpr (EPI == EPI_PROX_POSITIVE) {
-          x0 = max_zero(z0 - thr0[j]);   // lasso.py:228-241
-          x1 = max_zero(z1 - thr1[j]);
+      mbar_wait(opnd_bar, opnd_phase);
+      opnd_phase ^= 1u;
+
+      // per-column vectors of this lane's NJ column pairs: threshold step * alpha (lasso.py:287) and tolerance
+      // tol * s as bit patterns (lasso.py:130); columns beyond N get harmless zeros and are never stored
+      const long long col_lane = (long long)t.n0 + wn * C::WN + 2 * q;
+      double thr0[C::NJ], thr1[C::NJ];
+      unsigned long long tolb0[C::NJ], tolb1[C::NJ];
+  #pragma unroll
+      for (int j = 0; j < C::NJ; ++j) {
+        const long long col = col_lane + 8 * j;
+        thr0[j] = thr1[j] = 0.0;
+        tolb0[j] = tolb1[j] = 0ull;
+        if (col < gs.N) {
+          if constexpr (EPI == EPI_PROX_COMPLEX) {
+            thr0[j] = thr1[j] = __ldg(ep.colvec + (col >> 1));
+            if (ep.check) tolb0[j] = (unsigned long long)__double_as_longlong(__ldg(ep.colvec2 + (col >> 1)));
+          } else {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(ep.colvec + col));   // padded to even
+            thr0[j] = a.x;
+            thr1[j] = a.y;
+            if (ep.check) {
+              const double2 tl = __ldg(reinterpret_cast<const double2*>(ep.colvec2 + col));
+              tolb0[j] = (unsigned long long)__double_as_longlong(tl.x);
+              tolb1[j] = (unsigned long long)__double_as_longlong(tl.y);
+            }
+          }
+          if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) {
+            thr0[j] = step * thr0[j];
+            thr1[j] = step * thr1[j];
+          }
+        }
+      }
+
+      // fragment walk: row r = wm*WM + g + 8 i (so r & 7 == g), column c = wn*WN + 8 j + 2 q inside the tile
+      const long long row_lane = (long long)t.m0 + wm * C::WM + g;
+      const int c_lane = wn * C::WN + 2 * q;
+      const unsigned char* sc = opnd_c + (wm * C::WM + g) * 128;
+      const unsigned char* sp = opnd_p + (wm * C::WM + g) * 128;
+      double* po = ep.out + row_lane * ep.ldo + col_lane;
+      double* pw = ep.out2 != nullptr ? ep.out2 + row_lane * ep.ldo2 + col_lane : nullptr;
+      const bool interior = (long long)t.m0 + C::BM <= gs.M && (long long)t.n0 + C::BN <= gs.N;
+      const double mom = ep.momentum;
+
+      auto update = [&](int i, int j, bool store, bool two) {
+        const int c = c_lane + 8 * j;
+        const int off = (c >> 4) * S::BOX_BYTES + i * 1024 + ((((c & 15) >> 1) ^ g) << 4);
+        const double2 cc = *reinterpret_cast<const double2*>(sc + off);
+        const double2 pp = *reinterpret_cast<const double2*>(sp + off);
+        const double z0 = acc[i][j][0] + cc.x;
+        const double z1 = acc[i][j][1] + cc.y;
+        double x0, x1, d0, d1;
+        bool bad = false;
+        if constexpr (EPI == EPI_PROX_COMPLEX) {
+          // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
+          const double rr = hypot(z0, z1);
+          const double den = rr + kEps;
+          const double mag = max_zero(rr - thr0[j]);
+          x0 = mag * (z0 / den);
+          x1 = mag * (z1 / den);
+          d0 = x0 - pp.x;
+          d1 = x1 - pp.y;
+          if (ep.check) bad = !(abs_bits(hypot(d0, d1)) < tolb0[j]);
         } else {
-          // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
-          x0 = with_sign_of(max_zero(fabs(z0) - thr0[j]), z0);
-          x1 = with_sign_of(max_zero(fabs(z1) - thr1[j]), z1);
+          if constexpr (EPI == EPI_PROX_POSITIVE) {
+            x0 = max_zero(z0 - thr0[j]);   // lasso.py:228-241
+            x1 = max_zero(z1 - thr1[j]);
+          } else {
+            // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
+            x0 = with_sign_of(max_zero(fabs(z0) - thr0[j]), z0);
+            x1 = with_sign_of(max_zero(fabs(z1) - thr1[j]), z1);
+          }
+          d0 = x0 - pp.x;
+          d1 = x1 - pp.y;
+          if (ep.check) bad = !(abs_bits(d0) < tolb0[j]) || (two && !(abs_bits(d1) < tolb1[j]));
         }
-        d0 = x0 - pp.x;
-        d1 = x1 - pp.y;
-        if (ep.check) bad = !(abs_bits(d0) < tolb0[j]) || (two && !(abs_bits(d1) < tolb1[j]));
-      }
-      if (store) {
-        violated |= bad;
-        st_pair(po + 8 * j, x0, x1, two);
-        // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
-        if (pw != nullptr) st_pair(pw + 8 * j, x0 + mom * d0, x1 + mom * d1, two);
-      }
-    };
+        if (store) {
+          violated |= bad;
+          st_pair(po + 8 * j, x0, x1, two);
+          // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
+          if (pw != nullptr) st_pair(pw + 8 * j, x0 + mom * d0, x1 + mom * d1, two);
+        }
+      };
 
-    if (interior) {
-#pragma unroll
-      for (int i = 0; i < C::MI; ++i) {
-#pragma unroll
-        for (int j = 0; j < C::NJ; ++j) update(i, j, true, true);
-        po += 8 * ep.ldo;
-        if (pw != nullptr) pw += 8 * ep.ldo2;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < C::MI; ++i) {
-        const bool row_ok = row_lane + 8 * i < gs.M;
-#pragma unroll
-        for (int j = 0; j < C::NJ; ++j) {
-          const long long col = col_lane + 8 * j;
-          update(i, j, row_ok && col < gs.N, col + 1 < gs.N);
+      if (interior) {
+  #pragma unroll
+        for (int i = 0; i < C::MI; ++i) {
+  #pragma unroll
+          for (int j = 0; j < C::NJ; ++j) update(i, j, true, true);
+          po += 8 * ep.ldo;
+          if (pw != nullptr) pw += 8 * ep.ldo2;
         }
-        po += 8 * ep.ldo;
-        if (pw != nullptr) pw += 8 * ep.ldo2;
+      } else {
+  #pragma unroll
+        for (int i = 0; i < C::MI; ++i) {
+          const bool row_ok = row_lane + 8 * i < gs.M;
+  #pragma unroll
+          for (int j = 0; j < C::NJ; ++j) {
+            const long long col = col_lane + 8 * j;
+            update(i, j, row_ok && col < gs.N, col + 1 < gs.N);
+          }
+          po += 8 * ep.ldo;
+          if (pw != nullptr) pw += 8 * ep.ldo2;
+        }
       }
+      __syncwarp();
+      if (pipe.lane == 0) mbar_arrive(opnd_free);   // this warp is done with the operand tiles
     }
-    __syncthreads();   // every warp is done with the operand tiles before the next tile's requests overwrite them
   }
   if (ep.check) convergence_latch(ep, violated);
 }

@@ -137,7 +137,7 @@ static int launch_proxq(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   if (tiles <= 0) return DECOMP_OK;
   long long ctas = num_sms();
   if (ctas > tiles) ctas = tiles;
-  kern<<<(unsigned)ctas, C::MMA_THREADS, ProxqSmem<C>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, gs, ep, skip_if);
+  kern<<<(unsigned)ctas, C::MMA_THREADS + 128, ProxqSmem<C>::SMEM_BYTES, stream>>>(ta, tb, tc, tp, gs, ep, skip_if);
   return check_cuda(cudaGetLastError(), "proxq launch");
 }
 
