@@ -53,7 +53,8 @@ struct GemmCfg {
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int MMA_WARPS = WARPS_M * WARPS_N, EPI_WARPS = EPI_WARPS_;
   static constexpr int MMA_THREADS = MMA_WARPS * 32, EPI_THREADS = EPI_WARPS * 32;
-  static constexpr int THREADS = MMA_THREADS + EPI_THREADS;
+  static constexpr int PROD_THREADS = 128;   // producer warp group: one active thread, registers handed to the others
+  static constexpr int THREADS = MMA_THREADS + EPI_THREADS + PROD_THREADS;
   static constexpr int MI = WM / 8, NJ = WN / 8;
   static constexpr int A_BYTES = BM * BK * 8, B_BYTES = BN * BK * 8;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -494,11 +495,26 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   bool violated = false;
 
-  if (warp < C::MMA_WARPS) {
-    // ================================================================ MMA warps (+ elected TMA producer)
+  // Register budget (setmaxnreg, one warp group each): 512 threads start with 128 registers; the producer group
+  // keeps 24, the two MMA groups take 168 and the epilogue group 152  (8*168 + 4*152 + 4*24 = 16 * 128).
+  if (threadIdx.x >= C::MMA_THREADS + C::EPI_THREADS) {
+    // ================================================================ producer warp group (one active thread)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (threadIdx.x == C::MMA_THREADS + C::EPI_THREADS) {
+      MmaPipe<C, TN> prod;
+      prod.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
+      for (;;) {
+        prod.advance_cursor();
+        if (prod.p_tile >= tiles_total) break;
+        prod.produce_one();
+      }
+    }
+  } else if (warp < C::MMA_WARPS) {
+    // ================================================================ MMA warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     MmaPipe<C, TN> pipe;
     pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
-    pipe.fill_ring();
+    pipe.elected = false;   // the producer group owns the ring
     const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
 
     int buf = 0;
@@ -529,6 +545,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ================================================================ epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // A tile is swept in BM / (ROW_STEP * EPI_BATCH) batches of EPI_BATCH column pairs per thread; all operand
     // loads of a batch are issued before its first store.
     const int e = threadIdx.x - C::MMA_THREADS;
