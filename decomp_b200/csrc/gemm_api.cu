@@ -302,13 +302,8 @@ int decomp_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ld
   CUtensorMap ta, tb;
   int rc;
   // one 3-D TMA instruction per operand and k-block when both widths are multiples of 16, else 16x16 boxes
-  static int allow3d = -1;
-  if (allow3d < 0) {
-    const char* e = getenv("DECOMP_GEMM_TN3D");
-    allow3d = e != nullptr ? atoi(e) : 1;
-  }
   gs.tn3d = 0;
-  if (allow3d && (M % 16) == 0 && (N % 16) == 0 &&
+  if ((M % 16) == 0 && (N % 16) == 0 &&
       make_tensor_map_tn3d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, C::BM / 16) == DECOMP_OK &&
       make_tensor_map_tn3d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, C::BN / 16) == DECOMP_OK) {
     gs.tn3d = 1;
