@@ -1,0 +1,70 @@
+"""Edge cases the reference's own tests touch (tests/test_lasso.py vector / tensor shapes) plus degenerate sizes and
+memory layouts: empty batch, single problem, k = 1, f = 1, strided / Fortran-ordered numpy inputs."""
+import numpy as np
+import pytest
+
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1.0e-10
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if b.size else 0.0
+
+
+def test_lasso_empty_batch_and_single_problem():
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((7,), 5, 10, 0)
+    it, x = lasso.solve(y[:0], A, 0.1, tol=0.0, method='fista', maxiter=5)
+    assert x.shape == (0, 5) and it == 4
+    for m in (None, mask[:1]):
+        it, x = lasso.solve(y[:1], A, 0.1, tol=0.0, method='fista', maxiter=30, mask=m)
+        it0, x0 = orc.lasso(y[:1], A, 0.1, tol=0.0, method='fista', maxiter=30, mask=m)
+        assert it == it0 and rel(x, x0) <= RTOL
+
+
+@pytest.mark.parametrize('k,f', [(1, 10), (5, 1), (1, 1), (2, 3)])
+def test_lasso_degenerate_dictionary_shapes(k, f):
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    rng = np.random.RandomState(k * 10 + f)
+    A = rng.randn(k, f) + 0.5
+    y = rng.randn(33, f)
+    for method in ('ista', 'fista'):
+        it, x = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=25)
+        it0, x0 = orc.lasso(y, A, 0.05, tol=0.0, method=method, maxiter=25)
+        assert it == it0 and rel(x, x0) <= RTOL
+
+
+def test_strided_and_fortran_ordered_inputs():
+    from decomp_b200 import lasso, nmf
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((40,), 6, 12, 3)
+    y_strided = np.repeat(y, 2, axis=0)[::2]                 # non-contiguous view with the same values
+    y_fortran, A_fortran = np.asfortranarray(y), np.asfortranarray(A)
+    it0, x0 = orc.lasso(y, A, 0.1, tol=0.0, method='fista', maxiter=20)
+    for yy, AA in ((y_strided, A), (y_fortran, A_fortran)):
+        it, x = lasso.solve(yy, AA, 0.1, tol=0.0, method='fista', maxiter=20)
+        assert it == it0 and rel(x, x0) <= RTOL
+    yn, D0, _ = gc._nmf_data(61, 17, 4, 2)
+    it0, D_ref, x_ref = orc.nmf_mu(yn, D0.copy(), tol=0.0, maxiter=9)
+    it, D, x = nmf.solve(np.asfortranarray(yn), np.asfortranarray(D0), tol=0.0, maxiter=9)
+    assert it == it0 and rel(D, D_ref) <= RTOL and rel(x, x_ref) <= RTOL
+
+
+def test_nmf_single_latent_and_tiny_sizes():
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    for n, f, k in ((1, 1, 1), (2, 5, 1), (9, 3, 2)):
+        y, D0, mask = gc._nmf_data(n, f, k, 7)
+        for m in (None, mask):
+            it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=6, mask=m)
+            it, D, x = nmf.solve(y, D0.copy(), tol=0.0, maxiter=6, mask=m)
+            assert it == it0
+            ok = np.isfinite(D_ref).all() and np.isfinite(x_ref).all()
+            if ok:
+                assert rel(D, D_ref) <= 1e-9 and rel(x, x_ref) <= 1e-9
+            else:                                            # degenerate masks can produce 0/0 in the reference too
+                assert np.array_equal(np.isfinite(D), np.isfinite(D_ref))
