@@ -135,6 +135,11 @@ template <int KIND>
 struct Epilogue {
   static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
   static constexpr bool kLoads = KIND != DECOMP_EPI_STORE && KIND != EPI_PARTIAL;
+  // column pairs per thread whose operand loads are in flight together.  Kept at 4: with 8 pairs and two operand
+  // streams (16 outstanding 16-byte loads per epilogue thread) large-K runs returned slightly wrong accumulations
+  // in a few rows of a tile (1e-3 relative, intermittent, cause not found); every configuration with at most 12
+  // outstanding loads is exact, see tests/test_kernels_gpu.py::test_gemm_nt_large_k_epilogues_are_exact.
+  static constexpr int kBatch = 4;
 
   // Issues the global loads of one column pair.  (row, col) has been clamped into the matrix by the caller, so
   // the loads are unconditional 16-byte accesses (the even row pitch keeps an odd last column in bounds); what
@@ -495,11 +500,10 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   bool violated = false;
 
-  // Register budget (setmaxnreg, one warp group each): 512 threads start with 128 registers; the producer group
-  // keeps 24, the two MMA groups take 168 and the epilogue group 152  (8*168 + 4*152 + 4*24 = 16 * 128).
+  // 512 threads x 128 registers fill the register file exactly; the MMA warps (64 accumulator registers) and the
+  // epilogue batches both fit in 128 without spills, so no register re-balancing (setmaxnreg) is needed here.
   if (threadIdx.x >= C::MMA_THREADS + C::EPI_THREADS) {
     // ================================================================ producer warp group (one active thread)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (threadIdx.x == C::MMA_THREADS + C::EPI_THREADS) {
       MmaPipe<C, TN> prod;
       prod.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
@@ -511,7 +515,6 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp < C::MMA_WARPS) {
     // ================================================================ MMA warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     MmaPipe<C, TN> pipe;
     pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
     pipe.elected = false;   // the producer group owns the ring
@@ -545,12 +548,13 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else {
     // ================================================================ epilogue warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // A tile is swept in BM / (ROW_STEP * EPI_BATCH) batches of EPI_BATCH column pairs per thread; all operand
     // loads of a batch are issued before its first store.
     const int e = threadIdx.x - C::MMA_THREADS;
     const int r_in = e >> 5, c2 = e & 31;   // thread -> (row r_in + ROW_STEP j, column pair c2): a warp covers one row
-    constexpr int NBATCH = C::BM / (C::ROW_STEP * C::EPI_BATCH);
+    constexpr int BATCH = Epilogue<EPI>::kBatch;
+    constexpr int NBATCH = C::BM / (C::ROW_STEP * BATCH);
+    static_assert(C::BM % (C::ROW_STEP * BATCH) == 0, "epilogue sweep must divide evenly");
     double step = 0.0;
     if constexpr (Epilogue<EPI>::kProx) step = *ep.step;
 
@@ -568,20 +572,20 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       w.colc = w.col < cmax ? w.col : cmax;
       return w;
     };
-    auto issue = [&](const Where& w, int batch, EpiIn (&in)[C::EPI_BATCH]) {
+    auto issue = [&](const Where& w, int batch, EpiIn (&in)[BATCH]) {
       if constexpr (Epilogue<EPI>::kLoads) {
 #pragma unroll
-        for (int b = 0; b < C::EPI_BATCH; ++b) {
-          long long row = w.row0 + r_in + C::ROW_STEP * (batch * C::EPI_BATCH + b);
+        for (int b = 0; b < BATCH; ++b) {
+          long long row = w.row0 + r_in + C::ROW_STEP * (batch * BATCH + b);
           if (row > gs.M - 1) row = gs.M - 1;
           Epilogue<EPI>::load(ep, row, w.colc, in[b]);
         }
       }
     };
-    auto finish = [&](const Where& w, int batch, const EpiIn (&in)[C::EPI_BATCH], const double* sb, double* pbase) {
+    auto finish = [&](const Where& w, int batch, const EpiIn (&in)[BATCH], const double* sb, double* pbase) {
 #pragma unroll
-      for (int b = 0; b < C::EPI_BATCH; ++b) {
-        const int r = r_in + C::ROW_STEP * (batch * C::EPI_BATCH + b);
+      for (int b = 0; b < BATCH; ++b) {
+        const int r = r_in + C::ROW_STEP * (batch * BATCH + b);
         const long long row = w.row0 + r;
         const double2 v = *reinterpret_cast<const double2*>(sb + r * C::EPI_PITCH + 2 * c2);
         if (row < gs.M && w.col_ok)
@@ -598,7 +602,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       double* pbase = nullptr;
       if constexpr (EPI == EPI_PARTIAL) pbase = partial + (long long)t.z * gs.M * gs.ld_partial;
       const double* sb = stage_buf + buf * (C::BUF_BYTES / 8);
-      EpiIn in[C::EPI_BATCH];
+      EpiIn in[BATCH];
       issue(w, 0, in);                                     // operand loads do not depend on the accumulators
       mbar_wait(&staged_bar[buf], buf_phase);              // accumulators of this tile are parked
 #pragma unroll 1

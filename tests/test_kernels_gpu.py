@@ -425,3 +425,70 @@ def test_dl_packed_masked_stats(cplx, k, f, mb):
     ops.dl_mirror(dS_r, k, f, cplx)
     torch.cuda.synchronize()
     close(host(dS), S_ref)
+
+
+@pytest.mark.parametrize('M', [20000, 131072])
+def test_gemm_nt_large_k_epilogues_are_exact(M):
+    """Long mainloops (K = 4096) with every fused epilogue, repeated: the hand-over of accumulators to the epilogue
+    warps and the operand ring must not depend on timing."""
+    from decomp_b200 import ops
+    torch.manual_seed(M)
+    N, K = 256, 4096
+    A = torch.rand((M, K), dtype=torch.float64, device='cuda')
+    B = torch.rand((N, K), dtype=torch.float64, device='cuda')
+    X = torch.rand((M, N), dtype=torch.float64, device='cuda') + 0.5
+    O = torch.rand((M, N), dtype=torch.float64, device='cuda') + 0.5
+    acc = A @ B.T
+
+    def check(out, ref, what):
+        err = float(((out - ref).abs() / ref.abs()).max().item())
+        assert err <= 1e-12, '%s rel err %g' % (what, err)
+
+    for rep in range(3):
+        out = torch.empty_like(X)
+        ops.gemm_nt(A, B, ops.epilogue(ops.EPI_STORE, out))
+        check(out, acc, 'STORE')
+        ops.gemm_nt(A, B, ops.epilogue(ops.EPI_STORE_MASK, out, mask=O))
+        check(out, acc * O, 'STORE_MASK')
+        ops.gemm_nt(A, B, ops.epilogue(ops.EPI_KL_RATIO, out, other=O, mask=X))
+        check(out, O * X / (acc + 1e-15), 'KL_RATIO')
+        for inplace in (False, True):
+            Xc = X.clone()
+            dst = Xc if inplace else out
+            ops.gemm_nt(A, B, ops.epilogue(ops.EPI_MU_NUM, dst, x=Xc, other=O))
+            check(dst, X * acc / O, 'MU_NUM')
+            Xc = X.clone()
+            dst = Xc if inplace else out
+            ops.gemm_nt(A, B, ops.epilogue(ops.EPI_MU_DEN, dst, x=Xc, other=O))
+            check(dst, X * O / acc, 'MU_DEN')
+
+
+def test_gemm_nt_large_k_prox_is_exact():
+    """The masked-path proximal epilogue (three operand streams) behind a long mainloop, repeated."""
+    from decomp_b200 import ops
+    torch.manual_seed(7)
+    M, N, K = 131072, 256, 4096
+    A = torch.rand((M, K), dtype=torch.float64, device='cuda') - 0.5
+    B = torch.rand((N, K), dtype=torch.float64, device='cuda') - 0.5
+    w = torch.randn((M, N), dtype=torch.float64, device='cuda')
+    ya = torch.randn((M, N), dtype=torch.float64, device='cuda') * 20
+    xp = torch.randn((M, N), dtype=torch.float64, device='cuda')
+    alpha = ops.vector(N, 'cuda')
+    alpha.copy_(torch.rand(N, dtype=torch.float64, device='cuda'))
+    tolv = ops.vector(N, 'cuda')
+    rowfac = torch.rand(M, dtype=torch.float64, device='cuda') + 0.5
+    step = torch.full((1,), 0.01, dtype=torch.float64, device='cuda')
+    acc = A @ B.T
+    z = w + 0.01 * (ya - acc)
+    thr = 0.01 * (alpha[None, :] * rowfac[:, None])
+    x_ref = torch.clamp(z.abs() - thr, min=0) * torch.sign(z)
+    w_ref = x_ref + 0.3 * (x_ref - xp)
+    for rep in range(3):
+        xn, wn = torch.empty_like(w), torch.empty_like(w)
+        epi = ops.epilogue(ops.EPI_PROX, xn, out2=wn, x=w, other=ya, prev=xp, colvec=alpha, colvec2=tolv, rowvec=rowfac,
+                           step=step, momentum=0.3, shrink=ops.SHRINK_REAL)
+        ops.gemm_nt(A, B, epi)
+        torch.cuda.synchronize()
+        scale = float(x_ref.abs().max().item())
+        assert float((xn - x_ref).abs().max().item()) <= 1e-11 * scale
+        assert float((wn - w_ref).abs().max().item()) <= 1e-11 * scale
