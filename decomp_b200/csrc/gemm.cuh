@@ -5,16 +5,17 @@
 //     LDS.64 reads.  Two MMA warps per SM sub-partition are what saturates the FP64 tensor pipe (one warp per
 //     sub-partition reaches ~71 % of it, measured)
 //   * operand k-blocks stream through a shared-memory ring filled by TMA (cp.async.bulk.tensor, 128-byte
-//     swizzle) and guarded by full/empty mbarriers; one elected MMA thread refills the stage that was consumed
-//     one k-block earlier, and the ring keeps running across tile boundaries
+//     swizzle) and guarded by full/empty mbarriers; a dedicated producer thread (own warp group) keeps it full
+//     across tile boundaries.  A stage is handed back one k-block late, when the DMMAs that consumed it have
+//     issued (see MmaPipe::run for why the obvious place is a race)
 //   * 4 epilogue warps own all global-memory traffic of the fused update: when a tile's mainloop ends the MMA
 //     warps park the accumulators in one of two padded shared-memory staging buffers and immediately start the
 //     next tile; the epilogue warps sweep the staged tile row-contiguously (one warp = one 512-byte row, 16
 //     bytes per lane), issue all operand loads of a batch before its first store, and apply the fused update (MU
 //     ratio, mask, ISTA/FISTA proximal step + momentum + convergence test).  The memory-bound epilogue of tile t
 //     therefore runs under the DMMA mainloop of tile t+1 instead of stalling it
-//   * 12 warps = 3 per sub-partition -> 168 registers per thread: enough for the 64 accumulator registers of a
-//     32x32 warp tile and for the epilogue batches, no spills
+//   * 512 threads x 128 registers: enough for the 64 accumulator registers of a 32x32 warp tile and for the
+//     epilogue batches, no spills
 //
 //   NT: acc[m][n] = sum_k A[m][k] B[n][k]   both operands K-contiguous   (y.dot(d.T), x.dot(G), ...)
 //   TN: acc[m][n] = sum_k A[k][m] B[k][n]   both operands M/N-contiguous (x.T.dot(y), contraction over samples)
@@ -44,6 +45,7 @@ struct GemmGeom {
   long long M, N, K;
   int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
   long long ld_partial;  // TN: leading dimension of one partial slab (even)
+  int zero;              // always 0, opaque to the compiler
   int tn3d;              // TN: operands are described by 3-D tensor maps (one TMA instruction per operand)
 };
 
@@ -135,11 +137,9 @@ template <int KIND>
 struct Epilogue {
   static constexpr bool kProx = KIND == EPI_PROX_REAL || KIND == EPI_PROX_COMPLEX || KIND == EPI_PROX_POSITIVE;
   static constexpr bool kLoads = KIND != DECOMP_EPI_STORE && KIND != EPI_PARTIAL;
-  // column pairs per thread whose operand loads are in flight together.  Kept at 4: with 8 pairs and two operand
-  // streams (16 outstanding 16-byte loads per epilogue thread) large-K runs returned slightly wrong accumulations
-  // in a few rows of a tile (1e-3 relative, intermittent, cause not found); every configuration with at most 12
-  // outstanding loads is exact, see tests/test_kernels_gpu.py::test_gemm_nt_large_k_epilogues_are_exact.
-  static constexpr int kBatch = 4;
+  // column pairs per thread whose operand loads are in flight together (8 pairs x 2 streams for the MU ratio,
+  // 4 pairs x up to 3 streams elsewhere: what fits in 128 registers without spills)
+  static constexpr int kBatch = (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) ? 8 : 4;
 
   // Issues the global loads of one column pair.  (row, col) has been clamped into the matrix by the caller, so
   // the loads are unconditional 16-byte accesses (the even row pitch keeps an odd last column in bounds); what
@@ -280,6 +280,11 @@ __device__ __forceinline__ TileInfo tile_info(const GemmGeom& gs, int tiles_mn, 
   return t;
 }
 
+// Zero that the instruction scheduler has to wait for: `zero` is a kernel argument that is always 0, so the result
+// is 0, but it cannot be formed before the registers behind `dep` have been written.  Used as `lane == after(..)`
+// in front of an mbarrier arrival that must not overtake the shared-memory reads feeding those registers.
+__device__ __forceinline__ int after(int dep, int zero) { return dep & zero; }
+
 // --------------------------------------------------------------------------------------------------
 // Operand pipeline + DMMA mainloop of the 8 MMA warps, shared by both kernels below.
 // --------------------------------------------------------------------------------------------------
@@ -292,9 +297,8 @@ struct MmaPipe {
   uint64_t* full_bar;
   uint64_t* empty_bar;
   int tiles_mn, tiles_total;
-  bool elected;
   int lane, wm, wn, g, q;
-  // producer cursor (meaningful in the elected thread only): next k-block to request
+  // producer cursor (meaningful in the producer thread only): next k-block to request
   int p_tile, p_i, p_stage;
   uint32_t p_phase;   // parity of the `empty` completion the next refill of p_stage has to wait for
   bool p_wait;        // false while the ring is being filled for the first time
@@ -302,7 +306,6 @@ struct MmaPipe {
   // consumer cursor
   int s;
   uint32_t ph;
-  bool first;         // no refill after the very first k-block: the ring was filled STAGES deep
   int offA[4], offB[4];   // per-lane byte offsets inside a stage for the four k-steps of one 16-wide k-block
 
   __device__ __forceinline__ void init(const CUtensorMap* a, const CUtensorMap* b, const GemmGeom* geom,
@@ -315,7 +318,6 @@ struct MmaPipe {
     empty_bar = empty;
     tiles_mn = geom->tiles_m * geom->tiles_n;
     tiles_total = tiles_mn * geom->splits;
-    elected = threadIdx.x == 0;
     const int warp = threadIdx.x >> 5;
     lane = threadIdx.x & 31;
     wm = warp / C::WARPS_N;
@@ -330,7 +332,6 @@ struct MmaPipe {
     p_t = tile_info(*geom, tiles_mn, p_tile < tiles_total ? p_tile : 0, C::BM, C::BN);
     s = 0;
     ph = 0;
-    first = true;
     if constexpr (!TN) {
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
@@ -358,7 +359,7 @@ struct MmaPipe {
     }
   }
 
-  // requests the next k-block of this CTA's tile sequence into stage p_stage (elected thread only)
+  // requests the next k-block of this CTA's tile sequence into stage p_stage (producer thread only)
   __device__ __forceinline__ void produce_one() {
     advance_cursor();
     if (p_tile >= tiles_total) return;
@@ -387,25 +388,28 @@ struct MmaPipe {
     }
   }
 
-  __device__ __forceinline__ void fill_ring() {
-    if (elected) {
-#pragma unroll 1
-      for (int i = 0; i < C::STAGES; ++i) produce_one();
-    }
+  // hands stage `stage` back to the producer (one arrival per MMA warp)
+  __device__ __forceinline__ void release(int stage) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
   }
 
-  // acc = sum over the tile's k-blocks; refills the stage consumed one k-block ago (prefetch distance STAGES - 1).
-  // `hook(it)` runs in the elected thread after the refill of k-block `it` (used to trickle other TMA requests in
-  // between the operand refills instead of queueing them in front of the ring).
-  template <class Hook>
-  __device__ __forceinline__ void run(const TileInfo& t, double (&acc)[C::MI][C::NJ][2], Hook hook) {
+  // acc = sum over the tile's k-blocks
+  __device__ __forceinline__ void run(const TileInfo& t, double (&acc)[C::MI][C::NJ][2]) {
 #pragma unroll
     for (int i = 0; i < C::MI; ++i)
 #pragma unroll
       for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    int held = -1;   // stage whose release is still owed (see below)
 #pragma unroll 1
     for (int it = 0; it < t.nkb; ++it) {
       mbar_wait(&full_bar[s], ph);
+      // The stage read in the previous iteration is handed back only here.  Program order alone does not keep the
+      // arrival behind the shared-memory reads: ptxas hoists it above the DMMAs that consume the loaded registers,
+      // and a refill by TMA (async proxy) then raced with reads still in flight -- seen as wrong B fragments in one
+      // warp behind K = 4096 mainloops.  At this point every DMMA of the previous k-block has been issued, hence
+      // its operands had arrived in registers.
+      if (held >= 0) release(held);
       const unsigned char* st = smem + s * C::STAGE_BYTES;
 #pragma unroll
       for (int s4 = 0; s4 < 4; ++s4) {
@@ -431,17 +435,21 @@ struct MmaPipe {
 #pragma unroll
           for (int j = 0; j < C::NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-      if (elected) {
-        if (!first) produce_one();
-        hook(it);
-      }
-      first = false;
+      held = s;
       if (++s == C::STAGES) {
         s = 0;
         ph ^= 1u;
       }
+    }
+    // last k-block of the tile: the arrival is made to depend on the finished accumulators instead
+    if (held >= 0) {
+      int dep = 0;
+#pragma unroll
+      for (int i = 0; i < C::MI; ++i)
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) dep |= __double2hiint(acc[i][j][0]);
+      __syncwarp();
+      if (lane == after(dep, gs->zero)) mbar_arrive(&empty_bar[held]);
     }
   }
 };
@@ -517,7 +525,6 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================================================ MMA warps
     MmaPipe<C, TN> pipe;
     pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
-    pipe.elected = false;   // the producer group owns the ring
     const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
 
     int buf = 0;
@@ -527,7 +534,7 @@ gemm_f64_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
       double acc[C::MI][C::NJ][2];
-      pipe.run(t, acc, [](int) {});
+      pipe.run(t, acc);
 
       // park the accumulators for the epilogue warps and move on
       if (buf_wait) mbar_wait(&drained_bar[buf], buf_phase);
@@ -676,7 +683,7 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
 
   // The operand tiles of a tile are requested box by box (16 KB each) between the ring refills of that tile's own
-  // mainloop, so that they never queue in front of the GEMM operands (elected thread only).
+  // mainloop, so that they never queue in front of the GEMM operands (producer thread only).
   constexpr int NBOX = C::BN / 16;
   auto request_box = [&](const TileInfo& t, int b) {
     if (b == 0) mbar_arrive_expect_tx(opnd_bar, 2 * S::OPND_BYTES);
@@ -729,7 +736,6 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     MmaPipe<C, false> pipe;
     pipe.init(&tmA, &tmB, &gs, smem, full_bar, empty_bar);
-    pipe.elected = false;   // the producer group owns the ring
     const int wm = pipe.wm, wn = pipe.wn, g = pipe.g, q = pipe.q;
 
     double step = 0.0;
@@ -739,7 +745,7 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
       const TileInfo t = tile_info(gs, tiles_mn, tile, C::BM, C::BN);
       double acc[C::MI][C::NJ][2];
-        pipe.run(t, acc, [](int) {});
+        pipe.run(t, acc);
 
       mbar_wait(opnd_bar, opnd_phase);
       opnd_phase ^= 1u;
@@ -785,6 +791,7 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool interior = (long long)t.m0 + C::BM <= gs.M && (long long)t.n0 + C::BN <= gs.N;
       const double mom = ep.momentum;
 
+      int opnd_dep = 0;
       auto update = [&](int i, int j, bool store, bool two) {
         const int c = c_lane + 8 * j;
         const int off = (c >> 4) * S::BOX_BYTES + i * 1024 + ((((c & 15) >> 1) ^ g) << 4);
@@ -817,6 +824,7 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           d1 = x1 - pp.y;
           if (ep.check) bad = !(abs_bits(d0) < tolb0[j]) || (two && !(abs_bits(d1) < tolb1[j]));
         }
+        opnd_dep |= __double2hiint(d0) | __double2hiint(d1);
         if (store) {
           violated |= bad;
           st_pair(po + 8 * j, x0, x1, two);
@@ -846,8 +854,10 @@ gemm_f64_proxq_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (pw != nullptr) pw += 8 * ep.ldo2;
         }
       }
+      // this warp is done with the operand tiles; TMA overwrites them next, so the arrival waits for the values
+      // that were computed from them (same reasoning as in MmaPipe::run)
       __syncwarp();
-      if (pipe.lane == 0) mbar_arrive(opnd_free);   // this warp is done with the operand tiles
+      if (pipe.lane == after(opnd_dep, gs.zero)) mbar_arrive(opnd_free);
     }
   }
   if (ep.check) convergence_latch(ep, violated);

@@ -211,6 +211,7 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
   gs.kblocks_per_split = gs.kblocks_total;
   gs.ld_partial = 0;
   gs.tn3d = 0;
+  gs.zero = 0;
   cudaStream_t st = as_stream(stream);
   switch (epi->kind) {
     case DECOMP_EPI_STORE:
@@ -303,6 +304,7 @@ int decomp_gemm_tn_f64(const double* A, int64_t lda, const double* B, int64_t ld
   int rc;
   // one 3-D TMA instruction per operand and k-block when both widths are multiples of 16, else 16x16 boxes
   gs.tn3d = 0;
+  gs.zero = 0;
   if ((M % 16) == 0 && (N % 16) == 0 &&
       make_tensor_map_tn3d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, C::BM / 16) == DECOMP_OK &&
       make_tensor_map_tn3d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, C::BN / 16) == DECOMP_OK) {
