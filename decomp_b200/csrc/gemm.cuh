@@ -388,9 +388,9 @@ struct MmaPipe {
     }
   }
 
-  // hands stage `stage` back to the producer (one arrival per MMA warp)
+  // hands stage `stage` back to the producer (one arrival per MMA warp).  No __syncwarp: the caller has passed
+  // warp-synchronous DMMAs that consumed every lane's reads of that stage.
   __device__ __forceinline__ void release(int stage) {
-    __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
   }
 
