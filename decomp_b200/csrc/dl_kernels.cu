@@ -2,6 +2,7 @@
 // (k grid-wide barriers instead of k host round trips), and the masked Jacobi update, which streams the
 // [k, f, k] statistics tensor once from HBM.  Reference: decomp/dictionary_learning.py:154-159, 206-222.
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "common.h"
 
@@ -183,21 +184,37 @@ __global__ void scatter_stats_kernel(const double* __restrict__ P, long long ldp
 }
 
 // S[b][j][a] = conj(S[a][j][b]) for b > a: the masked statistics are Hermitian in (a, b), so only b >= a is
-// accumulated by the GEMMs and the rest is mirrored.  One block per (a, j) row, contiguous reads, strided writes.
+// accumulated by the GEMMs and the rest is mirrored.  One block per feature j and 32x32 tile pair of the upper
+// triangle, transposed through shared memory so that reads and writes are both 32 contiguous elements per warp.
 template <bool CPLX>
-__global__ void dl_mirror_kernel(double* __restrict__ S, int k, int f) {
-  constexpr int CW = CPLX ? 2 : 1;
-  const long long row = blockIdx.x;              // a * f + j
-  const int a = (int)(row / f);
-  const long long j = row % f;
-  const double* src = S + row * (long long)k * CW;
-  for (int b = a + 1 + threadIdx.x; b < k; b += blockDim.x) {
-    double* dst = S + (((long long)b * f + j) * k + a) * CW;
-    if (CPLX) {
-      const double2 v = *reinterpret_cast<const double2*>(src + 2 * b);
-      *reinterpret_cast<double2*>(dst) = make_double2(v.x, -v.y);
-    } else {
-      dst[0] = src[b];
+__global__ void __launch_bounds__(256) dl_mirror_kernel(double* __restrict__ S, int k, int f) {
+  using Elem = typename std::conditional<CPLX, double2, double>::type;
+  __shared__ Elem tile[32][33];
+  Elem* E = reinterpret_cast<Elem*>(S);
+  const long long j = blockIdx.x;
+  const int T = (k + 31) / 32;
+  int p = blockIdx.y, ta = 0;
+  while (p >= T - ta) {
+    p -= T - ta;
+    ++ta;
+  }
+  const int tb = ta + p;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ty + 8 * r;
+    const int a = ta * 32 + i, b = tb * 32 + tx;
+    if (a < k && b < k) tile[i][tx] = E[((long long)a * f + j) * k + b];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ty + 8 * r;
+    const int b = tb * 32 + i, a = ta * 32 + tx;
+    if (b < k && a < k && b > a) {
+      Elem v = tile[tx][i];
+      if constexpr (CPLX) v.y = -v.y;
+      E[((long long)b * f + j) * k + a] = v;
     }
   }
 }
@@ -384,15 +401,16 @@ int decomp_dl_scatter_stats_f64(const double* P, int64_t ldp, int64_t f, int64_t
 
 int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, void* stream) {
   if (k <= 1 || f <= 0) return DECOMP_OK;
-  const long long blocks = (long long)(k - 1) * f;   // the last atom has nothing to mirror
-  if (blocks > 2147483647LL) {
-    set_error("decomp_dl_mirror_f64: too many rows");
+  const long long T = (k + 31) / 32, pairs = T * (T + 1) / 2;
+  if (f > 2147483647LL || pairs > 65535) {
+    set_error("decomp_dl_mirror_f64: too many tiles (k <= 11552)");
     return DECOMP_ERR_INVALID;
   }
+  const dim3 grid((unsigned)f, (unsigned)pairs), block(32, 8);
   if (is_complex)
-    dl_mirror_kernel<true><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(S, (int)k, (int)f);
+    dl_mirror_kernel<true><<<grid, block, 0, as_stream(stream)>>>(S, (int)k, (int)f);
   else
-    dl_mirror_kernel<false><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(S, (int)k, (int)f);
+    dl_mirror_kernel<false><<<grid, block, 0, as_stream(stream)>>>(S, (int)k, (int)f);
   DCP_CHECK_LAUNCH("dl_mirror");
   return DECOMP_OK;
 }

@@ -427,6 +427,25 @@ def test_dl_packed_masked_stats(cplx, k, f, mb):
     close(host(dS), S_ref)
 
 
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('k,f', [(1, 3), (2, 1), (33, 5), (70, 9), (128, 2)])
+def test_dl_mirror_tiles(cplx, k, f):
+    """Lower triangle := conjugate of the upper one, the upper one and the diagonal untouched; k across several
+    32-wide tiles and not a multiple of the tile."""
+    from decomp_b200 import ops
+    rng = np.random.RandomState(k * 100 + f)
+    S = rng.randn(k, f, k) + (1j * rng.randn(k, f, k) if cplx else 0.0)
+    ref = S.copy()
+    for a in range(k):
+        for b in range(a + 1, k):
+            ref[b, :, a] = np.conj(S[a, :, b])
+    dS = torch.from_numpy(np.ascontiguousarray(S)).cuda()
+    dS_r = torch.view_as_real(dS).reshape(k, f, k * 2) if cplx else dS
+    ops.dl_mirror(dS_r, k, f, cplx)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(dS), ref)
+
+
 @pytest.mark.parametrize('M', [20000, 131072])
 def test_gemm_nt_large_k_epilogues_are_exact(M):
     """Long mainloops (K = 4096) with every fused epilogue, repeated: the hand-over of accumulators to the epilogue
