@@ -336,7 +336,9 @@ def run_ours(args):
                                'h2d_bytes_per_step': (y_np.nbytes + A_np.nbytes) / K,
                                'd2h_bytes_per_step': x_np.nbytes / K, 'ms_per_call': e2e * 1e3,
                                'note': 'one lasso.solve(maxiter=steps) call with host arrays: H2D of y and A, '
-                                       'set-up GEMMs, steps iterations, D2H of x; bytes are per call / steps'}
+                                       'set-up GEMMs, steps iterations, D2H of x, all inside the timed region '
+                                       '(tol = 0: the call runs the batch in row chunks so that copies overlap the '
+                                       'iterations); bytes are per call / steps'}
         del yh, Ah, y_np, A_np, x_np
         torch.cuda.empty_cache()
 

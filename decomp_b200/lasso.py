@@ -93,6 +93,13 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
     out_dtype = np_dtype(y)
     batch_shape = tuple(y.shape[:-1])
     k = A.shape[0]
+    # (a per-problem mask couples the rows through the batch mean of the mask, lasso.py:300-303: one piece)
+    if group is None and not float(tol) > 0.0 and not is_torch(y) and (mask is None or mask.ndim == 1):
+        chunks = _row_chunks(flatten_rows(y).shape[0], y.shape[-1], k * (2 if np_dtype(A).kind == 'c' else 1), device)
+        if chunks is not None:
+            it, res = _solve_pipelined(flatten_rows(y), A, float(alpha), None if x is None else flatten_rows(x),
+                                       int(maxiter), rule, positive, mask, precision, chunks, device, out_dtype)
+            return it, res.reshape(batch_shape + (k,))
     y2 = to_device2d(flatten_rows(y), device, copy=False)
     x2 = to_device2d(flatten_rows(x), device, copy=False) if x is not None else None
     A2 = to_device2d(A, device, copy=False)
@@ -105,6 +112,84 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
     it = state.iterations()
     res = to_host(state.result, y, out_dtype)
     return it, res.reshape(batch_shape + (k,))
+
+
+PIPELINE_MIN_BYTES = 64 << 20   # host batches below this are solved in one piece
+
+
+def _row_chunks(B, f, k_cols, device):
+    """Row ranges for the pipelined host path, or None when the batch is too small to be worth splitting.
+
+    Chunks are whole rounds of the persistent GEMM grid (one CTA tile of 128 rows x 64 columns per SM and round), so
+    splitting costs no tile quantisation; a short first chunk lets the iterations start early and a short last one
+    keeps the final device-to-host copy small (the ragged rest of the batch rides in a long middle chunk)."""
+    if B * f * 8 < PIPELINE_MIN_BYTES:
+        return None
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    tiles_n = -(-k_cols // 64)
+    unit = 128 * max(1, sms // tiles_n)
+    units = B // unit
+    if units < 4:
+        return None
+    first = 2 * unit if units >= 8 else unit
+    middle = B - first - unit                  # whole rounds plus the ragged rest of the batch
+    pieces = 2 if middle >= 8 * unit else 1
+    head = (middle // unit // pieces) * unit
+    sizes = [first] + [head] * (pieces - 1) + [middle - head * (pieces - 1), unit]
+    out, r0 = [], 0
+    for n in sizes:
+        out.append((r0, r0 + n))
+        r0 += n
+    assert r0 == B
+    return out
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_streams(device):
+    """One upload and one download stream per device, created on first use."""
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return _COPY_STREAMS[key]
+
+
+def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, chunks, device, out_dtype):
+    """Host arrays, ``tol <= 0``: every row runs exactly ``maxiter - 1`` iterations whatever the other rows do
+    (lasso.py:293/409 never fires), so the batch is solved chunk by chunk with the upload of the next chunk and the
+    download of the previous one overlapping the iterations of the current one.  Row results are bitwise those of the
+    one-piece solve: a row's dot products do not depend on which tile it sits in."""
+    cur = torch.cuda.current_stream(device)
+    up, down = _copy_streams(device)
+    up.wait_stream(cur)
+    down.wait_stream(cur)
+    k = A.shape[0]
+    A2 = to_device2d(A, device, copy=False)
+    m1 = to_device1d(mask, device) if mask is not None else None
+    tdt = getattr(torch, np.dtype(out_dtype).name)
+    host = torch.empty((y.shape[0], k), dtype=tdt, pin_memory=True)
+    staged = []
+    with torch.cuda.stream(up):
+        for r0, r1 in chunks:
+            yc = to_device2d(y[r0:r1], device, copy=False)
+            xc = to_device2d(x[r0:r1], device, copy=False) if x is not None else None
+            ev = torch.cuda.Event()
+            ev.record(up)
+            staged.append((yc, xc, ev))
+    keep = []
+    for (r0, r1), (yc, xc, ev) in zip(chunks, staged):
+        cur.wait_event(ev)
+        state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision)
+        res = state.result.to(dtype=tdt)
+        done = torch.cuda.Event()
+        done.record(cur)
+        down.wait_event(done)
+        with torch.cuda.stream(down):
+            host[r0:r1].copy_(res, non_blocking=True)
+        keep.append((state, res))
+    down.synchronize()
+    return maxiter - 1, host.numpy()
 
 
 class LassoState(object):

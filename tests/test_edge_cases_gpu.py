@@ -68,3 +68,48 @@ def test_nmf_single_latent_and_tiny_sizes():
                 assert rel(D, D_ref) <= 1e-9 and rel(x, x_ref) <= 1e-9
             else:                                            # degenerate masks can produce 0/0 in the reference too
                 assert np.array_equal(np.isfinite(D), np.isfinite(D_ref))
+
+
+@pytest.mark.parametrize('variant', ['plain', 'x0', 'mask2d', 'mask1d', 'complex', 'pos'])
+def test_lasso_pipelined_host_path_is_bitwise_the_one_piece_solve(variant, monkeypatch):
+    """tol = 0 with host arrays: the batch is uploaded / solved / downloaded chunk by chunk (lasso._solve_pipelined);
+    every row must come out exactly as from the one-piece device solve."""
+    import torch
+    from decomp_b200 import lasso
+    monkeypatch.setattr(lasso, 'PIPELINE_MIN_BYTES', 0)
+    rng = np.random.RandomState(11)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, k, f = 128 * sms * 5 + 77, 24, 32
+    cplx = variant == 'complex'
+    A = rng.randn(k, f) + (1j * rng.randn(k, f) if cplx else 0.0)
+    y = rng.randn(B, f) + (1j * rng.randn(B, f) if cplx else 0.0)
+    kw = {}
+    if variant == 'x0':
+        kw['x'] = rng.randn(B, k)
+    if variant == 'mask2d':
+        kw['mask'] = np.rint(rng.uniform(0.3, 1.0, size=(B, f)))
+    if variant == 'mask1d':
+        kw['mask'] = np.rint(rng.uniform(0.3, 1.0, size=f))
+    method = 'fista_pos' if variant == 'pos' else 'fista'
+    assert lasso._row_chunks(B, f, k * (2 if cplx else 1), torch.device('cuda', 0)) is not None
+    it, x = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=12, **kw)
+    dev = {n: torch.from_numpy(v).cuda() for n, v in kw.items()}
+    it_d, x_d = lasso.solve(torch.from_numpy(y).cuda(), torch.from_numpy(A).cuda(), 0.05, tol=0.0, method=method,
+                            maxiter=12, **dev)
+    assert it == it_d == 11
+    assert isinstance(x, np.ndarray) and x.shape == (B, k) and x.dtype == y.dtype
+    assert np.array_equal(x, x_d.cpu().numpy())
+    assert np.any(x != 0)
+
+
+def test_lasso_row_chunks_cover_the_batch():
+    import torch
+    from decomp_b200 import lasso
+    dev = torch.device('cuda', 0)
+    assert lasso._row_chunks(1000, 64, 16, dev) is None              # below PIPELINE_MIN_BYTES
+    for B, f, kc in [(100000, 1024, 256), (19000, 1024, 256), (400000, 512, 1024), (75777, 256, 32)]:
+        ch = lasso._row_chunks(B, f, kc, dev)
+        if ch is None:
+            continue
+        assert ch[0][0] == 0 and ch[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(r1 > r0 for r0, r1 in ch)
