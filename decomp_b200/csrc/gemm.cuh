@@ -454,21 +454,24 @@ struct MmaPipe {
   }
 };
 
-// last-CTA-done convergence latch shared by both kernels (lasso.py:293/409): every thread passes its flag
-__device__ __forceinline__ void convergence_latch(const decomp_epilogue_t& ep, bool violated) {
+// last-CTA-done convergence latch shared by the Lasso kernels (lasso.py:293/409): every thread passes its flag
+__device__ __forceinline__ void latch_vote(int* scratch, int* latch, int latch_value, bool violated) {
   const int any = __syncthreads_or(violated ? 1 : 0);
   if (threadIdx.x == 0) {
-    if (any) atomicOr(&ep.scratch[0], 1);
+    if (any) atomicOr(&scratch[0], 1);
     __threadfence();
-    const int ticket = atomicAdd(&ep.scratch[1], 1);
+    const int ticket = atomicAdd(&scratch[1], 1);
     if (ticket == (int)gridDim.x - 1) {
       __threadfence();
-      const int v = atomicOr(&ep.scratch[0], 0);
-      if (v == 0) *ep.latch = ep.latch_value;
-      ep.scratch[0] = 0;
-      ep.scratch[1] = 0;
+      const int v = atomicOr(&scratch[0], 0);
+      if (v == 0) *latch = latch_value;
+      scratch[0] = 0;
+      scratch[1] = 0;
     }
   }
+}
+__device__ __forceinline__ void convergence_latch(const decomp_epilogue_t& ep, bool violated) {
+  latch_vote(ep.scratch, ep.latch, ep.latch_value, violated);
 }
 
 // --------------------------------------------------------------------------------------------------

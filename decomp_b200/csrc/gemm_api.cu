@@ -8,6 +8,7 @@
 
 #include "common.h"
 #include "gemm.cuh"
+#include "lasso_resident.cuh"
 
 namespace dcp {
 
@@ -141,6 +142,22 @@ static int launch_proxq(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   return check_cuda(cudaGetLastError(), "proxq launch");
 }
 
+template <int SHRINK>
+static int launch_resident(const CUtensorMap& tw, const CUtensorMap& tq, const ResidentArgs& a, const int32_t* skip_if,
+                           cudaStream_t stream) {
+  auto kern = lasso_resident_kernel<SHRINK>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ResidentSmem::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resident smem)");
+    configured = true;
+  }
+  long long groups = (a.M + 7) / 8, ctas = num_sms();   // rows are dealt out in groups of 8
+  if (ctas > groups) ctas = groups;
+  kern<<<(unsigned)ctas, RES_THREADS, ResidentSmem::SMEM_BYTES, stream>>>(tw, tq, a, skip_if);
+  return check_cuda(cudaGetLastError(), "resident lasso launch");
+}
+
 static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
   using C = CfgMain;
   gs->M = M;
@@ -269,6 +286,67 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
     }
     default:
       set_error("decomp_gemm_nt_f64: unknown epilogue kind %d", epi->kind);
+      return DECOMP_ERR_INVALID;
+  }
+}
+
+int decomp_lasso_resident_supported(int64_t N) { return N == 32 || N == 64 || N == 128 || N == 256; }
+
+int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N, const decomp_epilogue_t* epi,
+                              int32_t iters, const double* momentum, const int32_t* skip_if, void* stream) {
+  if (epi == nullptr || Q == nullptr || momentum == nullptr || M < 0 || iters < 1 ||
+      iters > DECOMP_LASSO_RESIDENT_MAX_ITERS || !decomp_lasso_resident_supported(N)) {
+    set_error("decomp_lasso_resident_f64: invalid argument (N must be 32/64/128/256, 1 <= iters <= %d)",
+              DECOMP_LASSO_RESIDENT_MAX_ITERS);
+    return DECOMP_ERR_INVALID;
+  }
+  if (M == 0) return DECOMP_OK;
+  if (epi->x == nullptr || epi->other == nullptr || epi->out == nullptr || epi->colvec == nullptr ||
+      !(epi->flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD) ||
+      (epi->check && (epi->latch == nullptr || epi->scratch == nullptr || epi->colvec2 == nullptr))) {
+    set_error("decomp_lasso_resident_f64: needs x (w), other (c), out (x), colvec as threshold; with check also "
+              "colvec2, latch and scratch");
+    return DECOMP_ERR_INVALID;
+  }
+  if (((epi->ldo | epi->ldother) & 1) != 0 || ((reinterpret_cast<uintptr_t>(epi->out) |
+                                                reinterpret_cast<uintptr_t>(epi->other)) & 15u) != 0) {
+    set_error("decomp_lasso_resident_f64: x and c must be 16-byte aligned with even leading dimensions");
+    return DECOMP_ERR_INVALID;
+  }
+  const int bm = (int)(8192 / N);
+  CUtensorMap tw, tq;
+  int rc = make_tensor_map(&tw, epi->x, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldx, BK, (uint32_t)bm);
+  if (rc != DECOMP_OK) return rc;
+  rc = make_tensor_map(&tq, Q, (uint64_t)N, (uint64_t)N, (uint64_t)ldq, BK, (uint32_t)N);
+  if (rc != DECOMP_OK) return rc;
+  ResidentArgs a;
+  a.M = M;
+  a.N = (int)N;
+  a.iters = iters;
+  a.check = epi->check;
+  a.zero = 0;
+  a.c = epi->other;
+  a.ldc = epi->ldother;
+  a.x = epi->out;
+  a.ldx = epi->ldo;
+  a.w = const_cast<double*>(epi->x);
+  a.ldw = epi->ldx;
+  a.thr = epi->colvec;
+  a.tol = epi->colvec2;
+  a.latch = epi->latch;
+  a.scratch = epi->scratch;
+  a.latch_value = epi->latch_value;
+  for (int i = 0; i < RES_MAX_ITERS; ++i) a.momentum[i] = i < iters ? momentum[i] : 0.0;
+  cudaStream_t st = as_stream(stream);
+  switch (epi->shrink) {
+    case DECOMP_SHRINK_REAL:
+      return launch_resident<DECOMP_SHRINK_REAL>(tw, tq, a, skip_if, st);
+    case DECOMP_SHRINK_COMPLEX:
+      return launch_resident<DECOMP_SHRINK_COMPLEX>(tw, tq, a, skip_if, st);
+    case DECOMP_SHRINK_POSITIVE:
+      return launch_resident<DECOMP_SHRINK_POSITIVE>(tw, tq, a, skip_if, st);
+    default:
+      set_error("decomp_lasso_resident_f64: unknown shrink kind %d", epi->shrink);
       return DECOMP_ERR_INVALID;
   }
 }

@@ -1,0 +1,310 @@
+// Unmasked ISTA / FISTA with the iterate resident on chip: one launch runs `iters` iterations
+//     z = c + w Q;   x_new = shrink(z, thr);   w_next = x_new + momentum_i (x_new - x_prev)      (lasso.py:244-271, 405-414)
+// A batch row only ever needs its own row of w, so a CTA keeps a block of BM rows for all iterations of the launch:
+//   * w (the A operand of the next GEMM) lives in shared memory in the swizzled k-block layout the DMMA fragment
+//     loads expect, and the update writes w_next straight back into it
+//   * c = (y A^H)/L sits in a thread-private shared-memory array, x_prev in registers (every thread owns the same
+//     accumulator fragment in every iteration)
+//   * only Q = (I - G/L)^T streams, from L2, through a TMA ring
+// so HBM sees one read of (w, c, x) and one write of (x, w) per launch instead of per iteration, and there is one
+// launch per `iters` iterations.  BM * N = 8192 elements: N = 256 -> 32 rows, 1 x 8 warps of 32 x 32; N = 128 -> 64
+// rows, 2 x 4 warps; ...  Scalar FP64 instructions run on the same pipe as the DMMAs (about one DMMA slot per warp
+// instruction), so the update is kept to 3 of them per element: the accumulators start from c instead of zero
+// (no z = acc + c), |z| - t, and the two of the extrapolation.  (gemm_f64_proxq_kernel adds c after the sum, so the
+// two kernels agree to rounding, not to the bit.)
+#pragma once
+#include <type_traits>
+
+#include "gemm.cuh"
+
+namespace dcp {
+
+constexpr int RES_THREADS = 288;   // 8 MMA warps + 1 producer warp
+constexpr int RES_MAX_ITERS = 32;
+constexpr int RES_MAX_STAGES = 8;
+
+struct ResidentSmem {
+  static constexpr int W_BYTES = 65536, C_BYTES = 65536, RING_BYTES = 98304;
+  static constexpr int RING_OFF = W_BYTES + C_BYTES;
+  static constexpr int BAR_OFF = RING_OFF + RING_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * RES_MAX_STAGES + 1) * 8;
+};
+
+struct ResidentArgs {
+  long long M;
+  int N, iters, check, zero;
+  const double* c;     // [M, N]  (y A^H) / L
+  long long ldc;
+  double* x;           // [M, N]  in: x_prev, out: x after `iters` iterations
+  long long ldx;
+  double* w;           // [M, N]  in: the point the gradient is taken at (also behind tmW), out: the next one
+  long long ldw;
+  const double* thr;   // threshold step * alpha per column (complex: per column pair)
+  const double* tol;   // tolerance per column (read when check)
+  int* latch;
+  int* scratch;
+  int latch_value;
+  double momentum[RES_MAX_ITERS];
+};
+
+__device__ __forceinline__ void mma_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int SHRINK>
+__global__ void __launch_bounds__(RES_THREADS, 1)
+lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmQ,
+                      const ResidentArgs a, const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;
+  using S = ResidentSmem;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* Wt = smem;
+  double2* Ct = reinterpret_cast<double2*>(smem + S::W_BYTES);
+  unsigned char* ring = smem + S::RING_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty_bar = full_bar + RES_MAX_STAGES;
+  uint64_t* wbar = empty_bar + RES_MAX_STAGES;
+
+  const int N = a.N, KB = N >> 4, WN = N >> 5, WM = 8 / WN, BM = 32 * WM;
+  const int stage_bytes = N * 128;
+  const int stages = S::RING_BYTES / stage_bytes < RES_MAX_STAGES ? S::RING_BYTES / stage_bytes : RES_MAX_STAGES;
+  const int kb_bytes = BM * 128;   // one k-block of the resident w tile
+  // every CTA owns one contiguous range of rows (a multiple of the DMMA row granularity 8) and walks it in blocks of
+  // BM rows; the ragged last block only computes the 8-row groups it has, so the grid is loaded evenly to 8 rows
+  const long long per_cta = (((a.M + gridDim.x - 1) / gridDim.x) + 7) & ~7LL;
+  const long long row_begin = (long long)blockIdx.x * per_cta;
+  const long long row_end = row_begin + per_cta < a.M ? row_begin + per_cta : a.M;
+  const int tiles = row_begin < row_end ? (int)((row_end - row_begin + BM - 1) / BM) : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 8);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmQ);
+  }
+  __syncthreads();
+
+  bool violated = false;
+  if (warp == 8) {
+    // ================================================================ producer: Q k-blocks, round and round
+    if (lane == 0) {
+      const long long total = (long long)tiles * a.iters * KB;
+      int s = 0, kb = 0;
+      uint32_t ph = 0;
+      bool wait = false;
+      for (long long n = 0; n < total; ++n) {
+        if (wait) mbar_wait(&empty_bar[s], ph);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_2d(ring + s * stage_bytes, &tmQ, &full_bar[s], kb * BK, 0);
+        if (++kb == KB) kb = 0;
+        if (++s == stages) {
+          s = 0;
+          if (wait) ph ^= 1u;
+          wait = true;
+        }
+      }
+    }
+  } else {
+    // ================================================================ MMA warps
+    const int wn = warp % WN, wm = warp / WN, g = lane >> 2, q = lane & 3, tid = threadIdx.x;
+    int offA[4], offB[4];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
+      offA[s4] = (wm * 32 + g) * 128 + o;
+      offB[s4] = (wn * 32 + g) * 128 + o;
+    }
+    const int col_lane = wn * 32 + 2 * q;   // + 8 j
+    double thr0[4], thr1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col_lane + 8 * j;
+      if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
+        thr0[j] = thr1[j] = __ldg(a.thr + (col >> 1));
+      } else {
+        thr0[j] = __ldg(a.thr + col);
+        thr1[j] = __ldg(a.thr + col + 1);
+      }
+    }
+
+    int s = 0;
+    uint32_t ph = 0, wph = 0;
+#pragma unroll 1
+    for (int tile = 0; tile < tiles; ++tile) {
+      const long long m0 = row_begin + (long long)tile * BM;
+      // 8-row groups of this warp's 32 rows that lie inside the CTA's range
+      const long long left = row_end - (m0 + wm * 32);
+      const int mi = left >= 32 ? 4 : (left <= 0 ? 0 : (int)((left + 7) >> 3));
+      if (tid == 0) {
+        // the previous tile's w was read and written through the generic proxy; TMA overwrites it now
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(wbar, S::W_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(Wt + kb * kb_bytes, &tmW, wbar, kb * BK, (int)m0);
+      }
+      // this thread's fragment of x_prev (registers) and c (private shared-memory column): rows beyond M are clamped
+      // into the matrix, computed on and never stored
+      const long long row_lane = m0 + wm * 32 + g;
+      double2 prev[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        long long r = row_lane + 8 * i;
+        if (r > a.M - 1) r = a.M - 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          prev[i][j] = *reinterpret_cast<const double2*>(a.x + r * a.ldx + col_lane + 8 * j);
+          Ct[(i * 4 + j) * 256 + tid] = *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
+        }
+      }
+      mbar_wait(wbar, wph);
+      wph ^= 1u;
+
+#pragma unroll 1
+      for (int it = 0; it < a.iters; ++it) {
+        // the accumulators start from c, so the mainloop ends with z = c + w Q
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 cc = Ct[(i * 4 + j) * 256 + tid];
+            acc[i][j][0] = cc.x;
+            acc[i][j][1] = cc.y;
+          }
+        int held = -1;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          // late release of the stage read one k-block ago, see MmaPipe::run
+          if (held >= 0 && lane == 0) mbar_arrive(&empty_bar[held]);
+          const unsigned char* sa = Wt + kb * kb_bytes;
+          const unsigned char* sb = ring + s * stage_bytes;
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fa[i] = *reinterpret_cast<const double*>(sa + offA[s4] + i * 1024);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fb[j] = *reinterpret_cast<const double*>(sb + offB[s4] + j * 1024);
+            if (mi == 4) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                if (i < mi) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+                }
+            }
+          }
+          held = s;
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        {
+          int dep = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dep |= __double2hiint(acc[i][j][0]);
+          if (lane == after(dep, a.zero)) mbar_arrive(&empty_bar[held]);
+        }
+        mma_warps_sync();   // every warp is done reading w
+
+        const bool last = it == a.iters - 1;
+        const double mom = a.momentum[it];
+        // Three straight-line variants (inner iteration / last / last with the convergence test): with the mode
+        // tested per element the compiler kept one basic block per column pair and the 16 dependency chains of a
+        // thread ran one after the other.
+        auto update = [&](auto LAST, auto CHECK) {
+          constexpr bool kLast = decltype(LAST)::value, kCheck = decltype(CHECK)::value;
+          unsigned long long tb0[4], tb1[4];
+          if constexpr (kCheck) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = col_lane + 8 * j;
+              if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
+                tb0[j] = tb1[j] = (unsigned long long)__double_as_longlong(__ldg(a.tol + (col >> 1)));
+              } else {
+                tb0[j] = (unsigned long long)__double_as_longlong(__ldg(a.tol + col));
+                tb1[j] = (unsigned long long)__double_as_longlong(__ldg(a.tol + col + 1));
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const long long row = row_lane + 8 * i;
+            const bool row_ok = row < row_end;
+            unsigned char* wrow = Wt + (wm * 32 + g + 8 * i) * 128;
+            double* grow = a.w + row * a.ldw + col_lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int col = col_lane + 8 * j;
+              const double z0 = acc[i][j][0], z1 = acc[i][j][1];
+              double x0, x1, d0, d1;
+              if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
+                // z / (|z| + eps) * max(|z| - t, 0)   (lasso.py:210-225)
+                const double rr = hypot(z0, z1);
+                const double den = rr + kEps;
+                const double mag = max_zero(rr - thr0[j]);
+                x0 = mag * (z0 / den);
+                x1 = mag * (z1 / den);
+              } else if constexpr (SHRINK == DECOMP_SHRINK_POSITIVE) {
+                x0 = max_zero(z0 - thr0[j]);   // lasso.py:228-241
+                x1 = max_zero(z1 - thr1[j]);
+              } else {
+                // max(|z| - t, 0) * sign(z)   (lasso.py:206-207)
+                x0 = with_sign_of(max_zero(fabs(z0) - thr0[j]), z0);
+                x1 = with_sign_of(max_zero(fabs(z1) - thr1[j]), z1);
+              }
+              d0 = x0 - prev[i][j].x;
+              d1 = x1 - prev[i][j].y;
+              if constexpr (kCheck) {
+                bool bad;
+                if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX)
+                  bad = !(abs_bits(hypot(d0, d1)) < tb0[j]);
+                else
+                  bad = !(abs_bits(d0) < tb0[j]) || !(abs_bits(d1) < tb1[j]);
+                violated |= bad && row_ok;
+              }
+              prev[i][j] = make_double2(x0, x1);
+              // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
+              const double2 wv = make_double2(x0 + mom * d0, x1 + mom * d1);
+              if constexpr (!kLast) {
+                *reinterpret_cast<double2*>(wrow + (col >> 4) * kb_bytes + ((((col & 15) >> 1) ^ g) << 4)) = wv;
+              } else {
+                if (row_ok) *reinterpret_cast<double2*>(grow + 8 * j) = wv;
+              }
+            }
+          }
+        };
+        if (!last)
+          update(std::false_type{}, std::false_type{});
+        else if (a.check == 0)
+          update(std::true_type{}, std::false_type{});
+        else
+          update(std::true_type{}, std::true_type{});
+        if (!last) mma_warps_sync();   // w_next is complete
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = row_lane + 8 * i;
+        if (row < row_end) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2*>(a.x + row * a.ldx + col_lane + 8 * j) = prev[i][j];
+        }
+      }
+    }
+  }
+  if (a.check) latch_vote(a.scratch, a.latch, a.latch_value, violated);
+}
+
+}  // namespace dcp

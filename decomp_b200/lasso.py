@@ -33,6 +33,7 @@ from .utils import assertion
 AVAILABLE_METHODS = ['ista', 'cd', 'acc_ista', 'fista', 'parallel_cd', 'admm']
 AVAILABLE_NNLS_METHODS = ['ista_pos', 'cd_pos', 'acc_ista_pos', 'fista_pos', 'parallel_cd_pos', 'admm_pos']
 DEVICE_RULES = ('ista', 'fista', 'acc_ista')
+USE_RESIDENT = True   # several iterations per launch with the iterate on chip where the kernel covers the shape
 POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
 
 
@@ -316,6 +317,11 @@ class LassoSolver(object):
         else:
             self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
             self.W[0].copy_(X)
+        self.poll_at = POLL_EVERY
+        self.wi = 0                                                # W[wi] holds the current extrapolated point
+        # iterate resident on chip, several iterations per launch (FP64, unmasked, supported widths)
+        self.resident = (USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista')
+                         and ops.lasso_resident_supported(k * cw))
         self.mom = _momentum_schedule(rule, maxiter)
         # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
         # matters if it is a checking one, and then only when the check passes.
@@ -335,30 +341,59 @@ class LassoSolver(object):
             if check and self.group is not None:
                 torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
             return
+        wi = self.wi
+        self.wi = 1 - wi
         if not self.full_mask:
-            epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), other=rview(self.yAh),
+            epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, out2=rview(W[1 - wi]), other=rview(self.yAh),
                                prev=rview(self.X), colvec=self.thr, colvec2=self.tol_vec,
                                flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, momentum=self.mom[i], shrink=self.shrink,
                                check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
-            ops.gemm_nt(rview(W[i % 2]), self.Q_rhs, epi, skip=latch)
+            ops.gemm_nt(rview(W[wi]), self.Q_rhs, epi, skip=latch)
             if check and self.group is not None:
                 torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
             return
-        epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[(i + 1) % 2]), x=rview(W[i % 2]),
+        epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[1 - wi]), x=rview(W[wi]),
                            other=rview(self.yAh), prev=rview(self.X),
                            colvec=self.alpha_vec, colvec2=self.tol_vec,
                            rowvec=self.rowvec, step=self.step, momentum=self.mom[i], shrink=self.shrink,
                            check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
-        ops.gemm_nt(rview(W[i % 2]), self.A_rhs,
+        ops.gemm_nt(rview(W[wi]), self.A_rhs,
                     ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
         ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
         if check and self.group is not None:
             # the latch fires only if every shard passed the test (reference: one max over the whole batch)
             torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
 
+    def _launch_resident(self, i0, i1):
+        """Iterations i0 <= i < i1 in one launch; the convergence test may only sit on the last one."""
+        latch = self.latch
+        check = self.checks and (i1 - 1) % 10 == 0
+        W = rview(self.W[self.wi])
+        epi = ops.epilogue(ops.EPI_PROXQ, rview(self.X), cwidth=self.cw, x=W, other=rview(self.yAh),
+                           colvec=self.thr, colvec2=self.tol_vec, flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD,
+                           shrink=self.shrink, check=check, latch=latch, scratch=self.scratch, latch_value=i1)
+        ops.lasso_resident(self.Q_rhs, self.B, epi, self.mom[i0:i1], skip=latch)
+        if check and self.group is not None:
+            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+
     def iterate(self, begin, end):
         """Enqueue iterations ``begin <= i < end`` (in place on X)."""
-        for i in range(begin, min(end, self.n_inplace)):
+        end = min(end, self.n_inplace)
+        if self.resident:
+            i = begin
+            while i < end:
+                if self.checks and i >= self.poll_at:
+                    if int(self.latch.item()) != 0:
+                        self.stopped = True
+                        break
+                    self.poll_at = i + POLL_EVERY
+                stop = min(end, i + ops.RESIDENT_MAX_ITERS)
+                if self.checks:
+                    stop = min(stop, (i + 9) // 10 * 10 + 1)       # a launch ends on the next checking iteration
+                self._launch_resident(i, stop)
+                i = stop
+            return
+        for i in range(begin, end):
             if self.checks and i > 0 and i % POLL_EVERY == 0 and int(self.latch.item()) != 0:
                 self.stopped = True
                 break

@@ -353,6 +353,25 @@ def gemm_nt_tf32x3(A_hi, A_lo, B_hi, B_lo, P, skip=None):
     return P
 
 
+RESIDENT_MAX_ITERS = 32
+
+
+def lasso_resident_supported(n_real):
+    """True if the on-chip-resident Lasso kernel covers this (real) problem width."""
+    return bool(_lib.lib().decomp_lasso_resident_supported(int(n_real)))
+
+
+def lasso_resident(Q_rhs, M, epi, momentum, skip=None):
+    """len(momentum) ISTA/FISTA iterations on M rows in one launch; epi.x = w (in/out), epi.out = x (in/out),
+    epi.other = c."""
+    N = Q_rhs.shape[0]
+    mom = (ctypes.c_double * len(momentum))(*momentum)
+    rc = _lib.lib().decomp_lasso_resident_f64(_p(Q_rhs), ld(Q_rhs), M, N, ctypes.byref(epi), len(momentum), mom,
+                                              _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_lasso_resident_f64')
+    _count(1)
+
+
 def proxq_apply(P, epi, w_hi, w_lo, skip=None):
     """FP64 threshold / momentum / convergence pass after gemm_nt_tf32x3; writes w_next as (w_hi, w_lo)."""
     M, N = P.shape

@@ -195,6 +195,20 @@ int decomp_gemm_nt_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, con
 int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
                            int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream);
 
+/* `iters` (1..DECOMP_LASSO_RESIDENT_MAX_ITERS) unmasked ISTA / FISTA iterations in ONE launch with the iterate
+ * resident on chip (lasso.py:244-271, 405-414 with the gradient step folded into Q as for DECOMP_EPI_PROXQ):
+ *     z = c + w Q^T...;  x = shrink(z, thr);  w = x + momentum[i] (x - x_prev)
+ * Uses epi->{x (= w, in/out), ldx, other (= c = (y A^H)/L), ldother, out (= x, in: x_prev, out: x after the last
+ * iteration), ldo, colvec (= step * alpha, DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD), colvec2, shrink, check (the test of
+ * lasso.py:293/409 is evaluated in the LAST iteration of the launch), latch, scratch, latch_value}.
+ * Q is the [N, N] NT operand of decomp_gemm_nt_f64 (B = (I - G/L)^T); `momentum` is a HOST array of `iters` values.
+ * N must be 32, 64, 128 or 256 (decomp_lasso_resident_supported); results are bitwise those of `iters` launches of
+ * decomp_gemm_nt_f64 with DECOMP_EPI_PROXQ. */
+#define DECOMP_LASSO_RESIDENT_MAX_ITERS 32
+int decomp_lasso_resident_supported(int64_t N);
+int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N, const decomp_epilogue_t* epi,
+                              int32_t iters, const double* momentum, const int32_t* skip_if, void* stream);
+
 /* ---- dictionary-learning basis update ------------------------------------------------- */
 /* Gauss-Seidel atom sweep, dictionary_learning.py:154-159:
  *   for a in 0..k-1: u = (T[a] - S[a].D) / (S[a][a] + eps) + D[a];  D[a] = u / sqrt(max(|u|^2, 1))

@@ -511,3 +511,31 @@ def test_gemm_nt_large_k_prox_is_exact():
         scale = float(x_ref.abs().max().item())
         assert float((xn - x_ref).abs().max().item()) <= 1e-11 * scale
         assert float((wn - w_ref).abs().max().item()) <= 1e-11 * scale
+
+
+@pytest.mark.parametrize('method,cplx', [('fista', False), ('ista', False), ('fista_pos', False), ('fista', True)])
+@pytest.mark.parametrize('k', [32, 64, 128, 256])
+def test_lasso_resident_kernel_matches_the_per_iteration_kernel(method, cplx, k, monkeypatch):
+    """Several iterations per launch with the iterate resident on chip (decomp_lasso_resident_f64) against one
+    launch per iteration (DECOMP_EPI_PROXQ): same stopping iteration, x equal to rounding (the resident kernel starts
+    its accumulators from c, the other one adds c after the sum), ragged last row block."""
+    from decomp_b200 import lasso
+    if cplx:
+        k //= 2
+    rng = np.random.RandomState(k + 7)
+    f, B = 48, 148 * 32 * 2 + 37
+    A = rng.randn(k, f) + (1j * rng.randn(k, f) if cplx else 0.0)
+    xt = rng.randn(B, k) * np.rint(rng.uniform(size=(B, k)))
+    y = xt.dot(A) + 0.1 * rng.randn(B, f) + (0.1j * rng.randn(B, f) if cplx else 0.0)
+    dy, dA = torch.from_numpy(y).cuda(), torch.from_numpy(A).cuda()
+    fired = 0
+    for tol, maxiter in [(0.0, 1), (0.0, 2), (0.0, 12), (0.0, 45), (1e-3, 200), (5e-2, 300), (1e-12, 35)]:
+        monkeypatch.setattr(lasso, 'USE_RESIDENT', True)
+        it1, x1 = lasso.solve(dy, dA, 0.1, tol=tol, method=method, maxiter=maxiter)
+        monkeypatch.setattr(lasso, 'USE_RESIDENT', False)
+        it0, x0 = lasso.solve(dy, dA, 0.1, tol=tol, method=method, maxiter=maxiter)
+        assert it1 == it0, (tol, maxiter, it1, it0)
+        err = float((x1 - x0).abs().max() / x0.abs().max())
+        assert err <= 1e-12, (tol, maxiter, err)
+        fired += int(it1 < maxiter - 1)
+    assert fired > 0                          # the latch did fire inside a multi-iteration launch sequence
