@@ -33,6 +33,7 @@ from .utils import assertion
 AVAILABLE_METHODS = ['ista', 'cd', 'acc_ista', 'fista', 'parallel_cd', 'admm']
 AVAILABLE_NNLS_METHODS = ['ista_pos', 'cd_pos', 'acc_ista_pos', 'fista_pos', 'parallel_cd_pos', 'admm_pos']
 DEVICE_RULES = ('ista', 'fista', 'acc_ista')
+RESIDENT_PAD_WORK = 1.5e8   # rows x width^2 below which one iteration is launch-bound (< ~10 us of DMMA)
 USE_RESIDENT = True   # several iterations per launch with the iterate on chip where the kernel covers the shape
 POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
 
@@ -181,7 +182,8 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     keep = []
     for (r0, r1), (yc, xc, ev) in zip(chunks, staged):
         cur.wait_event(ev)
-        state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision)
+        state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision,
+                             rows_hint=y.shape[0])      # same kernel choice as the one-piece solve
         res = state.result.to(dtype=tdt)
         done = torch.cuda.Event()
         done.record(cur)
@@ -191,6 +193,14 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
         keep.append((state, res))
     down.synchronize()
     return maxiter - 1, host.numpy()
+
+
+def _padded2d(rows, cols, cplx, width, device):
+    """Zero-filled [rows, cols] buffer (complex if ``cplx``) inside a real [rows, width] one; returns (view, base)."""
+    base = torch.zeros((max(rows, 1), width), dtype=torch.float64, device=device)[:rows]
+    if cplx:
+        return torch.view_as_complex(base.view(rows, width // 2, 2))[:, :cols], base
+    return base[:, :cols], base
 
 
 class LassoState(object):
@@ -220,11 +230,13 @@ def _momentum_schedule(rule, maxiter):
     return out
 
 
-def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None, precision='fp64'):
+def lasso_device(y, A, alpha, x, tol, maxiter, rule, positive, mask=None, out=None, group=None, precision='fp64',
+                 rows_hint=None):
     """Enqueue a whole solve on the current stream. All arguments are device tensors ([B, f], [k, f],
     [B, k] or None for zeros; mask None, [f] or [B, f]). Nothing is synchronised unless the latch has to
     be polled (``tol > 0`` and more than POLL_EVERY iterations). Returns a ``LassoState``."""
-    solver = LassoSolver(y, A, alpha, x, tol, maxiter, rule, positive, mask=mask, group=group, precision=precision)
+    solver = LassoSolver(y, A, alpha, x, tol, maxiter, rule, positive, mask=mask, group=group, precision=precision,
+                         rows_hint=rows_hint)
     solver.iterate(0, solver.n_inplace)
     return solver.finish(out)
 
@@ -233,7 +245,8 @@ class LassoSolver(object):
     """One batched Lasso solve, split into set-up / iterations / read-out so that callers (and bench.py) can
     enqueue exactly the iterations they want. Every method only enqueues work on the current stream."""
 
-    def __init__(self, y, A, alpha, x, tol, maxiter, rule, positive, mask=None, group=None, precision='fp64'):
+    def __init__(self, y, A, alpha, x, tol, maxiter, rule, positive, mask=None, group=None, precision='fp64',
+                 rows_hint=None):
         dev = y.device
         if precision not in ('fp64', 'tf32x3'):
             raise ValueError("precision must be 'fp64' or 'tf32x3', given " + str(precision))
@@ -261,7 +274,22 @@ class LassoSolver(object):
         Anr = rview(An)
         self.alpha_vec, self.tol_vec = ops.lasso_vectors(s, alpha, tol, mult=1.0 if full_mask else float(f),
                                                          mult_dev=mult_dev)
-        self.X = X = empty2d(B, k, cplx, dev)
+        # iterate resident on chip, several iterations per launch: FP64, no per-problem mask, ista / fista, problem
+        # width (in doubles) 32 / 64 / 128 / 256 -- narrower problems are zero-padded up to the next of those when
+        # that costs little (<= 1.3x the flops) or when the iteration is launch-bound anyway
+        n_real = k * cw
+        self.npad = next((w for w in (32, 64, 128, 256) if w >= n_real), 0)
+        self.resident = bool(USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista')
+                             and self.npad and ops.lasso_resident_supported(self.npad)
+                             and (self.npad == n_real or (self.npad / n_real) ** 2 <= 1.3
+                                  or (rows_hint or B) * self.npad * self.npad <= RESIDENT_PAD_WORK))
+        self.pad = self.resident and self.npad != n_real
+        self.Xb = None
+        if self.pad:
+            self.X, self.Xb = _padded2d(B, k, cplx, self.npad, dev)
+            X = self.X
+        else:
+            self.X = X = empty2d(B, k, cplx, dev)
         if x is None:
             X.zero_()                                              # default x = zeros (lasso.py:73-74)
         else:
@@ -286,7 +314,11 @@ class LassoSolver(object):
         # threshold step * alpha (lasso.py:287) is formed once here unless alpha is per problem (full mask)
         self.thr = None if full_mask else ops.vector(k, dev)
         ops.gershgorin_step(rview(G), cplx, self.step, alpha_scaled=self.alpha_vec, thr_out=self.thr)
-        self.yAh = yAh = empty2d(B, k, cplx, dev)
+        if self.pad:
+            self.yAh, self.Cb = _padded2d(B, k, cplx, self.npad, dev)
+            yAh = self.yAh
+        else:
+            self.yAh = yAh = empty2d(B, k, cplx, dev)
         if full_mask:
             self.T = T = empty2d(B, f, cplx, dev)                  # also the per-iteration [B, f] temporary
             ops.mask_mul(yr, mask, rview(T), cwidth=cw)
@@ -298,6 +330,16 @@ class LassoSolver(object):
             Q = empty2d(k, k, cplx, dev)
             ops.lasso_q(rview(G), cplx, self.step, rview(Q))
             self.Q_rhs = ops.make_rhs(rview(Q), cplx, False)       # NT operand of  w . Q
+            if self.pad:
+                # zero rows / columns for the padding: it stays 0 through threshold and extrapolation
+                Qp = torch.zeros((self.npad, self.npad), dtype=torch.float64, device=dev)
+                Qp[:n_real, :n_real].copy_(self.Q_rhs)
+                self.Q_pad = Qp
+                nv = self.npad // cw
+                self.thr_pad = torch.zeros(nv, dtype=torch.float64, device=dev)
+                self.thr_pad[:k].copy_(self.thr)
+                self.tol_pad = torch.ones(nv, dtype=torch.float64, device=dev)
+                self.tol_pad[:k].copy_(self.tol_vec)
             ops.scale_scalar(rview(yAh), self.step, rview(yAh))    # yAh <- yAh / L
         if self.tf32:
             n_real = k * cw
@@ -314,14 +356,15 @@ class LassoSolver(object):
         if self.tf32:
             self.W_hi, self.W_lo = ops.split_tf32(rview(X))        # w0 = x0 as a TF32 pair, updated in place
             self.W = [X, X]
+        elif self.pad:
+            w0, self.Wb = _padded2d(B, k, cplx, self.npad, dev)
+            self.W = [w0, w0]                                      # updated in place by the resident kernel
+            w0.copy_(X)
         else:
             self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
             self.W[0].copy_(X)
         self.poll_at = POLL_EVERY
         self.wi = 0                                                # W[wi] holds the current extrapolated point
-        # iterate resident on chip, several iterations per launch (FP64, unmasked, supported widths)
-        self.resident = (USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista')
-                         and ops.lasso_resident_supported(k * cw))
         self.mom = _momentum_schedule(rule, maxiter)
         # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
         # matters if it is a checking one, and then only when the check passes.
@@ -368,11 +411,15 @@ class LassoSolver(object):
         """Iterations i0 <= i < i1 in one launch; the convergence test may only sit on the last one."""
         latch = self.latch
         check = self.checks and (i1 - 1) % 10 == 0
-        W = rview(self.W[self.wi])
-        epi = ops.epilogue(ops.EPI_PROXQ, rview(self.X), cwidth=self.cw, x=W, other=rview(self.yAh),
-                           colvec=self.thr, colvec2=self.tol_vec, flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD,
-                           shrink=self.shrink, check=check, latch=latch, scratch=self.scratch, latch_value=i1)
-        ops.lasso_resident(self.Q_rhs, self.B, epi, self.mom[i0:i1], skip=latch)
+        if self.pad:
+            X, W, C, Q, thr, tolv = self.Xb, self.Wb, self.Cb, self.Q_pad, self.thr_pad, self.tol_pad
+        else:
+            X, W, C, Q = rview(self.X), rview(self.W[self.wi]), rview(self.yAh), self.Q_rhs
+            thr, tolv = self.thr, self.tol_vec
+        epi = ops.epilogue(ops.EPI_PROXQ, X, cwidth=self.cw, x=W, other=C, colvec=thr, colvec2=tolv,
+                           flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, shrink=self.shrink, check=check, latch=latch,
+                           scratch=self.scratch, latch_value=i1)
+        ops.lasso_resident(Q, self.B, epi, self.mom[i0:i1], skip=latch)
         if check and self.group is not None:
             torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
 

@@ -514,7 +514,7 @@ def test_gemm_nt_large_k_prox_is_exact():
 
 
 @pytest.mark.parametrize('method,cplx', [('fista', False), ('ista', False), ('fista_pos', False), ('fista', True)])
-@pytest.mark.parametrize('k', [32, 64, 128, 256])
+@pytest.mark.parametrize('k', [32, 64, 128, 256, 6, 20, 100, 250])
 def test_lasso_resident_kernel_matches_the_per_iteration_kernel(method, cplx, k, monkeypatch):
     """Several iterations per launch with the iterate resident on chip (decomp_lasso_resident_f64) against one
     launch per iteration (DECOMP_EPI_PROXQ): same stopping iteration, x equal to rounding (the resident kernel starts
@@ -523,7 +523,7 @@ def test_lasso_resident_kernel_matches_the_per_iteration_kernel(method, cplx, k,
     if cplx:
         k //= 2
     rng = np.random.RandomState(k + 7)
-    f, B = 48, 148 * 32 * 2 + 37
+    f, B = 48, (148 * 32 * 2 + 37 if k >= 16 else 1003)            # narrow problems are zero-padded to 32 columns
     A = rng.randn(k, f) + (1j * rng.randn(k, f) if cplx else 0.0)
     xt = rng.randn(B, k) * np.rint(rng.uniform(size=(B, k)))
     y = xt.dot(A) + 0.1 * rng.randn(B, f) + (0.1j * rng.randn(B, f) if cplx else 0.0)
