@@ -322,6 +322,135 @@ __global__ void __launch_bounds__(256) dl_masked_update_kernel(const double* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gauss-Seidel sweep, slice-resident version: a block owns w consecutive columns of D and keeps its [k, w] slice in
+// shared memory for the whole sweep, so an atom costs one row of S (prefetched one atom ahead), k*w multiply-adds out
+// of shared memory and ONE grid-wide exchange (the norm of u).  The exchange is a hand-rolled barrier on a
+// monotonic counter plus block partials summed in block order by everybody (deterministic).  Thread = (column jj,
+// row group bg): bg strides the atoms b = bg, bg + NBG, ...
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_sweep_slice_kernel(const double* __restrict__ S, long long lds,
+                                                             const double* __restrict__ T, long long ldt, double* D,
+                                                             long long ldd, int k, int f, int w, int wpad,
+                                                             double* partials, unsigned* counter) {
+  using Elem = typename std::conditional<CPLX, double2, double>::type;
+  constexpr int CW = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char dl_smem[];
+  Elem* Ds = reinterpret_cast<Elem*>(dl_smem);                       // [k][w]
+  Elem* Sr = Ds + (size_t)k * w;                                     // [2][k]
+  Elem* red = Sr + 2 * (size_t)k;                                    // [NBG][wpad]
+  __shared__ double blk[8];
+  __shared__ double bcast;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nbg = 256 / wpad, jj = tid % wpad, bg = tid / wpad;
+  const int j0 = blockIdx.x * w;
+  const int wv = min(w, f - j0);                                     // valid columns of this slice (> 0)
+  const unsigned nblk = gridDim.x;
+
+  for (int idx = tid; idx < k * w; idx += 256) {
+    const int b = idx / w, c = idx % w;
+    Elem v;
+    if constexpr (CPLX) v = make_double2(0.0, 0.0); else v = 0.0;
+    if (c < wv) v = *reinterpret_cast<const Elem*>(D + (long long)b * ldd + (long long)CW * (j0 + c));
+    Ds[idx] = v;
+  }
+  for (int b = tid; b < k; b += 256) Sr[b] = *reinterpret_cast<const Elem*>(S + CW * b);
+  __syncthreads();
+
+  for (int a = 0; a < k; ++a) {
+    const Elem* sa = Sr + (size_t)(a & 1) * k;
+    // next atom's row of S (does not depend on this atom's update)
+    if (a + 1 < k) {
+      Elem* sn = Sr + (size_t)((a + 1) & 1) * k;
+      for (int b = tid; b < k; b += 256) sn[b] = *reinterpret_cast<const Elem*>(S + (long long)(a + 1) * lds + CW * b);
+    }
+    double sr = 0.0, si = 0.0;
+    if (jj < wv) {
+      for (int b = bg; b < k; b += nbg) {
+        if constexpr (CPLX) {
+          const double2 s = sa[b], d = Ds[(size_t)b * w + jj];
+          sr += s.x * d.x - s.y * d.y;
+          si += s.x * d.y + s.y * d.x;
+        } else {
+          sr += sa[b] * Ds[(size_t)b * w + jj];
+        }
+      }
+    }
+    if constexpr (CPLX) red[bg * wpad + jj] = make_double2(sr, si); else red[bg * wpad + jj] = sr;
+    __syncthreads();
+    double local = 0.0;
+    if (bg == 0 && jj < wv) {
+      double dr = 0.0, di = 0.0;
+      for (int t = 0; t < nbg; ++t) {
+        if constexpr (CPLX) {
+          const double2 r = red[t * wpad + jj];
+          dr += r.x;
+          di += r.y;
+        } else {
+          dr += red[t * wpad + jj];
+        }
+      }
+      const long long j = j0 + jj;
+      if constexpr (CPLX) {
+        const double2 t2 = *reinterpret_cast<const double2*>(T + (long long)a * ldt + 2 * j);
+        const double2 saa = sa[a], dj = Ds[(size_t)a * w + jj];
+        const double2 qv = cdiv(t2.x - dr, t2.y - di, saa.x + kEpsDl, saa.y);
+        const double ur = qv.x + dj.x, ui = qv.y + dj.y;
+        Ds[(size_t)a * w + jj] = make_double2(ur, ui);
+        local = ur * ur + ui * ui;
+      } else {
+        const double u = (T[(long long)a * ldt + j] - dr) / (sa[a] + kEpsDl) + Ds[(size_t)a * w + jj];
+        Ds[(size_t)a * w + jj] = u;
+        local = u * u;
+      }
+    }
+    // |u|^2 of this slice -> partials, grid-wide exchange
+    local = warp_sum_dl(local);
+    if (lane == 0) blk[warp] = local;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int t = 0; t < 8; ++t) tot += blk[t];
+      partials[(size_t)(a & 1) * nblk + blockIdx.x] = tot;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      const unsigned target = (unsigned)(a + 1) * nblk;
+      while (ld_acquire_u32(counter) < target) {
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double tot = 0.0;
+      const double* pp = partials + (size_t)(a & 1) * nblk;
+      for (unsigned b = lane; b < nblk; b += 32) tot += __ldcg(pp + b);
+      tot = warp_sum_dl(tot);
+      if (lane == 0) bcast = sqrt(fmax(tot, 1.0));
+    }
+    __syncthreads();
+    const double nrm = bcast;
+    if (bg == 0 && jj < wv) {
+      if constexpr (CPLX) {
+        double2 v = Ds[(size_t)a * w + jj];
+        Ds[(size_t)a * w + jj] = make_double2(v.x / nrm, v.y / nrm);
+      } else {
+        Ds[(size_t)a * w + jj] = Ds[(size_t)a * w + jj] / nrm;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < k * w; idx += 256) {
+    const int b = idx / w, c = idx % w;
+    if (c < wv) *reinterpret_cast<Elem*>(D + (long long)b * ldd + (long long)CW * (j0 + c)) = Ds[idx];
+  }
+}
+
 }  // namespace dcp
 
 using namespace dcp;
@@ -332,6 +461,34 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
                         int64_t f, int32_t is_complex, void* stream) {
   if (k <= 0 || f <= 0) return DECOMP_OK;
   cudaStream_t st = as_stream(stream);
+  {
+    // slice-resident sweep when a block's [k, w] slice of D (+ two rows of S + the reduction scratch) fits
+    const int cw = is_complex ? 2 : 1;
+    const int sms = num_sms();
+    const long long w = (f + sms - 1) / sms;
+    int wpad = 1;
+    while (wpad < w) wpad <<= 1;
+    const long long blocks = (f + w - 1) / w;
+    const size_t smem = (size_t)cw * 8 * ((size_t)k * w + 2 * (size_t)k + 256);
+    if (wpad <= 256 && smem <= 200 * 1024) {
+      void* kern = is_complex ? (void*)dl_sweep_slice_kernel<true> : (void*)dl_sweep_slice_kernel<false>;
+      int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "dl_sweep smem");
+      if (rc != DECOMP_OK) return rc;
+      double* scratch = nullptr;   // 2 * blocks partials, then the barrier counter
+      rc = check_cuda(cudaMallocAsync(&scratch, sizeof(double) * (2 * blocks + 1), st), "dl_sweep scratch");
+      if (rc != DECOMP_OK) return rc;
+      unsigned* counter = reinterpret_cast<unsigned*>(scratch + 2 * blocks);
+      cudaMemsetAsync(counter, 0, sizeof(double), st);
+      long long lds_ = lds, ldt_ = ldt, ldd_ = ldd;
+      int k_ = (int)k, f_ = (int)f, w_ = (int)w;
+      void* args[] = {(void*)&S, (void*)&lds_, (void*)&T, (void*)&ldt_, (void*)&D, (void*)&ldd_, (void*)&k_, (void*)&f_,
+                      (void*)&w_, (void*)&wpad, (void*)&scratch, (void*)&counter};
+      cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(256), args, smem, st);
+      cudaFreeAsync(scratch, st);
+      return check_cuda(e, "dl_sweep slice launch");
+    }
+  }
   void* kern = is_complex ? (void*)dl_sweep_kernel<true> : (void*)dl_sweep_kernel<false>;
   int per_sm = 0;
   int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0), "dl_sweep occupancy");
