@@ -324,9 +324,13 @@ def test_normalize_rows_and_latch(cplx):
 
 
 @pytest.mark.parametrize('cplx', [False, True])
-@pytest.mark.parametrize('k,f', [(3, 5), (9, 70), (40, 300)])
+@pytest.mark.parametrize('k,f', [(3, 5), (9, 70), (40, 300), (130, 5000), (1500, 3000)])
 def test_dl_sweep(cplx, k, f):
+    """Slice-resident sweep (D slice in shared memory; (130, 5000): 34 columns per block, 64-wide thread rows) and,
+    for (1500, 3000), the L2-streaming kernel that serves slices too large for shared memory."""
     from decomp_b200 import ops
+    if cplx and k > 1000:
+        pytest.skip('the real case covers the large-slice kernel')
     rng = np.random.RandomState(k * f)
 
     def randn(*s):
@@ -344,7 +348,7 @@ def test_dl_sweep(cplx, k, f):
     dD = dev(D)
     ops.dl_sweep(rv(dev(S)), rv(dev(T)), rv(dD), cplx)
     torch.cuda.synchronize()
-    close(host(dD), Dn, 1e-10)
+    close(host(dD), Dn, 1e-10 if k < 100 else 1e-9)
 
 
 @pytest.mark.parametrize('cplx', [False, True])
