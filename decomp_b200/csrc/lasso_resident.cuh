@@ -118,17 +118,6 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       offB[s4] = (wn * 32 + g) * 128 + o;
     }
     const int col_lane = wn * 32 + 2 * q;   // + 8 j
-    double thr0[4], thr1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = col_lane + 8 * j;
-      if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
-        thr0[j] = thr1[j] = __ldg(a.thr + (col >> 1));
-      } else {
-        thr0[j] = __ldg(a.thr + col);
-        thr1[j] = __ldg(a.thr + col + 1);
-      }
-    }
 
     int s = 0;
     uint32_t ph = 0, wph = 0;
@@ -225,6 +214,17 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         // thread ran one after the other.
         auto update = [&](auto LAST, auto CHECK) {
           constexpr bool kLast = decltype(LAST)::value, kCheck = decltype(CHECK)::value;
+          double thr0[4], thr1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = col_lane + 8 * j;
+            if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
+              thr0[j] = thr1[j] = __ldg(a.thr + (col >> 1));
+            } else {
+              thr0[j] = __ldg(a.thr + col);
+              thr1[j] = __ldg(a.thr + col + 1);
+            }
+          }
           unsigned long long tb0[4], tb1[4];
           if constexpr (kCheck) {
 #pragma unroll
