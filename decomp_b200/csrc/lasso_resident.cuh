@@ -95,7 +95,25 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       int s = 0, kb = 0;
       uint32_t ph = 0;
       bool wait = false;
+      const long long per_tile = (long long)a.iters * KB;
+      long long next_tile_at = 0;
+      int tile = 0;
       for (long long n = 0; n < total; ++n) {
+        if (n == next_tile_at) {
+          // a row block starts: pull the NEXT one's w, c and x towards L2, so that its prologue, which every CTA
+          // reaches at about the same time, is not a burst of HBM reads
+          next_tile_at += per_tile;
+          ++tile;
+          if (tile < tiles) {
+            const long long m1 = row_begin + (long long)tile * BM;
+            for (int kb2 = 0; kb2 < KB; ++kb2) tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1);
+            const long long rows = row_end - m1 < BM ? row_end - m1 : BM;
+            for (long long r = 0; r < rows; ++r) {
+              bulk_prefetch_l2(a.c + (m1 + r) * a.ldc, (uint32_t)N * 8u);
+              bulk_prefetch_l2(a.x + (m1 + r) * a.ldx, (uint32_t)N * 8u);
+            }
+          }
+        }
         if (wait) mbar_wait(&empty_bar[s], ph);
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         tma_load_2d(ring + s * stage_bytes, &tmQ, &full_bar[s], kb * BK, 0);
