@@ -211,15 +211,31 @@ __global__ void gershgorin_kernel(const double* __restrict__ G, long long ldg, i
                                   double* __restrict__ thr_out) {
   __shared__ double red[32];
   __shared__ double step_s;
+  __shared__ double part[32][33];
+  // column sums of |G|: 32 columns at a time (coalesced), the rows dealt out to the 32 warps, partial sums combined
+  // in warp order
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   double best = 0.0;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+  for (int jb = 0; jb < k; jb += 32) {
+    const int j = jb + tx;
     double s = 0.0;
-    if (is_complex) {
-      for (int i = 0; i < k; ++i) s += hypot(G[(long long)i * ldg + 2 * j], G[(long long)i * ldg + 2 * j + 1]);
-    } else {
-      for (int i = 0; i < k; ++i) s += fabs(G[(long long)i * ldg + j]);
+    if (j < k) {
+      if (is_complex) {
+        for (int i = ty; i < k; i += 32) s += hypot(G[(long long)i * ldg + 2 * j], G[(long long)i * ldg + 2 * j + 1]);
+      } else {
+        for (int i = ty; i < k; i += 32) s += fabs(G[(long long)i * ldg + j]);
+      }
     }
-    best = fmax(best, s);
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+      double c = 0.0;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) c += part[t][tx];
+      // sums of magnitudes are >= 0 or NaN: ordering by bit pattern keeps a NaN, like numpy's max
+      if ((unsigned long long)__double_as_longlong(c) > (unsigned long long)__double_as_longlong(best)) best = c;
+    }
+    __syncthreads();
   }
   best = block_max_nan(best, red);
   if (threadIdx.x == 0) {
