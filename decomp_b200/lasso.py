@@ -279,7 +279,7 @@ class LassoSolver(object):
         # that costs little (<= 1.3x the flops) or when the iteration is launch-bound anyway
         n_real = k * cw
         self.npad = next((w for w in (32, 64, 128, 256) if w >= n_real), 0)
-        self.resident = bool(USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista')
+        self.resident = bool(USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista', 'acc_ista')
                              and self.npad and ops.lasso_resident_supported(self.npad)
                              and (self.npad == n_real or (self.npad / n_real) ** 2 <= 1.3
                                   or (rows_hint or B) * self.npad * self.npad <= RESIDENT_PAD_WORK))
@@ -357,8 +357,11 @@ class LassoSolver(object):
             self.W_hi, self.W_lo = ops.split_tf32(rview(X))        # w0 = x0 as a TF32 pair, updated in place
             self.W = [X, X]
         elif self.pad:
-            w0, self.Wb = _padded2d(B, k, cplx, self.npad, dev)
-            self.W = [w0, w0]                                      # updated in place by the resident kernel
+            w0, wb0 = _padded2d(B, k, cplx, self.npad, dev)        # updated in place by the resident kernel
+            self.W, self.Wb = [w0, w0], [wb0, wb0]
+            if rule == 'acc_ista':                                 # its last iteration may run per-iteration (finish)
+                w1, wb1 = _padded2d(B, k, cplx, self.npad, dev)
+                self.W, self.Wb = [w0, w1], [wb0, wb1]
             w0.copy_(X)
         else:
             self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
@@ -412,7 +415,8 @@ class LassoSolver(object):
         latch = self.latch
         check = self.checks and (i1 - 1) % 10 == 0
         if self.pad:
-            X, W, C, Q, thr, tolv = self.Xb, self.Wb, self.Cb, self.Q_pad, self.thr_pad, self.tol_pad
+            X, W, C, Q = self.Xb, self.Wb[self.wi], self.Cb, self.Q_pad
+            thr, tolv = self.thr_pad, self.tol_pad
         else:
             X, W, C, Q = rview(self.X), rview(self.W[self.wi]), rview(self.yAh), self.Q_rhs
             thr, tolv = self.thr, self.tol_vec
