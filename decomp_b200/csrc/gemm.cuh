@@ -121,6 +121,20 @@ __device__ __forceinline__ unsigned long long abs_bits(double v) {
   return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
 }
 
+// v * m without touching the FP64 pipe when m is exactly 1.0 or +0.0 (what masks hold): the product is then v, or a
+// zero with v's sign (NaN for a non-finite v), formed with integer instructions; any other weight multiplies.
+// Scalar FP64 instructions of the epilogue warps compete with the DMMAs for the same pipe.
+__device__ __forceinline__ double mask_mul(double v, double m) {
+  const unsigned long long mb = (unsigned long long)__double_as_longlong(m);
+  if (mb == 0x3ff0000000000000ull) return v;
+  if (mb == 0ull) {
+    const unsigned hi = (unsigned)__double2hiint(v);
+    if ((hi & 0x7ff00000u) == 0x7ff00000u) return __longlong_as_double(0x7ff8000000000000ll);   // inf * 0, NaN * 0
+    return __hiloint2double((int)(hi & 0x80000000u), 0);
+  }
+  return v * m;
+}
+
 struct EpiIn {
   Pair p0, p1, p2;
 };
@@ -173,7 +187,7 @@ struct Epilogue {
     } else if constexpr (KIND == DECOMP_EPI_STORE) {
       st_pair(ep.out + row * ep.ldo + col, v0, v1, two);
     } else if constexpr (KIND == DECOMP_EPI_STORE_MASK) {
-      st_pair(ep.out + row * ep.ldo + col, v0 * in.p0.a, v1 * in.p0.b, two);
+      st_pair(ep.out + row * ep.ldo + col, mask_mul(v0, in.p0.a), mask_mul(v1, in.p0.b), two);
     } else if constexpr (KIND == DECOMP_EPI_MU_NUM || KIND == DECOMP_EPI_MU_DEN) {
       double n0, n1, d0, d1;
       if constexpr (KIND == DECOMP_EPI_MU_NUM) {
