@@ -545,3 +545,28 @@ def test_lasso_resident_kernel_matches_the_per_iteration_kernel(method, cplx, k,
         assert err <= 1e-12, (tol, maxiter, err)
         fired += int(it1 < maxiter - 1)
     assert fired > 0                          # the latch did fire inside a multi-iteration launch sequence
+
+
+def test_store_mask_fast_paths_are_exact():
+    """The STORE_MASK epilogue multiplies by weights 0 and 1 with integer instructions: same bits as the FP64 product,
+    signed zeros and non-finite accumulators included; other weights take the multiply."""
+    from decomp_b200 import ops
+    torch.manual_seed(3)
+    M, N, K = 300, 130, 40
+    A = torch.randn((M, K), dtype=torch.float64, device='cuda')
+    B = torch.randn((N, K), dtype=torch.float64, device='cuda')
+    A[7, 3] = float('inf')
+    A[9, 0] = float('nan')
+    mask = torch.tensor([0.0, 1.0, 0.5, 2.0], dtype=torch.float64, device='cuda')[
+        torch.randint(0, 4, (M, N), device='cuda')].contiguous()
+    out = torch.empty((M, N), dtype=torch.float64, device='cuda')
+    plain = torch.empty_like(out)
+    ops.gemm_nt(A, B, ops.epilogue(ops.EPI_STORE, plain))
+    ops.gemm_nt(A, B, ops.epilogue(ops.EPI_STORE_MASK, out, mask=mask))
+    torch.cuda.synchronize()
+    ref = plain * mask
+    nan = torch.isnan(ref)
+    assert torch.equal(torch.isnan(out), nan) and bool(nan.any())
+    same_bits = out.view(torch.int64) == ref.view(torch.int64)
+    assert bool((same_bits | nan).all())
+    assert bool(((ref == 0) & torch.signbit(ref)).any())      # negative zeros were exercised
