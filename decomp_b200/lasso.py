@@ -34,6 +34,7 @@ AVAILABLE_METHODS = ['ista', 'cd', 'acc_ista', 'fista', 'parallel_cd', 'admm']
 AVAILABLE_NNLS_METHODS = ['ista_pos', 'cd_pos', 'acc_ista_pos', 'fista_pos', 'parallel_cd_pos', 'admm_pos']
 DEVICE_RULES = ('ista', 'fista', 'acc_ista')
 RESIDENT_PAD_WORK = 1.5e8   # rows x width^2 below which one iteration is launch-bound (< ~10 us of DMMA)
+RESIDENT_MIN_ITERS = 7      # launches up to this length run per iteration when the batch is not launch-bound
 USE_RESIDENT = True   # several iterations per launch with the iterate on chip where the kernel covers the shape
 POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
 
@@ -278,11 +279,12 @@ class LassoSolver(object):
         # width (in doubles) 32 / 64 / 128 / 256 -- narrower problems are zero-padded up to the next of those when
         # that costs little (<= 1.3x the flops) or when the iteration is launch-bound anyway
         n_real = k * cw
+        self.rows_total = rows_hint or B          # rows of the whole batch when this solver runs one chunk of it
         self.npad = next((w for w in (32, 64, 128, 256) if w >= n_real), 0)
         self.resident = bool(USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista', 'acc_ista')
                              and self.npad and ops.lasso_resident_supported(self.npad)
                              and (self.npad == n_real or (self.npad / n_real) ** 2 <= 1.3
-                                  or (rows_hint or B) * self.npad * self.npad <= RESIDENT_PAD_WORK))
+                                  or self.rows_total * self.npad * self.npad <= RESIDENT_PAD_WORK))
         self.pad = self.resident and self.npad != n_real
         self.Xb = None
         if self.pad:
@@ -441,7 +443,13 @@ class LassoSolver(object):
                 stop = min(end, i + ops.RESIDENT_MAX_ITERS)
                 if self.checks:
                     stop = min(stop, (i + 9) // 10 * 10 + 1)       # a launch ends on the next checking iteration
-                self._launch_resident(i, stop)
+                if stop - i <= RESIDENT_MIN_ITERS and not self.pad and self.rows_total * self.npad ** 2 > RESIDENT_PAD_WORK * 3:
+                    # a resident launch reads and writes the whole state once (~0.27 ms at C2) whatever its length:
+                    # short launches of big batches are cheaper one iteration at a time
+                    for j in range(i, stop):
+                        self._launch(j, rview(self.X))
+                else:
+                    self._launch_resident(i, stop)
                 i = stop
             return
         for i in range(begin, end):
