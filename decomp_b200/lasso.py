@@ -10,14 +10,16 @@ Device data flow (all FP64; complex data as interleaved doubles through the 2x2 
     prologue   s_k = |A_k|, A <- A/s, alpha_k, tol_k, x <- x*s               lasso.py:120-138,163
                G = A A^H (mask: (A * mean(mask)) A^H), 1/L by Gershgorin       lasso.py:285-287,317-319
                yAh = y A^H (mask: (y*mask) A^H)                                lasso.py:289,321
-    iteration  x_new = shrink(w + (yAh - w G)/L, alpha/L)  [+ momentum, + convergence latch]
-               one NT GEMM launch whose epilogue does the whole update         lasso.py:244-256,405-414
-               (mask: w A -> *mask fused in the first GEMM's epilogue, then the same fused launch)
+    iteration  x_new = shrink(w + (yAh - w G)/L, alpha/L)  [+ momentum, + convergence latch]     lasso.py:244-256,405-414
+               no per-problem mask, width <= 256 doubles: the iterate stays on chip and one launch of the resident
+               kernel runs up to 32 iterations (ops.lasso_resident); otherwise one NT GEMM launch per iteration whose
+               epilogue does the whole update (per-problem mask: w A -> *mask fused in a first GEMM's epilogue)
     epilogue   x / s                                                           lasso.py:189
 
 The convergence test (every 10th iteration, global over the batch, lasso.py:293/409) is evaluated inside
-the update launch; when it passes, a device latch is set and every later launch returns immediately, so
-the host never has to synchronise inside the loop to get the reference's result.
+the update launch (launches are cut so that it falls on their last iteration); when it passes, a device latch is
+set and every later launch returns immediately, so the host never has to synchronise inside the loop to get the
+reference's result.  Host arrays with ``tol <= 0`` are solved in row chunks whose copies overlap the iterations.
 """
 import math
 
