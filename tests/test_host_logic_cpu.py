@@ -1,0 +1,86 @@
+"""Host-side scheduling logic of the Lasso driver, without a GPU: how a host batch is cut into row chunks and how
+iterations are grouped into launches of the resident kernel."""
+import types
+
+import pytest
+import torch
+
+from decomp_b200 import lasso, ops
+
+
+@pytest.fixture
+def b200(monkeypatch):
+    monkeypatch.setattr(torch.cuda, 'get_device_properties',
+                        lambda device=None: types.SimpleNamespace(multi_processor_count=148))
+
+
+def test_row_chunks_are_whole_rounds_of_the_grid(b200):
+    assert lasso._row_chunks(1000, 64, 16, None) is None                       # small: one piece
+    assert lasso._row_chunks(10000, 1024, 256, None) is None                   # < 4 rounds of 4736 rows
+    for B, f, width in [(100000, 1024, 256), (19000, 1024, 256), (400000, 512, 1024), (75777, 256, 32),
+                        (3000000, 64, 64)]:
+        chunks = lasso._row_chunks(B, f, width, None)
+        assert chunks is not None and 3 <= len(chunks) <= 4
+        assert chunks[0][0] == 0 and chunks[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+        unit = 128 * max(1, 148 // -(-width // 64))
+        sizes = [r1 - r0 for r0, r1 in chunks]
+        assert sizes[0] % unit == 0 and sizes[-1] == unit                      # short first and last chunk
+        assert sum(1 for n in sizes if n % unit) <= 1                          # the ragged rest rides in one chunk
+        assert sizes[0] <= 2 * unit
+
+
+def _bare_solver(B, npad, checks, pad=False, n_inplace=10 ** 9, group=None):
+    s = object.__new__(lasso.LassoSolver)
+    s.resident, s.checks, s.pad, s.B, s.rows_total, s.npad, s.group = True, checks, pad, B, B, npad, group
+    s.n_inplace, s.poll_at, s.stopped = n_inplace, 10 ** 9, False
+    s.X = torch.zeros((1, 2), dtype=torch.float64)
+    s.calls = []
+    s._launch_resident = lambda i0, i1: s.calls.append(('resident', i0, i1))
+    s._launch = lambda i, out: s.calls.append(('single', i, i + 1))
+    return s
+
+
+def test_launches_without_checks_are_cut_at_the_kernel_limit():
+    s = _bare_solver(1000, 32, checks=False)
+    s.iterate(0, 70)
+    assert s.calls == [('resident', 0, 32), ('resident', 32, 64), ('resident', 64, 70)]
+    assert ops.RESIDENT_MAX_ITERS == 32
+
+
+def test_launches_with_checks_end_on_the_checking_iterations():
+    s = _bare_solver(1000, 32, checks=True)
+    s.iterate(0, 35)
+    # iterations 0, 10, 20, 30 evaluate the test (lasso.py:293/409) and must be the last of their launch
+    assert s.calls == [('resident', 0, 1), ('resident', 1, 11), ('resident', 11, 21), ('resident', 21, 31),
+                       ('resident', 31, 35)]
+    s = _bare_solver(1000, 32, checks=True)
+    s.iterate(5, 12)
+    assert s.calls == [('resident', 5, 11), ('resident', 11, 12)]
+
+
+def test_short_launches_of_big_batches_run_per_iteration():
+    big = _bare_solver(100000, 256, checks=True)
+    big.iterate(0, 21)
+    assert big.calls == [('single', 0, 1), ('resident', 1, 11), ('resident', 11, 21)]
+    big = _bare_solver(100000, 256, checks=False)
+    big.iterate(0, 36)
+    assert big.calls == [('resident', 0, 32)] + [('single', i, i + 1) for i in range(32, 36)]
+    padded = _bare_solver(100000, 256, checks=True, pad=True)                  # padded buffers: always resident
+    padded.iterate(0, 11)
+    assert padded.calls == [('resident', 0, 1), ('resident', 1, 11)]
+
+
+def test_iterate_honours_the_in_place_limit_of_acc_ista():
+    s = _bare_solver(1000, 32, checks=False, n_inplace=9)                      # maxiter 10: the last one is finish()'s
+    s.iterate(0, 10)
+    assert s.calls == [('resident', 0, 9)]
+
+
+def test_momentum_schedules():
+    assert lasso._momentum_schedule('ista', 3) == [0.0, 0.0, 0.0]
+    assert lasso._momentum_schedule('acc_ista', 3) == [0.0, 0.25, 0.4]
+    m = lasso._momentum_schedule('fista', 3)                                   # (beta - 1) / beta_next, beta_0 = 1
+    b1 = 0.5 * (1 + 5 ** 0.5)
+    b2 = 0.5 * (1 + (1 + 4 * b1 * b1) ** 0.5)
+    assert m[0] == 0.0 and abs(m[1] - (b1 - 1) / b2) < 1e-15
