@@ -120,6 +120,8 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
 
 
 PIPELINE_MIN_BYTES = 64 << 20   # host batches below this are solved in one piece
+PIPELINE_MAX_CHUNK_BYTES = 2 << 30   # upper bound of one chunk of y on the device
+PIPELINE_DEPTH = 3              # chunks resident on the device at a time: uploading / iterating / downloading
 
 
 def _row_chunks(B, f, k_cols, device):
@@ -138,7 +140,8 @@ def _row_chunks(B, f, k_cols, device):
         return None
     first = 2 * unit if units >= 8 else unit
     middle = B - first - unit                  # whole rounds plus the ragged rest of the batch
-    pieces = 2 if middle >= 8 * unit else 1
+    pieces = max(2 if middle >= 8 * unit else 1, -(-middle * f * 8 // PIPELINE_MAX_CHUNK_BYTES))
+    pieces = max(1, min(pieces, middle // unit))
     head = (middle // unit // pieces) * unit
     sizes = [first] + [head] * (pieces - 1) + [middle - head * (pieces - 1), unit]
     out, r0 = [], 0
@@ -164,7 +167,8 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     """Host arrays, ``tol <= 0``: every row runs exactly ``maxiter - 1`` iterations whatever the other rows do
     (lasso.py:293/409 never fires), so the batch is solved chunk by chunk with the upload of the next chunk and the
     download of the previous one overlapping the iterations of the current one.  Row results are bitwise those of the
-    one-piece solve: a row's dot products do not depend on which tile it sits in."""
+    one-piece solve: a row's dot products do not depend on which tile it sits in.  Only PIPELINE_DEPTH chunks of at
+    most PIPELINE_MAX_CHUNK_BYTES are on the device at a time, so the host batch may exceed the device memory."""
     cur = torch.cuda.current_stream(device)
     up, down = _copy_streams(device)
     up.wait_stream(cur)
@@ -174,16 +178,24 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     m1 = to_device1d(mask, device) if mask is not None else None
     tdt = getattr(torch, np.dtype(out_dtype).name)
     host = torch.empty((y.shape[0], k), dtype=tdt, pin_memory=True)
-    staged = []
-    with torch.cuda.stream(up):
-        for r0, r1 in chunks:
+    # At most PIPELINE_DEPTH chunks live on the device, so the batch may be larger than HBM: chunk j is uploaded once
+    # chunk j - PIPELINE_DEPTH has been downloaded and its buffers dropped.
+    n = len(chunks)
+    staged, finished = {}, {}
+
+    def upload(j):
+        r0, r1 = chunks[j]
+        with torch.cuda.stream(up):
             yc = to_device2d(y[r0:r1], device, copy=False)
             xc = to_device2d(x[r0:r1], device, copy=False) if x is not None else None
             ev = torch.cuda.Event()
             ev.record(up)
-            staged.append((yc, xc, ev))
-    keep = []
-    for (r0, r1), (yc, xc, ev) in zip(chunks, staged):
+        staged[j] = (yc, xc, ev)
+
+    for j in range(min(n, PIPELINE_DEPTH - 1)):
+        upload(j)
+    for c, (r0, r1) in enumerate(chunks):
+        yc, xc, ev = staged.pop(c)
         cur.wait_event(ev)
         state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision,
                              rows_hint=y.shape[0])      # same kernel choice as the one-piece solve
@@ -193,7 +205,15 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
         down.wait_event(done)
         with torch.cuda.stream(down):
             host[r0:r1].copy_(res, non_blocking=True)
-        keep.append((state, res))
+            copied = torch.cuda.Event()
+            copied.record(down)
+        finished[c] = (copied, yc, xc, state, res)      # the buffers stay referenced until the copy has finished
+        del yc, xc, state, res
+        j = c + PIPELINE_DEPTH - 1
+        if j < n:
+            if j - PIPELINE_DEPTH >= 0:
+                finished.pop(j - PIPELINE_DEPTH)[0].synchronize()
+            upload(j)
     down.synchronize()
     return maxiter - 1, host.numpy()
 

@@ -70,13 +70,16 @@ def test_nmf_single_latent_and_tiny_sizes():
                 assert np.array_equal(np.isfinite(D), np.isfinite(D_ref))
 
 
-@pytest.mark.parametrize('variant', ['plain', 'x0', 'mask2d', 'mask1d', 'complex', 'pos', 'f32'])
+@pytest.mark.parametrize('variant', ['plain', 'x0', 'mask2d', 'mask1d', 'complex', 'pos', 'f32', 'many_chunks'])
 def test_lasso_pipelined_host_path_is_bitwise_the_one_piece_solve(variant, monkeypatch):
     """tol = 0 with host arrays: the batch is uploaded / solved / downloaded chunk by chunk (lasso._solve_pipelined);
     every row must come out exactly as from the one-piece device solve."""
     import torch
     from decomp_b200 import lasso
     monkeypatch.setattr(lasso, 'PIPELINE_MIN_BYTES', 0)
+    if variant == 'many_chunks':            # bounded device memory: small chunks, two resident at a time
+        monkeypatch.setattr(lasso, 'PIPELINE_MAX_CHUNK_BYTES', 5 << 20)
+        monkeypatch.setattr(lasso, 'PIPELINE_DEPTH', 2)
     rng = np.random.RandomState(11)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     B, k, f = 128 * sms * 5 + 77, 24, 32
@@ -93,7 +96,8 @@ def test_lasso_pipelined_host_path_is_bitwise_the_one_piece_solve(variant, monke
     if variant == 'f32':
         A, y = A.astype(np.float32), y.astype(np.float32)
     method = 'fista_pos' if variant == 'pos' else 'fista'
-    assert lasso._row_chunks(B, f, k * (2 if cplx else 1), torch.device('cuda', 0)) is not None
+    chunks = lasso._row_chunks(B, f, k * (2 if cplx else 1), torch.device('cuda', 0))
+    assert chunks is not None and (variant != 'many_chunks' or len(chunks) >= 5)
     it, x = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=12, **kw)
     dev = {n: torch.from_numpy(v).cuda() for n, v in kw.items()}
     it_d, x_d = lasso.solve(torch.from_numpy(y).cuda(), torch.from_numpy(A).cuda(), 0.05, tol=0.0, method=method,

@@ -20,7 +20,7 @@ def test_row_chunks_are_whole_rounds_of_the_grid(b200):
     for B, f, width in [(100000, 1024, 256), (19000, 1024, 256), (400000, 512, 1024), (75777, 256, 32),
                         (3000000, 64, 64)]:
         chunks = lasso._row_chunks(B, f, width, None)
-        assert chunks is not None and 3 <= len(chunks) <= 4
+        assert chunks is not None and len(chunks) >= 3
         assert chunks[0][0] == 0 and chunks[-1][1] == B
         assert all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
         unit = 128 * max(1, 148 // -(-width // 64))
@@ -28,6 +28,7 @@ def test_row_chunks_are_whole_rounds_of_the_grid(b200):
         assert sizes[0] % unit == 0 and sizes[-1] == unit                      # short first and last chunk
         assert sum(1 for n in sizes if n % unit) <= 1                          # the ragged rest rides in one chunk
         assert sizes[0] <= 2 * unit
+        assert max(sizes) * f * 8 <= lasso.PIPELINE_MAX_CHUNK_BYTES + unit * f * 8 or len(chunks) <= 4
 
 
 def _bare_solver(B, npad, checks, pad=False, n_inplace=10 ** 9, group=None):
