@@ -100,7 +100,8 @@ def solve_fastpath(y, A, alpha, x, tol, maxiter, method, xp=None, mask=None, gro
     k = A.shape[0]
     # (a per-problem mask couples the rows through the batch mean of the mask, lasso.py:300-303: one piece)
     if group is None and not float(tol) > 0.0 and not is_torch(y) and (mask is None or mask.ndim == 1):
-        chunks = _row_chunks(flatten_rows(y).shape[0], y.shape[-1], k * (2 if np_dtype(A).kind == 'c' else 1), device)
+        chunks = _row_chunks(flatten_rows(y).shape[0], y.shape[-1], k * (2 if np_dtype(A).kind == 'c' else 1), device,
+                             pinned=_is_pinned(y))
         if chunks is not None:
             it, res = _solve_pipelined(flatten_rows(y), A, float(alpha), None if x is None else flatten_rows(x),
                                        int(maxiter), rule, positive, mask, precision, chunks, device, out_dtype)
@@ -124,12 +125,16 @@ PIPELINE_MAX_CHUNK_BYTES = 2 << 30   # upper bound of one chunk of y on the devi
 PIPELINE_DEPTH = 3              # chunks resident on the device at a time: uploading / iterating / downloading
 
 
-def _row_chunks(B, f, k_cols, device):
+def _row_chunks(B, f, k_cols, device, pinned=True):
     """Row ranges for the pipelined host path, or None when the batch is too small to be worth splitting.
 
     Chunks are whole rounds of the persistent GEMM grid (one CTA tile of 128 rows x 64 columns per SM and round), so
     splitting costs no tile quantisation; a short first chunk lets the iterations start early and a short last one
-    keeps the final device-to-host copy small (the ragged rest of the batch rides in a long middle chunk)."""
+    keeps the final device-to-host copy small (the ragged rest of the batch rides in a long middle chunk).
+
+    Uploads from pageable host memory run at a fifth of the PCIe rate and block the calling thread, which makes them
+    about as long as the iterations they are supposed to hide behind: such a batch is cut into uniform short chunks,
+    so that the host uploads chunk c+1 while the device iterates on chunk c."""
     if B * f * 8 < PIPELINE_MIN_BYTES:
         return None
     sms = torch.cuda.get_device_properties(device).multi_processor_count
@@ -138,6 +143,12 @@ def _row_chunks(B, f, k_cols, device):
     units = B // unit
     if units < 4:
         return None
+    if not pinned:
+        step = 2 * unit
+        out = [(r0, min(B, r0 + step)) for r0 in range(0, B, step)]
+        if len(out) > 1 and out[-1][1] - out[-1][0] < unit:      # a short tail joins its neighbour
+            out[-2:] = [(out[-2][0], B)]
+        return out
     first = 2 * unit if units >= 8 else unit
     middle = B - first - unit                  # whole rounds plus the ragged rest of the batch
     pieces = max(2 if middle >= 8 * unit else 1, -(-middle * f * 8 // PIPELINE_MAX_CHUNK_BYTES))
@@ -150,6 +161,14 @@ def _row_chunks(B, f, k_cols, device):
         r0 += n
     assert r0 == B
     return out
+
+
+def _is_pinned(a):
+    """True if the numpy array lives in page-locked host memory (its copies are asynchronous and at PCIe speed)."""
+    try:
+        return bool(a.size > 0 and torch.from_numpy(a[:1]).is_pinned())      # a view: nothing is copied
+    except (TypeError, ValueError, RuntimeError):
+        return False
 
 
 _COPY_STREAMS = {}
@@ -178,8 +197,8 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     m1 = to_device1d(mask, device) if mask is not None else None
     tdt = getattr(torch, np.dtype(out_dtype).name)
     host = torch.empty((y.shape[0], k), dtype=tdt, pin_memory=True)
-    # At most PIPELINE_DEPTH chunks live on the device, so the batch may be larger than HBM: chunk j is uploaded once
-    # chunk j - PIPELINE_DEPTH has been downloaded and its buffers dropped.
+    # At most PIPELINE_DEPTH chunks live on the device (uploading / iterating / downloading), so the batch may be
+    # larger than HBM: chunk j is uploaded once chunk j - PIPELINE_DEPTH has been downloaded and its buffers dropped.
     n = len(chunks)
     staged, finished = {}, {}
 
@@ -192,8 +211,7 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
             ev.record(up)
         staged[j] = (yc, xc, ev)
 
-    for j in range(min(n, PIPELINE_DEPTH - 1)):
-        upload(j)
+    upload(0)
     for c, (r0, r1) in enumerate(chunks):
         yc, xc, ev = staged.pop(c)
         cur.wait_event(ev)
@@ -209,11 +227,12 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
             copied.record(down)
         finished[c] = (copied, yc, xc, state, res)      # the buffers stay referenced until the copy has finished
         del yc, xc, state, res
-        j = c + PIPELINE_DEPTH - 1
-        if j < n:
-            if j - PIPELINE_DEPTH >= 0:
-                finished.pop(j - PIPELINE_DEPTH)[0].synchronize()
-            upload(j)
+        # the next chunk goes up while this one iterates (from pageable memory the copy blocks this thread, which
+        # is why it comes after the launches above)
+        if c + 1 < n:
+            if c + 1 - PIPELINE_DEPTH >= 0:
+                finished.pop(c + 1 - PIPELINE_DEPTH)[0].synchronize()
+            upload(c + 1)
     down.synchronize()
     return maxiter - 1, host.numpy()
 

@@ -70,7 +70,7 @@ def test_nmf_single_latent_and_tiny_sizes():
                 assert np.array_equal(np.isfinite(D), np.isfinite(D_ref))
 
 
-@pytest.mark.parametrize('variant', ['plain', 'x0', 'mask2d', 'mask1d', 'complex', 'pos', 'f32', 'many_chunks'])
+@pytest.mark.parametrize('variant', ['plain', 'x0', 'mask2d', 'mask1d', 'complex', 'pos', 'f32', 'many_chunks', 'pinned'])
 def test_lasso_pipelined_host_path_is_bitwise_the_one_piece_solve(variant, monkeypatch):
     """tol = 0 with host arrays: the batch is uploaded / solved / downloaded chunk by chunk (lasso._solve_pipelined);
     every row must come out exactly as from the one-piece device solve."""
@@ -95,8 +95,13 @@ def test_lasso_pipelined_host_path_is_bitwise_the_one_piece_solve(variant, monke
         kw['mask'] = np.rint(rng.uniform(0.3, 1.0, size=f))
     if variant == 'f32':
         A, y = A.astype(np.float32), y.astype(np.float32)
+    if variant in ('pinned', 'many_chunks'):    # page-locked input: short first / last chunk, long middle ones
+        yp = torch.empty(y.shape, dtype=torch.float64, pin_memory=True)
+        yp.copy_(torch.from_numpy(y))
+        y = yp.numpy()
+        assert lasso._is_pinned(y) and not lasso._is_pinned(A)
     method = 'fista_pos' if variant == 'pos' else 'fista'
-    chunks = lasso._row_chunks(B, f, k * (2 if cplx else 1), torch.device('cuda', 0))
+    chunks = lasso._row_chunks(B, f, k * (2 if cplx else 1), torch.device('cuda', 0), pinned=lasso._is_pinned(y))
     assert chunks is not None and (variant != 'many_chunks' or len(chunks) >= 5)
     it, x = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=12, **kw)
     dev = {n: torch.from_numpy(v).cuda() for n, v in kw.items()}
