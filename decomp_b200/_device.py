@@ -50,6 +50,57 @@ def full2d(rows, cols, value, cplx=False, device=None):
     return t
 
 
+STAGE_MIN_BYTES = 64 << 20    # pageable arrays from this size on go up through the staged path below
+STAGE_PIECE_BYTES = 32 << 20
+STAGE_SLOTS = 4
+STAGE_THREADS = 4
+_stage = {}
+
+
+def _staged_upload(src, out):
+    """Pageable host array -> device through a ring of page-locked staging buffers filled by a few threads.
+
+    torch's own copy from pageable memory stages through one buffer on the calling thread (11 GB/s measured on the
+    B200 boxes); several memcpy threads feeding asynchronous copies get closer to what the link carries.  ``src`` is a
+    C-contiguous 2-D numpy array, ``out`` a device tensor of the same shape and dtype with contiguous rows.
+    Enqueues on the current stream and returns when the last piece has been handed to the copy engine."""
+    from concurrent.futures import ThreadPoolExecutor
+    if 'pool' not in _stage:
+        _stage['pool'] = ThreadPoolExecutor(max_workers=STAGE_THREADS)
+        _stage['bufs'] = [torch.empty(STAGE_PIECE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(STAGE_SLOTS)]
+    pool, bufs = _stage['pool'], _stage['bufs']
+    rows, cols = src.shape
+    row_bytes = cols * src.itemsize
+    step = max(1, STAGE_PIECE_BYTES // row_bytes)
+    pieces = [(r0, min(rows, r0 + step)) for r0 in range(0, rows, step)]
+    flat = src.view(np.uint8).reshape(rows, row_bytes)
+    stream = torch.cuda.current_stream(out.device)
+    events, futures = [None] * STAGE_SLOTS, {}
+
+    def fill(q):
+        r0, r1 = pieces[q]
+        np.copyto(bufs[q % STAGE_SLOTS].numpy()[:(r1 - r0) * row_bytes].reshape(r1 - r0, row_bytes), flat[r0:r1])
+
+    submitted = 0
+    for p, (r0, r1) in enumerate(pieces):
+        while submitted < len(pieces) and submitted < p + STAGE_SLOTS:
+            slot = submitted % STAGE_SLOTS
+            if events[slot] is not None and submitted >= STAGE_SLOTS:
+                events[slot].synchronize()            # the copy out of this slot (piece submitted - SLOTS) is done
+            futures[submitted] = pool.submit(fill, submitted)
+            submitted += 1
+        futures.pop(p).result()
+        slot = p % STAGE_SLOTS
+        piece = bufs[slot][:(r1 - r0) * row_bytes].view(out.dtype).view(r1 - r0, cols)
+        out[r0:r1].copy_(piece, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        events[slot] = ev
+    for ev in events:
+        if ev is not None:
+            ev.synchronize()                          # the staging buffers are reused by the next call
+
+
 def to_device2d(a, device=None, copy=True):
     """numpy array / torch tensor [rows, cols] -> FP64 (or complex128) device buffer, even pitch.
 
@@ -65,6 +116,10 @@ def to_device2d(a, device=None, copy=True):
             and (cplx or src.stride(0) % 2 == 0) and src.data_ptr() % 16 == 0):
         return src
     out = empty2d(src.shape[0], src.shape[1], cplx, device)
+    if (not is_torch(a) and src.dtype == want and src.dim() == 2 and src.is_contiguous() and out.is_contiguous()
+            and src.numel() * src.element_size() >= STAGE_MIN_BYTES and not src.is_pinned()):
+        _staged_upload(src.numpy(), out)
+        return out
     out.copy_(src, non_blocking=True)
     return out
 

@@ -124,3 +124,21 @@ def test_lasso_row_chunks_cover_the_batch():
             continue
         assert ch[0][0] == 0 and ch[-1][1] == B
         assert all(a[1] == b[0] for a, b in zip(ch, ch[1:])) and all(r1 > r0 for r0, r1 in ch)
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+def test_staged_upload_of_pageable_arrays(cplx, monkeypatch):
+    """Big pageable arrays go up through a ring of page-locked buffers filled by several threads
+    (_device._staged_upload); here with tiny pieces so that the ring wraps many times."""
+    import torch
+    from decomp_b200 import _device
+    monkeypatch.setattr(_device, 'STAGE_MIN_BYTES', 0)
+    monkeypatch.setattr(_device, 'STAGE_PIECE_BYTES', 4096)
+    monkeypatch.setattr(_device, '_stage', {})
+    rng = np.random.RandomState(2)
+    for rows, cols in [(1, 2), (37, 6), (1000, 30), (513, 128)]:
+        a = rng.randn(rows, cols) + (1j * rng.randn(rows, cols) if cplx else 0.0)
+        d = _device.to_device2d(a, torch.device('cuda', 0))
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), a)
+    monkeypatch.setattr(_device, '_stage', {})

@@ -21,3 +21,20 @@ for name, arr in (('pageable', y_page), ('pinned', y_pin)):
             x = None
             t0 = T(); it, x = lasso.solve(arr, A_page, 0.1, tol=0.0, method='fista', maxiter=K); best = min(best, T() - t0)
         print('%-9s %-10s %.1f ms' % (name, mode, best * 1e3))
+
+from decomp_b200 import _device
+d = None
+for name, thr in (('staged (4 threads)', 64 << 20), ('torch pageable copy', 1 << 60)):
+    _device.STAGE_MIN_BYTES = thr
+    best = 1e9
+    for _ in range(3):
+        d = None
+        t0 = T(); d = _device.to_device2d(y_page, dev); best = min(best, T() - t0)
+    print('upload 819 MB, %-20s %.1f ms = %.1f GB/s' % (name, best * 1e3, 0.8192 / best))
+_device.STAGE_MIN_BYTES = 64 << 20
+lasso.PIPELINE_MIN_BYTES = 1 << 60
+for tol in (1e-12,):
+    best = 1e9
+    for _ in range(3):
+        t0 = T(); it, x = lasso.solve(y_page, A_page, 0.1, tol=tol, method='fista', maxiter=K); best = min(best, T() - t0)
+    print('pageable, tol > 0 (one piece, staged upload): %.1f ms' % (best * 1e3))
