@@ -1,5 +1,6 @@
+"""lasso.solve on a host batch cut into many chunks (1e6 problems, 8.2 GB of y): run time and peak device memory."""
 import sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch
 from decomp_b200 import lasso
 rng = np.random.RandomState(0)
