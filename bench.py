@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload both|fista|nmf]
 
 Primary workload (BASELINE.json configs[1]): batched FISTA Lasso, 100 000 problems per GPU, A (256, 1024),
-alpha = 0.1, float64, tol = 0 (fixed iteration count).  One *step* is one FISTA iteration over the whole batch
-= one launch of the fused GEMM + proximal-update kernel.  ``value`` is problem-iterations per second with
-everything resident in HBM; ``e2e`` is the same metric through ``decomp_b200.lasso.solve`` with pinned HOST
-arrays in and a host array out (H2D of y and A, D2H of x inside the timed region).
+alpha = 0.1, float64, tol = 0 (fixed iteration count).  One *step* is one FISTA iteration over the whole batch;
+the iterate-resident kernel runs up to 32 of them per launch (``gpu_launches`` counts the launches, the roofline is
+per launch).  ``value`` is problem-iterations per second with everything resident in HBM; ``e2e`` is the same metric
+through ``decomp_b200.lasso.solve`` with pinned HOST arrays in and a host array out (H2D of y and A, D2H of x inside
+the timed region; the call overlaps them with the iterations chunk by chunk).
 
 Secondary workload (configs[2], reported under "secondary"): NMF multiplicative update, 1 000 000 rows per GPU
 x 4096 features, k = 256, float64; one step is one full sweep (x update + statistics + all-reduce + D update).
