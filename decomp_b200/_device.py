@@ -50,6 +50,7 @@ def full2d(rows, cols, value, cplx=False, device=None):
     return t
 
 
+_STAGED_DTYPES = (torch.float32, torch.float64, torch.complex64, torch.complex128)
 STAGE_MIN_BYTES = 64 << 20    # pageable arrays from this size on go up through the staged path below
 STAGE_PIECE_BYTES = 32 << 20
 STAGE_SLOTS = 4
@@ -62,7 +63,8 @@ def _staged_upload(src, out):
 
     torch's own copy from pageable memory stages through one buffer on the calling thread (11 GB/s measured on the
     B200 boxes); several memcpy threads feeding asynchronous copies get closer to what the link carries.  ``src`` is a
-    C-contiguous 2-D numpy array, ``out`` a device tensor of the same shape and dtype with contiguous rows.
+    C-contiguous 2-D numpy array, ``out`` a device tensor of the same shape with contiguous rows (float32 / complex64
+    sources are widened on the device, piece by piece).
     Enqueues on the current stream and returns when the last piece has been handed to the copy engine."""
     from concurrent.futures import ThreadPoolExecutor
     if 'pool' not in _stage:
@@ -70,6 +72,7 @@ def _staged_upload(src, out):
         _stage['bufs'] = [torch.empty(STAGE_PIECE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(STAGE_SLOTS)]
     pool, bufs = _stage['pool'], _stage['bufs']
     rows, cols = src.shape
+    src_dtype = getattr(torch, src.dtype.name)
     row_bytes = cols * src.itemsize
     step = max(1, STAGE_PIECE_BYTES // row_bytes)
     pieces = [(r0, min(rows, r0 + step)) for r0 in range(0, rows, step)]
@@ -91,7 +94,7 @@ def _staged_upload(src, out):
             submitted += 1
         futures.pop(p).result()
         slot = p % STAGE_SLOTS
-        piece = bufs[slot][:(r1 - r0) * row_bytes].view(out.dtype).view(r1 - r0, cols)
+        piece = bufs[slot][:(r1 - r0) * row_bytes].view(src_dtype).view(r1 - r0, cols)
         out[r0:r1].copy_(piece, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(stream)
@@ -116,7 +119,7 @@ def to_device2d(a, device=None, copy=True):
             and (cplx or src.stride(0) % 2 == 0) and src.data_ptr() % 16 == 0):
         return src
     out = empty2d(src.shape[0], src.shape[1], cplx, device)
-    if (not is_torch(a) and src.dtype == want and src.dim() == 2 and src.is_contiguous() and out.is_contiguous()
+    if (not is_torch(a) and src.dtype in _STAGED_DTYPES and src.dim() == 2 and src.is_contiguous() and out.is_contiguous()
             and src.numel() * src.element_size() >= STAGE_MIN_BYTES and not src.is_pinned()):
         _staged_upload(src.numpy(), out)
         return out

@@ -141,4 +141,9 @@ def test_staged_upload_of_pageable_arrays(cplx, monkeypatch):
         d = _device.to_device2d(a, torch.device('cuda', 0))
         torch.cuda.synchronize()
         assert np.array_equal(d.cpu().numpy(), a)
+        a32 = a.astype(np.complex64 if cplx else np.float32)            # widened on the device, piece by piece
+        d = _device.to_device2d(a32, torch.device('cuda', 0))
+        torch.cuda.synchronize()
+        assert d.dtype == (torch.complex128 if cplx else torch.float64)
+        assert np.array_equal(d.cpu().numpy(), a32.astype(a.dtype))
     monkeypatch.setattr(_device, '_stage', {})
