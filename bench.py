@@ -1,24 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the deComP hot path on B200 ("Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload both|fista|nmf]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs a,b,...]
 
 Primary workload (BASELINE.json configs[1]): batched FISTA Lasso, 100 000 problems per GPU, A (256, 1024),
-alpha = 0.1, float64, tol = 0 (fixed iteration count).  One *step* is one FISTA iteration over the whole batch;
-the iterate-resident kernel runs up to 32 of them per launch (``gpu_launches`` counts the launches, the roofline is
-per launch).  ``value`` is problem-iterations per second with everything resident in HBM; ``e2e`` is the same metric
-through ``decomp_b200.lasso.solve`` with pinned HOST arrays in and a host array out (H2D of y and A, D2H of x inside
-the timed region; the call overlaps them with the iterations chunk by chunk).
+alpha = 0.1, float64, tol = 0 (fixed iteration count).  One *step* is one FISTA iteration over the whole batch.
+After W warm-up iterations (plus one untimed region, so that the launch pattern being timed has run before), the
+region "K iterations" is timed ``--repeats`` times back to back on the same solve (CUDA events on the launching
+stream between barriers, max over ranks) and the MEDIAN region is reported: ``value`` = problems x K / median.
+``gpu_launches`` counts the kernel launches of one region, the roofline is per launch of the dominant kernel.
 
-Secondary workload (configs[2], reported under "secondary"): NMF multiplicative update, 1 000 000 rows per GPU
-x 4096 features, k = 256, float64; one step is one full sweep (x update + statistics + all-reduce + D update).
+``e2e``: the same metric through ``decomp_b200.lasso.solve`` with ORDINARY (pageable) numpy arrays in and a numpy
+array out -- H2D of y and A, set-up GEMMs, K iterations, D2H of x inside the timed region (median of 5 calls, max
+over ranks); ``e2e_pinned`` is the same call on page-locked arrays.
 
-Multi-GPU (torchrun, one rank per GPU): the sample axis is sharded, every rank holds the same number of rows
-(weak scaling).  FISTA needs no data-path collective; NMF all-reduces the [k, f] and [k, k] statistics per
-sweep over NCCL.  Timing: CUDA events on the launching stream between barriers, max over ranks.
+Secondary (configs[2]): NMF multiplicative update, 4096 features, k = 256, float64; one step = one full sweep.
+``secondary`` = 1 000 000 rows per GPU (weak scaling); ``secondary_strong`` = 1 000 000 rows in total, sharded
+(what the ">= 7x at 8 GPUs" target is quoted on), both with the time spent in the all-reduces per sweep, a CPU
+baseline at n = 65 536 and an end-to-end ``nmf.solve`` call on host arrays at n = 131 072.
+``extra_configs``: configs[3] (dictionary-learning minibatch step, complex128, 10 % mask) and configs[4] (masked
+NMF sweep and masked FISTA iteration, 1 000 000 rows per GPU x 1024, k = 128).
+``parity_multi_gpu``: small sharded NMF / Lasso / dictionary-learning solves checked against the numpy oracle on
+rank 0, outside every timed region.
 
-``--impl reference`` times the CPU restatement of the reference's numpy algorithm (oracle/decomp_oracle.py,
-kind "port": the reference itself is a Python package that does not travel to the GPU box) on the host cores.
+``--impl reference`` times the reference's own numpy implementation on the host cores with all BLAS threads: the
+unmodified reference from baseline/_ref when it is installed there (kind "reference"), else the pinned numpy port
+oracle/decomp_oracle.py (kind "port").  Under torchrun only rank 0 works.
 """
 import argparse
 import json
@@ -33,8 +40,14 @@ if ROOT not in sys.path:
 
 FISTA = dict(batch=100000, k=256, f=1024, alpha=0.1)
 NMF = dict(n=1000000, f=4096, k=256)
-CPU_FISTA_BATCH = 24576         # bounded CPU sample (problems): ~10 s per 100 iterations on 16 cores
+C5 = dict(n=1000000, f=1024, k=128)
+C4 = dict(n=32768, f=2048, k=512, minibatch=8192)
+CPU_FISTA_BATCH = 24576         # bounded CPU sample of the cpu_baseline leg (problems)
+CPU_NMF_ROWS = 65536
+E2E_NMF_ROWS = 131072
+CPU_REFERENCE_BUDGET = 1.4e7    # problem-iterations of the --impl reference run (~60 s on 16 cores)
 L2_BYTES = 126 * 2 ** 20
+ALL_LEGS = ('fista', 'tf32', 'e2e', 'nmf', 'nmf_strong', 'nmf_e2e', 'configs', 'parity', 'cpu')
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -98,12 +111,19 @@ class ClockSampler(object):
 def merge_clocks(a, b):
     if a is None:
         return b
+    if b is None:
+        return a
     out = dict(a)
     if b.get('sm_mhz') is not None and (a.get('sm_mhz') is None or b['sm_mhz'] < a['sm_mhz']):
         out['sm_mhz'] = b['sm_mhz']
     out['reasons'] = sorted(set(a.get('reasons', [])) | set(b.get('reasons', [])))
     out['samples'] = a.get('samples', 0) + b.get('samples', 0)
     return out
+
+
+def median(v):
+    s = sorted(v)
+    return s[len(s) // 2] if len(s) % 2 else 0.5 * (s[len(s) // 2 - 1] + s[len(s) // 2])
 
 
 def load_peaks():
@@ -113,6 +133,24 @@ def load_peaks():
             p = json.load(fh)
         return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/)."""
+    path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
+def fista_config(batch, world):
+    """The config both arms print (the CPU arm's bounded sample is described in its cpu_baseline.sample)."""
+    return {'workload': 'batched FISTA Lasso: %d problems per GPU, A (256,1024), alpha=0.1, float64, tol=0 '
+                        '(BASELINE.json configs[1])' % batch,
+            'l2': 'working set per iteration 5*B*k*8 = %.0f MB > %d MB L2 (inputs larger than L2, no flush)'
+                  % (5.0 * batch * 256 * 8 / 1e6, L2_BYTES // 2 ** 20),
+            'parallelism': 'sample axis sharded over %d GPU(s), no data-path collective' % world}
 
 
 # ------------------------------------------------------------------------------------------ synthetic data
@@ -136,49 +174,68 @@ def fista_data_device(torch, B, k, f, seed, device):
 def fista_data_host(np, B, k, f, seed):
     rng = np.random.RandomState(seed)
     A = np.random.RandomState(0).randn(k, f)
-    xt = rng.randn(B, k) * np.rint(rng.uniform(size=(B, k)))
-    y = xt.dot(A) + 0.1 * rng.randn(B, f)
+    y = np.empty((B, f))
+    chunk = 16384
+    for r0 in range(0, B, chunk):
+        r1 = min(B, r0 + chunk)
+        xt = rng.randn(r1 - r0, k) * np.rint(rng.uniform(size=(r1 - r0, k)))
+        y[r0:r1] = xt.dot(A) + 0.1 * rng.randn(r1 - r0, f)
     return y, A
 
 
-def nmf_data_device(torch, n, f, k, seed, device):
-    """Ct, Dt = max(N(0,1), 0); Y = Ct Dt + 0.1 N(0,1); D0 = max(Dt + 0.3 N, 0.1) replicated."""
+def nmf_data_device(torch, n, f, k, seed, device, masked=False):
+    """SURVEY.md 8(d) C3/C5: Ct, Dt = max(N(0,1), 0); Y = Ct Dt + 0.1 N(0,1); D0 = max(Dt + 0.3 N, 0.1) replicated;
+    mask = (U > 0.1) in y's dtype."""
     g = torch.Generator(device=device)
     g.manual_seed(0)
     Dt = torch.randn((k, f), dtype=torch.float64, device=device, generator=g).clamp_(min=0.0)
     D0 = (Dt + 0.3 * torch.randn((k, f), dtype=torch.float64, device=device, generator=g)).clamp_(min=0.1)
     g.manual_seed(2000 + seed)
     y = torch.empty((n, f), dtype=torch.float64, device=device)
+    mask = torch.empty((n, f), dtype=torch.float64, device=device) if masked else None
     chunk = 32768
     for r0 in range(0, n, chunk):
         r1 = min(n, r0 + chunk)
         ct = torch.randn((r1 - r0, k), dtype=torch.float64, device=device, generator=g).clamp_(min=0.0)
         y[r0:r1] = ct @ Dt
         y[r0:r1] += 0.1 * torch.randn((r1 - r0, f), dtype=torch.float64, device=device, generator=g)
+        if masked:
+            mask[r0:r1] = (torch.rand((r1 - r0, f), dtype=torch.float64, device=device, generator=g) > 0.1).double()
+    return y, D0, mask
+
+
+def nmf_data_host(np, n, f, k, seed):
+    rng = np.random.RandomState(seed)
+    Dt = np.maximum(rng.randn(k, f), 0.0)
+    D0 = np.maximum(Dt + 0.3 * rng.randn(k, f), 0.1)
+    y = np.empty((n, f))
+    chunk = 16384
+    for r0 in range(0, n, chunk):
+        r1 = min(n, r0 + chunk)
+        y[r0:r1] = np.maximum(rng.randn(r1 - r0, k), 0.0).dot(Dt) + 0.1 * rng.randn(r1 - r0, f)
     return y, D0
 
 
-# ------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_fista(np, steps, warmup, batch=CPU_FISTA_BATCH):
-    """The oracle port of decomp.lasso (fista, tol=0) on the host cores; returns problem-iterations/s."""
-    from oracle import decomp_oracle as orc
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_fista(np, arm, steps, warmup, batch):
+    """decomp.lasso.solve(method='fista', tol=0) on the host cores; returns (problem-iterations/s, seconds)."""
     k, f, alpha = FISTA['k'], FISTA['f'], FISTA['alpha']
     y, A = fista_data_host(np, batch, k, f, 0)
     if warmup > 0:
-        orc.lasso(y[:1024], A, alpha, tol=0.0, method='fista', maxiter=max(1, min(warmup, 5)))
+        arm.lasso(y[:1024], A, alpha, tol=0.0, method='fista', maxiter=max(1, min(warmup, 5)))
     t0 = time.perf_counter()
-    orc.lasso(y, A, alpha, tol=0.0, method='fista', maxiter=steps)
+    arm.lasso(y, A, alpha, tol=0.0, method='fista', maxiter=steps)
     dt = time.perf_counter() - t0
     return batch * steps / dt, dt
 
 
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        n = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
-        return max(n) if n else (os.cpu_count() or 1)
-    except Exception:
-        return os.cpu_count() or 1
+def cpu_nmf(np, arm, sweeps, rows):
+    """decomp.nmf.solve(method='mu', 'l2', tol=0) on the host cores; returns (row-iterations/s, seconds)."""
+    y, D0 = nmf_data_host(np, rows, NMF['f'], NMF['k'], 0)
+    t0 = time.perf_counter()
+    arm.nmf(y, D0, tol=0.0, maxiter=sweeps + 1)
+    dt = time.perf_counter() - t0
+    return rows * sweeps / dt, dt
 
 
 def run_reference(args):
@@ -186,19 +243,21 @@ def run_reference(args):
     if rank != 0:
         return
     import numpy as np
+    from oracle import cpu_arm
+    cores = cpu_arm.set_blas_threads()
+    arm = cpu_arm.load()
     steps = max(1, args.steps)
-    batch = CPU_FISTA_BATCH
-    value, dt = cpu_fista(np, steps, args.warmup, batch)
+    batch = int(min(args.batch, max(4096, CPU_REFERENCE_BUDGET // steps)))
+    value, dt = cpu_fista(np, arm, steps, args.warmup, batch)
     line = {
         'impl': 'reference',
         'metric': 'batched_fista_problem_iterations_per_second', 'value': value, 'unit': 'problem-iters/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': dt / steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'batched FISTA Lasso, A (256,1024), alpha=0.1, float64, tol=0 '
-                               '(BASELINE.json configs[1]); CPU sample of %d problems' % batch},
-        'cpu_baseline': {'value': value, 'unit': 'problem-iters/s', 'cores': blas_threads(), 'kind': 'port',
-                         'sample': '%d problems x %d FISTA iterations, numpy/OpenBLAS via oracle/decomp_oracle.py '
-                                   '(set-up GEMMs included)' % (batch, steps)},
+        'config': fista_config(args.batch, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'problem-iters/s', 'cores': cores, 'kind': arm.kind,
+                         'sample': '%d problems x %d FISTA iterations in one lasso.solve call (%.1f s, set-up GEMMs '
+                                   'included), %s' % (batch, steps, dt, arm.where)},
         'e2e': {'value': value, 'unit': 'problem-iters/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -224,7 +283,8 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=device)
         group = dist.group.WORLD
 
-    from decomp_b200 import lasso, nmf, ops
+    from decomp_b200 import dictionary_learning, lasso, nmf, ops
+    legs = set(args.legs)
 
     def barrier():
         torch.cuda.synchronize()
@@ -232,59 +292,88 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
+    def max_over_ranks(v):
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn):
-        """fn enqueues work on the current stream; returns (device ms max over ranks, launches, clocks)."""
+    def timed_regions(region, repeats):
+        """region(r) enqueues region r on the current stream.  Returns ([ms per region, max over ranks], launches of
+        one region, clocks sampled over all regions)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out, launches = [], 0
         barrier()
-        before = ops.LAUNCHES
         with ClockSampler(local) as cs:
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        launches = ops.LAUNCHES - before
+            for r in range(repeats):
+                barrier()
+                before = ops.LAUNCHES
+                e0.record()
+                region(r)
+                e1.record()
+                torch.cuda.synchronize()
+                launches = ops.LAUNCHES - before
+                out.append(max_over_ranks(e0.elapsed_time(e1)))
         barrier()
-        return max_over_ranks(ms), launches, cs.summary()
+        return out, launches, cs.summary()
+
+    def wall_calls(call, repeats):
+        """call() is a blocking host-level API call; returns the median wall time in seconds, max over ranks."""
+        times = []
+        for _ in range(repeats):
+            barrier()
+            t0 = time.perf_counter()
+            call()
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        return max_over_ranks(median(times)), times
 
     hbm_peak, hbm_src = load_peaks()
+    traffic = load_traffic()
     dmma_peak = ops.probe_dmma_tflops()
-    K, W = max(1, args.steps), max(0, args.warmup)
+    K, W, R = max(1, args.steps), max(0, args.warmup), max(1, args.repeats)
     out = {}
     clocks = None
+    cpu_arm_mod = None
+    if rank == 0 and world == 1 and 'cpu' in legs:
+        from oracle import cpu_arm as cpu_arm_mod
+        cpu_cores = cpu_arm_mod.set_blas_threads()
+        cpu = cpu_arm_mod.load()
 
     # ---------------------------------------------------------------- batched FISTA (primary)
-    if args.workload in ('both', 'fista'):
+    if 'fista' in legs:
         B, k, f, alpha = args.batch, FISTA['k'], FISTA['f'], FISTA['alpha']
         y, A = fista_data_device(torch, B, k, f, rank, device)
-        solver = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K, 'fista', False)
+        total = W + K * (R + 1)
+        solver = lasso.LassoSolver(y, A, alpha, None, 0.0, total, 'fista', False)
         solver.iterate(0, W)
-        ms, launches, clocks = timed(lambda: solver.iterate(W, W + K))
-        state = solver.finish()
-        xs = state.result
+        solver.iterate(W, W + K)                               # untimed: the launch pattern of a region has run once
+        ms_list, launches, clocks = timed_regions(lambda r: solver.iterate(W + K * (r + 1), W + K * (r + 2)), R)
+        ms = median(ms_list)
+        xs = solver.finish().result
         finite = bool(torch.isfinite(xs).all().item())
         nnz = float((xs != 0).double().mean().item())
-        del solver, state, xs
+        del solver, xs
         sec = ms * 1e-3
-        per_launch = K / float(max(launches, 1))            # iterations one launch of the resident kernel runs
+        per_launch = K / float(max(launches, 1))            # iterations one launch of the dominant kernel runs
         flops_launch = 2.0 * B * k * k * per_launch         # SURVEY.md 8(d): 2 B k^2 per iteration
         bytes_launch = 5.0 * B * k * 8                      # read yAh, w, x_prev; write x_new, w_next: once per launch
         t_launch = sec / max(launches, 1)
+        resident = per_launch > 1.0
         out['fista'] = {
             'value': B * world * K / sec, 'iters_per_s': K / sec, 'ms_per_step': ms / K, 'launches': launches,
             'finite': finite, 'nonzero_fraction': nnz,
+            'timing': {'regions_ms': ms_list, 'statistic': 'median of %d timed regions of %d iterations each' % (R, K),
+                       'min_ms': min(ms_list), 'max_ms': max(ms_list)},
             'roofline': {'bound': 'tensor', 'achieved': flops_launch / t_launch / 1e12, 'peak': dmma_peak,
                          'unit': 'TFLOP/s', 'frac': flops_launch / t_launch / 1e12 / dmma_peak,
-                         'traffic': args.traffic_fista,
-                         'kernel': 'lasso_resident_kernel (iterate resident in shared memory, Q streamed by TMA, '
-                                   'DMMA GEMM + ISTA/FISTA update, up to 32 iterations per launch)',
+                         'traffic': traffic.get('lasso_resident_dram_bytes_per_launch' if resident
+                                                else 'fista_proxq_dram_bytes_per_launch'),
+                         'traffic_source': traffic.get('lasso_resident_source' if resident else 'fista_proxq_source'),
+                         'kernel': ('lasso_resident_kernel (iterate resident in shared memory, Q streamed by TMA, '
+                                    'DMMA GEMM + ISTA/FISTA update, up to 32 iterations per launch)') if resident else
+                                   'gemm_f64_proxq_kernel (one FISTA iteration per launch)',
                          'iterations_per_launch': per_launch,
                          'peak_source': 'FP64 tensor (DMMA.8x8x4) issue rate measured live by '
                                         'decomp_probe_dmma_tflops(); MEASURED_PEAKS.json has no FP64 entry',
@@ -294,14 +383,17 @@ def run_ours(args):
                                  'frac': bytes_launch / t_launch / 1e9 / hbm_peak, 'peak_source': hbm_src}},
         }
         # ---- the TF32-split (tcgen05) variant of the same iterations: reported beside, never as the headline
-        if not args.no_tf32:
-            solver = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K, 'fista', False, precision='tf32x3')
-            solver.iterate(0, W)
-            ms32, launches32, c32 = timed(lambda: solver.iterate(W, W + K))
+        if 'tf32' in legs:
+            R32 = min(R, 5)
+            solver = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K * (R32 + 1), 'fista', False, precision='tf32x3')
+            solver.iterate(0, W + K)
+            ms32_list, launches32, c32 = timed_regions(
+                lambda r: solver.iterate(W + K * (r + 1), W + K * (r + 2)), R32)
             clocks = merge_clocks(clocks, c32)
+            ms32 = median(ms32_list)
             x32 = solver.finish().result
-            ref = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K, 'fista', False)
-            ref.iterate(0, W + K)
+            ref = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K * (R32 + 1), 'fista', False)
+            ref.iterate(0, W + K * (R32 + 1))
             x64 = ref.finish().result
             dev_err = float(((x32 - x64).abs().max() / x64.abs().max()).item())
             del solver, ref, x32, x64
@@ -312,135 +404,357 @@ def run_ours(args):
                 'ms_per_step': ms32 / K, 'launches': launches32, 'dtype': 'tf32x3 GEMM (FP32 accumulate) + f64 update',
                 'max_rel_diff_x_vs_fp64': dev_err,
                 'roofline': {'bound': 'hbm', 'achieved': bytes32 / t32 / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                             'frac': bytes32 / t32 / 1e9 / hbm_peak, 'traffic': None,
+                             'frac': bytes32 / t32 / 1e9 / hbm_peak, 'traffic': traffic.get('tf32x3_dram_bytes_per_iteration'),
                              'kernel': 'tf32x3_gemm_kernel (tcgen05.mma kind::tf32, TMEM) + proxq_apply_kernel',
                              'algorithmic_bytes_per_iteration': bytes32, 'peak_source': hbm_src},
             }
-        # ---- end to end through the public API with pinned host buffers
-        yh = torch.empty((B, f), dtype=torch.float64, pin_memory=True)
-        Ah = torch.empty((k, f), dtype=torch.float64, pin_memory=True)
-        yh.copy_(y)
-        Ah.copy_(A)
-        del y
-        torch.cuda.synchronize()
-        y_np, A_np = yh.numpy(), Ah.numpy()
-        lasso.solve(y_np[:4096], A_np, alpha, tol=0.0, method='fista', maxiter=3)       # allocator / module warm-up
-        e2e_ms = []
-        x_np = None
-        for _ in range(3):
-            x_np = None        # drop the previous result: its page-locked block returns to torch's host cache
-            barrier()
-            t0 = time.perf_counter()
-            it, x_np = lasso.solve(y_np, A_np, alpha, tol=0.0, method='fista', maxiter=K)
-            torch.cuda.synchronize()
-            e2e_ms.append((time.perf_counter() - t0) * 1e3)
-        e2e = max_over_ranks(min(e2e_ms)) * 1e-3
-        assert it == K - 1 and x_np.shape == (B, k)
-        out['fista']['e2e'] = {'value': B * world * K / e2e, 'unit': 'problem-iters/s',
-                               'h2d_bytes_per_step': (y_np.nbytes + A_np.nbytes) / K,
-                               'd2h_bytes_per_step': x_np.nbytes / K, 'ms_per_call': e2e * 1e3,
-                               'note': 'one lasso.solve(maxiter=steps) call with host arrays: H2D of y and A, '
-                                       'set-up GEMMs, steps iterations, D2H of x, all inside the timed region '
-                                       '(tol = 0: the call runs the batch in row chunks so that copies overlap the '
-                                       'iterations); bytes are per call / steps'}
-        del yh, Ah, y_np, A_np, x_np
+        # ---- end to end through the public API: ordinary numpy arrays first, page-locked ones beside
+        if 'e2e' in legs:
+            y_np, A_np = y.cpu().numpy(), A.cpu().numpy()              # pageable host arrays
+            del y
+            torch.cuda.empty_cache()
+            lasso.solve(y_np[:8192], A_np, alpha, tol=0.0, method='fista', maxiter=3)    # allocator / module warm-up
+            res = {}
+
+            def call(yy, AA):
+                res['x'] = None     # drop the previous result: its page-locked block returns to torch's host cache
+                res['it'], res['x'] = lasso.solve(yy, AA, alpha, tol=0.0, method='fista', maxiter=K)
+
+            call(y_np, A_np)
+            e2e, e2e_times = wall_calls(lambda: call(y_np, A_np), 5)
+            assert res['it'] == K - 1 and res['x'].shape == (B, k)
+            h2d, d2h = (y_np.nbytes + A_np.nbytes) / K, res['x'].nbytes / K
+            note = ('one lasso.solve(maxiter=steps) call with %s numpy arrays in and a numpy array out: H2D of y and '
+                    'A, set-up GEMMs, steps iterations, D2H of x, all inside the timed region (tol = 0: the call runs '
+                    'the batch in row chunks so that copies overlap the iterations); median of 5 calls, max over '
+                    'ranks; bytes are per call / steps')
+            out['fista']['e2e'] = {'value': B * world * K / e2e, 'unit': 'problem-iters/s',
+                                   'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'ms_per_call': e2e * 1e3,
+                                   'host_memory': 'pageable', 'calls_ms': [t * 1e3 for t in e2e_times],
+                                   'h2d_gbs_per_gpu_if_copy_only': (y_np.nbytes + A_np.nbytes) / e2e / 1e9,
+                                   'note': note % 'ordinary (pageable)'}
+            yh = torch.empty((B, f), dtype=torch.float64, pin_memory=True)
+            Ah = torch.empty((k, f), dtype=torch.float64, pin_memory=True)
+            yh.copy_(torch.from_numpy(y_np))
+            Ah.copy_(torch.from_numpy(A_np))
+            del y_np, A_np
+            yp, Ap = yh.numpy(), Ah.numpy()
+            call(yp, Ap)
+            e2ep, e2ep_times = wall_calls(lambda: call(yp, Ap), 5)
+            out['fista']['e2e_pinned'] = {'value': B * world * K / e2ep, 'unit': 'problem-iters/s',
+                                          'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                                          'ms_per_call': e2ep * 1e3, 'host_memory': 'page-locked',
+                                          'calls_ms': [t * 1e3 for t in e2ep_times], 'note': note % 'page-locked'}
+            res.clear()
+            del yh, Ah, yp, Ap
+        else:
+            del y
         torch.cuda.empty_cache()
 
-    # ---------------------------------------------------------------- NMF-MU (secondary)
-    if args.workload in ('both', 'nmf'):
-        n, f, k = args.rows, NMF['f'], NMF['k']
-        Kn = max(2, args.nmf_steps)
-        Wn = 3
-        y, D0 = nmf_data_device(torch, n, f, k, rank, device)
-        X = torch.ones((n, k), dtype=torch.float64, device=device)
-        solver = nmf.MuSolver(y, D0, X, 0.0, group=group)
+    # ---------------------------------------------------------------- NMF-MU (secondary): weak and strong scaling
+    def nmf_leg(n_rows, label, masked=False, shape=NMF):
+        f, k = shape['f'], shape['k']
+        Kn, Wn, Rn = max(2, args.nmf_steps), 2, 3
+        y, D0, mask = nmf_data_device(torch, n_rows, f, k, rank, device, masked=masked)
+        X = torch.ones((n_rows, k), dtype=torch.float64, device=device)
+        solver = nmf.MuSolver(y, D0, X, 0.0, mask=mask, group=group)
         for it in range(1, Wn + 1):
             solver.sweep(it)
-        ms, launches, c2 = timed(lambda: [solver.sweep(it) for it in range(Wn + 1, Wn + Kn + 1)])
-        clocks = merge_clocks(clocks, c2)
-        D = solver.Dbuf[(Wn + Kn) % 2]
+        solver.comm_events = [] if world > 1 else None
+        ms_list, launches, c2 = timed_regions(
+            lambda r: [solver.sweep(it) for it in range(Wn + 1 + r * Kn, Wn + 1 + (r + 1) * Kn)], Rn)
+        ms = median(ms_list)
+        comm_ms = None
+        if solver.comm_events:
+            torch.cuda.synchronize()
+            per_sweep = [sum(a.elapsed_time(b) for a, b in evs) for evs in solver.comm_events]
+            comm_ms = max_over_ranks(median(per_sweep))
+        D = solver.Dbuf[(Wn + Rn * Kn) % 2]
         finite = bool(torch.isfinite(D).all().item() and torch.isfinite(X).all().item())
         sec = ms * 1e-3
-        flops_sweep = 4.0 * n * k * f + 4.0 * n * k * k + 4.0 * k * k * f
-        bytes_sweep = 2.0 * n * f * 8 + 6.0 * n * k * 8                        # Y twice; X, NEG r/w
+        n_total = n_rows * world if label != 'strong' else args.strong_rows
+        if masked:
+            flops_sweep = 12.0 * n_rows * k * f                                   # no re-association under a mask
+            bytes_sweep = 2.0 * n_rows * f * 8 + 2.0 * n_rows * k * 8             # Y*M and M once (row-block fused)
+        else:
+            flops_sweep = 4.0 * n_rows * k * f + 4.0 * n_rows * k * k + 4.0 * k * k * f
+            bytes_sweep = 1.0 * n_rows * f * 8 + 2.0 * n_rows * k * 8             # Y once + C r/w
         t_sweep = sec / Kn
-        out['nmf'] = {
-            'metric': 'nmf_mu_row_iterations_per_second', 'value': n * world * Kn / sec, 'unit': 'row-iters/s',
+        res = {
+            'metric': 'nmf_mu_row_iterations_per_second', 'value': n_total * Kn / sec, 'unit': 'row-iters/s',
             'iters_per_s': Kn / sec, 'ms_per_step': ms / Kn, 'steps': Kn, 'warmup': Wn, 'launches': launches,
-            'finite': finite,
-            'config': {'workload': 'NMF-MU l2, %d rows per GPU x %d features, k=%d, float64, tol=0 '
-                                   '(BASELINE.json configs[2], weak scaling)' % (n, f, k)},
+            'rows_per_gpu': n_rows, 'rows_total': n_total, 'finite': finite,
+            'timing': {'regions_ms': ms_list, 'statistic': 'median of %d regions of %d sweeps' % (Rn, Kn)},
+            'allreduce_ms_per_sweep': comm_ms,
+            'allreduce_bytes_per_sweep': (2 * k * f if masked else k * f + k * k) * 8 if world > 1 else 0,
             'roofline': {'bound': 'tensor', 'achieved': flops_sweep / t_sweep / 1e12, 'peak': dmma_peak,
-                         'unit': 'TFLOP/s', 'frac': flops_sweep / t_sweep / 1e12 / dmma_peak, 'traffic': None,
-                         'kernel': 'whole sweep: gemm_f64_kernel<NT, MU_NUM> (Y D^T) + gemm_f64_kernel<TN> (X^T Y) '
-                                   'dominate with 2nkf flop each',
+                         'unit': 'TFLOP/s', 'frac': flops_sweep / t_sweep / 1e12 / dmma_peak,
+                         'traffic': traffic.get('nmf_sweep_dram_bytes' if not masked else 'nmf_masked_sweep_dram_bytes'),
+                         'kernel': 'whole sweep (per GPU): gemm_f64_kernel<NT, MU_NUM> (Y D^T) + gemm_f64_kernel<TN> '
+                                   '(X^T Y) dominate with 2nkf flop each' if not masked else
+                                   'whole masked sweep (per GPU): six 2nkf GEMMs, [n,f] intermediate fused where the '
+                                   'B2B kernel applies',
                          'algorithmic_flops_per_sweep': flops_sweep,
                          'hbm': {'algorithmic_bytes_per_sweep': bytes_sweep,
                                  'achieved_gbs': bytes_sweep / t_sweep / 1e9, 'peak_gbs': hbm_peak}},
         }
-        del solver, y, X, D0, D
+        del solver, y, X, D0, D, mask
+        torch.cuda.empty_cache()
+        return res, c2
+
+    if 'nmf' in legs:
+        res, c2 = nmf_leg(args.rows, 'weak')
+        res['config'] = {'workload': 'NMF-MU l2, %d rows per GPU x %d features, k=%d, float64, tol=0 '
+                                     '(BASELINE.json configs[2] shape, weak scaling)' % (args.rows, NMF['f'], NMF['k'])}
+        res['scaling'] = 'weak'
+        out['nmf'] = res
+        clocks = merge_clocks(clocks, c2)
+    if 'nmf_strong' in legs:
+        n_tot = args.strong_rows
+        lo, hi = rank * n_tot // world, (rank + 1) * n_tot // world
+        if world == 1 and 'nmf' in out and args.rows == n_tot:
+            res = dict(out['nmf'])
+            res['same_run_as_secondary'] = True
+        else:
+            res, c2 = nmf_leg(hi - lo, 'strong')
+            clocks = merge_clocks(clocks, c2)
+        res['config'] = {'workload': 'NMF-MU l2, %d rows IN TOTAL x %d features, k=%d, float64, tol=0, sample axis '
+                                     'sharded over %d GPU(s) with all-reduce of X^T Y [k,f] and X^T X [k,k] per sweep '
+                                     '(BASELINE.json configs[2], strong scaling)' % (n_tot, NMF['f'], NMF['k'], world)}
+        res['scaling'] = 'strong'
+        res['sweeps_per_s'] = res['iters_per_s']
+        out['nmf_strong'] = res
+    if 'nmf_e2e' in legs:
+        n_e, f, k = args.e2e_nmf_rows, NMF['f'], NMF['k']
+        y_d, D0_d, _ = nmf_data_device(torch, n_e, f, k, rank, device)
+        y_np, D_np = y_d.cpu().numpy(), D0_d.cpu().numpy()
+        del y_d, D0_d
+        sweeps = max(2, args.nmf_steps)
+        nmf.solve(y_np[:4096], D_np, tol=0.0, maxiter=3)
+        res = {}
+
+        def call_nmf():
+            res.clear()
+            res['out'] = nmf.solve(y_np, D_np, tol=0.0, maxiter=sweeps + 1)
+
+        call_nmf()
+        t_e, times = wall_calls(call_nmf, 3)
+        it_e, D_e, x_e = res['out']
+        assert it_e == sweeps + 1 and x_e.shape == (n_e, k)
+        out['nmf_e2e'] = {'value': n_e * world * sweeps / t_e, 'unit': 'row-iters/s', 'ms_per_call': t_e * 1e3,
+                          'rows_per_gpu': n_e, 'sweeps': sweeps, 'host_memory': 'pageable',
+                          'h2d_bytes_per_step': (y_np.nbytes + D_np.nbytes + n_e * k * 8) / sweeps,
+                          'd2h_bytes_per_step': (x_e.nbytes + D_e.nbytes) / sweeps,
+                          'calls_ms': [t * 1e3 for t in times],
+                          'note': 'one nmf.solve(tol=0, maxiter=sweeps+1) call with ordinary numpy arrays in and out '
+                                  '(H2D of y, D and the default x = ones; D2H of D and x), median of 3 calls'}
+        res.clear()
+        del y_np, D_np, D_e, x_e
         torch.cuda.empty_cache()
 
-    # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        v, dt = cpu_fista(np, 100, 1)
-        cpu = {'value': v, 'unit': 'problem-iters/s', 'cores': blas_threads(), 'kind': 'port',
-               'sample': '%d problems x 100 FISTA iterations (%.1f s), numpy/OpenBLAS via oracle/decomp_oracle.py'
-                         % (CPU_FISTA_BATCH, dt)}
+    # ---------------------------------------------------------------- BASELINE configs[3] and [4]
+    if 'configs' in legs:
+        extra = {}
+        res, c2 = nmf_leg(args.c5_rows, 'weak', masked=True, shape=C5)
+        clocks = merge_clocks(clocks, c2)
+        res['config'] = {'workload': 'masked NMF-MU l2, %d rows per GPU x %d, k=%d, 10 %% missing, float64 '
+                                     '(BASELINE.json configs[4], per-GPU shard)' % (args.c5_rows, C5['f'], C5['k'])}
+        extra['c5_masked_nmf_sweep'] = res
+        # masked FISTA iteration (the Lasso-C step of configs[4])
+        n5, f5, k5 = args.c5_rows, C5['f'], C5['k']
+        y5, A5, m5 = nmf_data_device(torch, n5, f5, k5, rank, device, masked=True)
+        s5 = lasso.LassoSolver(y5, A5, 0.1, None, 0.0, 100000, 'fista', False, mask=m5)
+        s5.iterate(0, 3)
+        ms5, l5, c5 = timed_regions(lambda r: s5.iterate(3 + 5 * r, 8 + 5 * r), 3)
+        clocks = merge_clocks(clocks, c5)
+        t5 = median(ms5) * 1e-3 / 5
+        fl5 = 4.0 * n5 * k5 * f5
+        by5 = n5 * f5 * 8.0 + 5.0 * n5 * k5 * 8
+        extra['c5_masked_fista_iter'] = {
+            'value': n5 * world / t5, 'unit': 'problem-iters/s', 'ms_per_step': t5 * 1e3, 'launches_per_iteration': l5 / 5.0,
+            'rows_per_gpu': n5,
+            'roofline': {'bound': 'tensor', 'achieved': fl5 / t5 / 1e12, 'peak': dmma_peak, 'unit': 'TFLOP/s',
+                         'frac': fl5 / t5 / 1e12 / dmma_peak, 'traffic': traffic.get('masked_fista_dram_bytes_per_iteration'),
+                         'algorithmic_flops_per_iteration': fl5,
+                         'hbm': {'algorithmic_bytes_per_iteration': by5, 'achieved_gbs': by5 / t5 / 1e9,
+                                 'peak_gbs': hbm_peak}},
+            'config': {'workload': 'masked FISTA iteration ((w A)*M) A^H, %d problems per GPU, A (%d,%d), float64 '
+                                   '(the Lasso-C step of BASELINE.json configs[4])' % (n5, k5, f5)}}
+        del s5, y5, A5, m5
+        torch.cuda.empty_cache()
+        # dictionary-learning minibatch step (configs[3]); the ranks share each minibatch when world > 1
+        n4, f4, k4, mb = C4['n'], C4['f'], C4['k'], C4['minibatch']
+        g = torch.Generator(device=device)
+        g.manual_seed(7)
+
+        def crandn(*s):
+            return torch.complex(torch.randn(s, dtype=torch.float64, device=device, generator=g),
+                                 torch.randn(s, dtype=torch.float64, device=device, generator=g))
+
+        Dt = crandn(k4, f4)
+        y4 = (crandn(n4, k4) * torch.rand((n4, k4), dtype=torch.float64, device=device, generator=g)) @ Dt
+        y4 += 0.1 * crandn(n4, f4)
+        D04 = Dt + 0.2 * crandn(k4, f4)
+        m4 = (torch.rand((n4, f4), dtype=torch.float64, device=device, generator=g) > 0.1).double()
+        kw4 = dict(tol=0.0, minibatch=mb, maxiter=2, lasso_method='fista', lasso_iter=10, mask=m4, random_seed=0,
+                   group=group)
+        dictionary_learning.solve(y4[:2 * mb], D04, 0.1, **dict(kw4, mask=m4[:2 * mb]))        # warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        before = ops.LAUNCHES
+        e0.record()
+        it4, D4, x4 = dictionary_learning.solve(y4, D04, 0.1, **kw4)
+        e1.record()
+        torch.cuda.synchronize()
+        steps4 = n4 // mb
+        ms4 = max_over_ranks(e0.elapsed_time(e1)) / steps4
+        fl4 = (10 * 16 * k4 * f4 + 8 * k4 * f4) * float(mb) + 2.0 * k4 * k4 * f4 * mb + 8.0 * k4 * k4 * f4
+        extra['c4_dl_masked_step'] = {
+            'value': 1e3 / ms4, 'unit': 'minibatch-steps/s', 'ms_per_step': ms4, 'minibatch': mb,
+            'launches_per_step': (ops.LAUNCHES - before) / float(steps4),
+            'finite': bool(torch.isfinite(torch.view_as_real(D4)).all().item()),
+            'roofline': {'bound': 'tensor', 'achieved': fl4 / ms4 / 1e9, 'peak': dmma_peak, 'unit': 'TFLOP/s',
+                         'frac': fl4 / ms4 / 1e9 / dmma_peak / world, 'traffic': None,
+                         'algorithmic_flops_per_step': fl4,
+                         'note': 'flops = 10 masked FISTA iterations + x^H(y*m) + Hermitian half of the masked '
+                                 'statistics (2 k^2 f per row) + atom update; frac is per GPU'},
+            'config': {'workload': 'dictionary learning block_cd, complex128 y %dx%d (one epoch of %d minibatch steps '
+                                   'of %d rows; BASELINE.json configs[3] has n=200000), k=%d, 10 %% mask, fista x10, '
+                                   '%d GPU(s) sharing each minibatch' % (n4, f4, steps4, mb, k4, world)}}
+        del y4, D04, m4, Dt, D4, x4
+        torch.cuda.empty_cache()
+        out['extra_configs'] = extra
+
+    # ---------------------------------------------------------------- multi-GPU parity self-check (outside timing)
+    if 'parity' in legs:
+        out['parity'] = parity_check(np, torch, dist, world, rank, group, device)
+
+    # ---------------------------------------------------------------- CPU baselines (rank 0, N = 1 only)
+    cpu_f = cpu_n = None
+    if cpu_arm_mod is not None:
+        v, dt = cpu_fista(np, cpu, 100, 1, CPU_FISTA_BATCH)
+        cpu_f = {'value': v, 'unit': 'problem-iters/s', 'cores': cpu_cores, 'kind': cpu.kind,
+                 'sample': '%d problems x 100 FISTA iterations (%.1f s), %s' % (CPU_FISTA_BATCH, dt, cpu.where)}
+        if 'nmf' in legs or 'nmf_strong' in legs:
+            v, dt = cpu_nmf(np, cpu, 2, CPU_NMF_ROWS)
+            cpu_n = {'value': v, 'unit': 'row-iters/s', 'cores': cpu_cores, 'kind': cpu.kind,
+                     'sample': 'n = %d rows x %d features, k=%d, 2 sweeps of nmf.solve (%.1f s), %s'
+                               % (CPU_NMF_ROWS, NMF['f'], NMF['k'], dt, cpu.where)}
 
     if rank == 0:
-        prim = out.get('fista') or out.get('nmf')
         if 'fista' in out:
+            prim = out['fista']
+            cfg = fista_config(args.batch, world)
+            cfg['timing'] = prim['timing']['statistic']
             line = {
                 'metric': 'batched_fista_problem_iterations_per_second', 'value': prim['value'],
                 'unit': 'problem-iters/s', 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': prim['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': 'batched FISTA Lasso: %d problems per GPU, A (256,1024), alpha=0.1, float64, '
-                                       'tol=0 (BASELINE.json configs[1])' % args.batch,
-                           'l2': 'working set per iteration 5*B*k*8 = %.0f MB > %d MB L2 (inputs larger than L2, '
-                                 'no flush)' % (5.0 * args.batch * 256 * 8 / 1e6, L2_BYTES // 2 ** 20),
-                           'parallelism': 'sample axis sharded over %d GPU(s), no data-path collective' % world},
-                'iters_per_s': prim['iters_per_s'],
-                'roofline': prim['roofline'], 'e2e': prim['e2e'], 'gpu_launches': prim['launches'],
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+                'iters_per_s': prim['iters_per_s'], 'timing': prim['timing'],
+                'roofline': prim['roofline'], 'gpu_launches': prim['launches'],
                 'results_finite': prim['finite'],
             }
-            if 'nmf' in out:
-                line['secondary'] = out['nmf']
-            if 'tf32x3' in prim:
-                line['tf32x3'] = prim['tf32x3']
+            for key in ('e2e', 'e2e_pinned', 'tf32x3'):
+                if key in prim:
+                    line[key] = prim[key]
+            if cpu_f is not None:
+                line['cpu_baseline'] = cpu_f
         else:
-            line = dict(out['nmf'])
-            line.update({'n_gpus': world, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                         'dtype': 'f64', 'data': 'synthetic', 'gpu_launches': prim['launches']})
-        if cpu is not None:
-            line['cpu_baseline'] = cpu
+            first = out.get('nmf') or out.get('nmf_strong') or {}
+            line = dict(first)
+            line.update({'n_gpus': world, 'higher_is_better': True, 'vs_baseline': None, 'dtype': 'f64',
+                         'data': 'synthetic', 'gpu_launches': first.get('launches', 0)})
+        if 'nmf' in out and 'fista' in out:
+            line['secondary'] = out['nmf']
+        if 'nmf_strong' in out:
+            line['secondary_strong'] = out['nmf_strong']
+        for key in ('secondary', 'secondary_strong'):
+            if key in line and cpu_n is not None:
+                line[key]['cpu_baseline'] = cpu_n
+            if key in line and 'nmf_e2e' in out:
+                line[key]['e2e'] = out['nmf_e2e']
+        if 'extra_configs' in out:
+            line['extra_configs'] = out['extra_configs']
+        if 'parity' in out:
+            line['parity_multi_gpu'] = out['parity']
         line['clocks'] = clocks
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+def parity_check(np, torch, dist, world, rank, group, device):
+    """Small solves with the sample axis sharded over the ranks (all ranks at once when world > 1), compared with the
+    numpy oracle on the same seeded inputs; relative max-norm errors and iteration counts. Test infrastructure."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import golden_cases as gc
+    from decomp_b200 import dictionary_learning, lasso, nmf
+    from oracle import decomp_oracle as orc
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    def shard(a):
+        n = a.shape[0]
+        return a[rank * n // world:(rank + 1) * n // world]
+
+    res = {'world': world, 'tolerance': 1e-10}
+    worst = 0.0
+    y, D0, mask = gc._nmf_data(1501, 130, 24, 5)
+    for name, m in (('nmf', None), ('nmf_mask', mask)):
+        it, D, x = nmf.solve(shard(y), D0.copy(), tol=1e-4, maxiter=400, mask=None if m is None else shard(m), group=group)
+        it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=1e-4, maxiter=400, mask=m)
+        res[name] = {'it': it, 'it_oracle': it0, 'err_D': rel(D, D_ref), 'err_x': rel(x, shard(x_ref))}
+        worst = max(worst, res[name]['err_D'], res[name]['err_x'], float(it != it0))
+    A, yl, maskl, _ = gc._lasso_data((901,), 24, 40, 3)
+    for name, m in (('lasso', None), ('lasso_mask', maskl)):
+        it, x = lasso.solve_fastpath(shard(yl), A, 0.05, None, 1e-6, 1000, 'fista', None,
+                                     mask=None if m is None else shard(m), group=group)
+        it0, x_ref = orc.lasso(yl, A, 0.05, tol=1e-6, method='fista', maxiter=1000, mask=m)
+        res[name] = {'it': it, 'it_oracle': it0, 'err_x': rel(x, shard(x_ref))}
+        worst = max(worst, res[name]['err_x'], float(it != it0))
+    for cplx in (False, True):
+        yd, Dd, md = gc._dl_data(230, 33, 12, 9, cplx)
+        for masked in (False, True):
+            yy = yd * md if masked else yd
+            kw = dict(tol=0.0, minibatch=63, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
+                      mask=md if masked else None, random_seed=4)
+            it, D, x = dictionary_learning.solve(yy, Dd.copy(), 0.05, group=group, **kw)
+            it0, D_ref, x_ref = orc.dictionary_learning(yy, Dd.copy(), 0.05, **kw)
+            name = 'dl_%s_%s' % ('c128' if cplx else 'f64', 'mask' if masked else 'nomask')
+            res[name] = {'it': it, 'it_oracle': it0, 'err_D': rel(D, D_ref), 'err_x': rel(x, x_ref)}
+            worst = max(worst, res[name]['err_D'], res[name]['err_x'], float(it != it0))
+    if world > 1:
+        t = torch.tensor([worst], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = float(t.item())
+    res['worst_error_over_ranks'] = worst
+    res['pass'] = bool(worst < 1e-10)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--repeats', type=int, default=10, help='timed regions of --steps iterations (median reported)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='both', choices=['both', 'fista', 'nmf'])
+    ap.add_argument('--legs', default='all', help='comma list of ' + ','.join(ALL_LEGS) + ' (default all)')
+    ap.add_argument('--skip', default='', help='comma list of legs to leave out')
     ap.add_argument('--batch', type=int, default=FISTA['batch'], help='FISTA problems per GPU')
-    ap.add_argument('--rows', type=int, default=NMF['n'], help='NMF rows per GPU')
-    ap.add_argument('--nmf-steps', type=int, default=5)
-    ap.add_argument('--no-cpu', action='store_true')
-    ap.add_argument('--no-tf32', action='store_true')
+    ap.add_argument('--rows', type=int, default=NMF['n'], help='NMF rows per GPU (weak-scaling leg)')
+    ap.add_argument('--strong-rows', type=int, default=NMF['n'], help='NMF rows in total (strong-scaling leg)')
+    ap.add_argument('--e2e-nmf-rows', type=int, default=E2E_NMF_ROWS)
+    ap.add_argument('--c5-rows', type=int, default=C5['n'], help='rows per GPU of the configs[4] legs')
+    ap.add_argument('--nmf-steps', type=int, default=4)
     args = ap.parse_args()
-    # dram bytes per launch of the dominant kernel, copied from the committed ncu --set full capture
-    args.traffic_fista = None
-    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            args.traffic_fista = json.load(fh).get('fista_prox_dram_bytes_per_launch')
+    legs = list(ALL_LEGS) if args.legs == 'all' else [s for s in args.legs.split(',') if s]
+    args.legs = [s for s in legs if s not in set(args.skip.split(','))]
+    for s in args.legs:
+        if s not in ALL_LEGS:
+            raise SystemExit('unknown leg ' + s)
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':

@@ -5,6 +5,9 @@ even row pitch, which is what the TMA tensor maps of the GEMM need (16-byte row 
 float32 / complex64 inputs are widened on entry and narrowed on exit: the hot path computes
 in FP64 throughout.
 """
+import threading
+import warnings
+
 import numpy as np
 import torch
 
@@ -56,6 +59,7 @@ STAGE_PIECE_BYTES = 32 << 20
 STAGE_SLOTS = 4
 STAGE_THREADS = 4
 _stage = {}
+_stage_lock = threading.Lock()    # one staged upload at a time per process: the ring of pinned buffers is shared
 
 
 def _staged_upload(src, out):
@@ -63,60 +67,81 @@ def _staged_upload(src, out):
 
     torch's own copy from pageable memory stages through one buffer on the calling thread (11 GB/s measured on the
     B200 boxes); several memcpy threads feeding asynchronous copies get closer to what the link carries.  ``src`` is a
-    C-contiguous 2-D numpy array, ``out`` a device tensor of the same shape with contiguous rows (float32 / complex64
-    sources are widened on the device, piece by piece).
+    C-contiguous numpy array, ``out`` a contiguous device tensor with the same number of elements (float32 /
+    complex64 sources are widened on the device, piece by piece).  The array is cut into pieces of STAGE_PIECE_BYTES
+    over its flat element range, whatever its row length.
     Enqueues on the current stream and returns when the last piece has been handed to the copy engine."""
     from concurrent.futures import ThreadPoolExecutor
-    if 'pool' not in _stage:
-        _stage['pool'] = ThreadPoolExecutor(max_workers=STAGE_THREADS)
-        _stage['bufs'] = [torch.empty(STAGE_PIECE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(STAGE_SLOTS)]
-    pool, bufs = _stage['pool'], _stage['bufs']
-    rows, cols = src.shape
-    src_dtype = getattr(torch, src.dtype.name)
-    row_bytes = cols * src.itemsize
-    step = max(1, STAGE_PIECE_BYTES // row_bytes)
-    pieces = [(r0, min(rows, r0 + step)) for r0 in range(0, rows, step)]
-    flat = src.view(np.uint8).reshape(rows, row_bytes)
-    stream = torch.cuda.current_stream(out.device)
-    events, futures = [None] * STAGE_SLOTS, {}
+    with _stage_lock:
+        if 'pool' not in _stage:
+            _stage['pool'] = ThreadPoolExecutor(max_workers=STAGE_THREADS)
+            _stage['bufs'] = [torch.empty(STAGE_PIECE_BYTES, dtype=torch.uint8, pin_memory=True)
+                              for _ in range(STAGE_SLOTS)]
+        pool, bufs = _stage['pool'], _stage['bufs']
+        src_dtype = getattr(torch, src.dtype.name)
+        flat = src.reshape(-1)
+        out_flat = out.view(-1)
+        total = flat.shape[0]
+        step = max(1, STAGE_PIECE_BYTES // src.itemsize)
+        pieces = [(e0, min(total, e0 + step)) for e0 in range(0, total, step)]
+        stream = torch.cuda.current_stream(out.device)
+        events, futures = [None] * STAGE_SLOTS, {}
 
-    def fill(q):
-        r0, r1 = pieces[q]
-        np.copyto(bufs[q % STAGE_SLOTS].numpy()[:(r1 - r0) * row_bytes].reshape(r1 - r0, row_bytes), flat[r0:r1])
+        def fill(q):
+            e0, e1 = pieces[q]
+            np.copyto(bufs[q % STAGE_SLOTS].numpy()[:(e1 - e0) * src.itemsize].view(src.dtype), flat[e0:e1])
 
-    submitted = 0
-    for p, (r0, r1) in enumerate(pieces):
-        while submitted < len(pieces) and submitted < p + STAGE_SLOTS:
-            slot = submitted % STAGE_SLOTS
-            if events[slot] is not None and submitted >= STAGE_SLOTS:
-                events[slot].synchronize()            # the copy out of this slot (piece submitted - SLOTS) is done
-            futures[submitted] = pool.submit(fill, submitted)
-            submitted += 1
-        futures.pop(p).result()
-        slot = p % STAGE_SLOTS
-        piece = bufs[slot][:(r1 - r0) * row_bytes].view(src_dtype).view(r1 - r0, cols)
-        out[r0:r1].copy_(piece, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        events[slot] = ev
-    for ev in events:
-        if ev is not None:
-            ev.synchronize()                          # the staging buffers are reused by the next call
+        submitted = 0
+        try:
+            for p, (e0, e1) in enumerate(pieces):
+                while submitted < len(pieces) and submitted < p + STAGE_SLOTS:
+                    slot = submitted % STAGE_SLOTS
+                    if events[slot] is not None and submitted >= STAGE_SLOTS:
+                        events[slot].synchronize()        # the copy out of this slot (piece submitted - SLOTS) is done
+                    futures[submitted] = pool.submit(fill, submitted)
+                    submitted += 1
+                futures.pop(p).result()
+                slot = p % STAGE_SLOTS
+                piece = bufs[slot][:(e1 - e0) * src.itemsize].view(src_dtype)
+                out_flat[e0:e1].copy_(piece, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                events[slot] = ev
+        finally:
+            for fut in futures.values():                  # after an error: nobody may still be writing into the ring
+                try:
+                    fut.result()
+                except Exception:
+                    pass
+            for ev in events:
+                if ev is not None:
+                    ev.synchronize()                      # the staging buffers are reused by the next call
+
+
+def _from_numpy(a):
+    """torch view of a numpy array; arrays torch cannot alias (read-only, negative or otherwise exotic strides) are
+    copied into a C-contiguous one first, as the reference's numpy code would accept them."""
+    if any(s < 0 for s in a.strides):
+        a = np.ascontiguousarray(a)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore', UserWarning)       # read-only arrays: the inputs are only ever read
+        try:
+            return torch.from_numpy(a)
+        except (ValueError, TypeError):
+            return torch.from_numpy(np.ascontiguousarray(a))
 
 
 def to_device2d(a, device=None, copy=True):
     """numpy array / torch tensor [rows, cols] -> FP64 (or complex128) device buffer, even pitch.
 
-    With copy=False a suitably laid out CUDA tensor is used in place (read-only inputs)."""
+    With copy=False a suitably laid out CUDA tensor that already lives on ``device`` is used in place (read-only
+    inputs)."""
     device = device or require_cuda()
-    if is_torch(a):
-        src = a
-    else:
-        src = torch.from_numpy(np.ascontiguousarray(a)) if not a.flags.writeable else torch.from_numpy(a)
+    src = a if is_torch(a) else _from_numpy(a)
     cplx = src.is_complex()
     want = torch.complex128 if cplx else torch.float64
-    if (not copy and src.is_cuda and src.dtype == want and src.dim() == 2 and src.stride(1) == 1
-            and (cplx or src.stride(0) % 2 == 0) and src.data_ptr() % 16 == 0):
+    if (not copy and src.is_cuda and src.device == device and src.dtype == want and src.dim() == 2
+            and src.stride(1) == 1 and (cplx or src.stride(0) % 2 == 0) and src.data_ptr() % 16 == 0):
         return src
     out = empty2d(src.shape[0], src.shape[1], cplx, device)
     if (not is_torch(a) and src.dtype in _STAGED_DTYPES and src.dim() == 2 and src.is_contiguous() and out.is_contiguous()
@@ -129,7 +154,7 @@ def to_device2d(a, device=None, copy=True):
 
 def to_device1d(a, device=None):
     device = device or require_cuda()
-    src = a if is_torch(a) else torch.from_numpy(np.ascontiguousarray(a))
+    src = a if is_torch(a) else _from_numpy(np.ascontiguousarray(a))
     return src.to(device=device, dtype=torch.float64, non_blocking=True).contiguous()
 
 

@@ -457,9 +457,24 @@ using namespace dcp;
 
 extern "C" {
 
+size_t decomp_dl_sweep_workspace_bytes(int64_t k, int64_t f, int32_t is_complex) {
+  (void)k;
+  (void)is_complex;
+  if (f <= 0) return 0;
+  // two partial sums per block (slice kernel: <= f blocks; L2-streaming kernel: <= 8 blocks per SM) + the counter
+  const long long cap = 8LL * num_sms();
+  const long long blocks = f > cap ? f : cap;
+  return sizeof(double) * (size_t)(2 * blocks + 2);
+}
+
 int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t ldt, double* D, int64_t ldd, int64_t k,
-                        int64_t f, int32_t is_complex, void* stream) {
+                        int64_t f, int32_t is_complex, void* workspace, size_t workspace_bytes, void* stream) {
   if (k <= 0 || f <= 0) return DECOMP_OK;
+  if (workspace == nullptr || workspace_bytes < decomp_dl_sweep_workspace_bytes(k, f, is_complex)) {
+    set_error("decomp_dl_sweep_f64: workspace too small (%zu < %zu)", workspace_bytes,
+              decomp_dl_sweep_workspace_bytes(k, f, is_complex));
+    return DECOMP_ERR_INVALID;
+  }
   cudaStream_t st = as_stream(stream);
   {
     // slice-resident sweep when a block's [k, w] slice of D (+ two rows of S + the reduction scratch) fits
@@ -475,9 +490,7 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
       int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "dl_sweep smem");
       if (rc != DECOMP_OK) return rc;
-      double* scratch = nullptr;   // 2 * blocks partials, then the barrier counter
-      rc = check_cuda(cudaMallocAsync(&scratch, sizeof(double) * (2 * blocks + 1), st), "dl_sweep scratch");
-      if (rc != DECOMP_OK) return rc;
+      double* scratch = reinterpret_cast<double*>(workspace);   // 2 * blocks partials, then the barrier counter
       unsigned* counter = reinterpret_cast<unsigned*>(scratch + 2 * blocks);
       cudaMemsetAsync(counter, 0, sizeof(double), st);
       long long lds_ = lds, ldt_ = ldt, ldd_ = ldd;
@@ -485,7 +498,6 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
       void* args[] = {(void*)&S, (void*)&lds_, (void*)&T, (void*)&ldt_, (void*)&D, (void*)&ldd_, (void*)&k_, (void*)&f_,
                       (void*)&w_, (void*)&wpad, (void*)&scratch, (void*)&counter};
       cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(256), args, smem, st);
-      cudaFreeAsync(scratch, st);
       return check_cuda(e, "dl_sweep slice launch");
     }
   }
@@ -498,15 +510,12 @@ int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t l
   int blocks = groups;
   const int cap = per_sm * num_sms();
   if (blocks > cap) blocks = cap;
-  double* partials = nullptr;
-  rc = check_cuda(cudaMallocAsync(&partials, sizeof(double) * 2 * blocks, st), "dl_sweep scratch");
-  if (rc != DECOMP_OK) return rc;
+  double* partials = reinterpret_cast<double*>(workspace);
   long long lds_ = lds, ldt_ = ldt, ldd_ = ldd;
   int k_ = (int)k, f_ = (int)f;
   void* args[] = {(void*)&S, (void*)&lds_, (void*)&T, (void*)&ldt_, (void*)&D, (void*)&ldd_, (void*)&k_, (void*)&f_,
                   (void*)&partials};
   cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(256), args, 0, st);
-  cudaFreeAsync(partials, st);
   return check_cuda(e, "dl_sweep launch");
 }
 

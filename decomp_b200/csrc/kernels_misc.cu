@@ -583,23 +583,34 @@ int decomp_mask_mul_f64(const double* A, int64_t lda, const double* mask, int64_
   return DECOMP_OK;
 }
 
-// workspace-free column sums: the partial buffer lives in a small static device allocation per call size
-int decomp_col_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
-                        void* stream) {
-  if (cols <= 0) return DECOMP_OK;
-  cudaStream_t st = as_stream(stream);
+static int col_sums_chunks(int64_t rows) {
   int chunks = (int)((rows + 4095) / 4096);
   if (chunks < 1) chunks = 1;
   if (chunks > 1024) chunks = 1024;
-  double* partial = nullptr;
-  int rc = check_cuda(cudaMallocAsync(&partial, (size_t)chunks * cols * sizeof(double), st), "col_sums scratch");
-  if (rc != DECOMP_OK) return rc;
+  return chunks;
+}
+
+size_t decomp_col_sums_workspace_bytes(int64_t rows, int64_t cols) {
+  if (cols <= 0) return 0;
+  return (size_t)col_sums_chunks(rows) * (size_t)cols * sizeof(double);
+}
+
+// column sums in two deterministic stages: per row chunk into the caller's workspace, then over the chunks
+int decomp_col_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (cols <= 0) return DECOMP_OK;
+  if (workspace == nullptr || workspace_bytes < decomp_col_sums_workspace_bytes(rows, cols)) {
+    set_error("decomp_col_sums_f64: workspace too small (%zu < %zu)", workspace_bytes,
+              decomp_col_sums_workspace_bytes(rows, cols));
+    return DECOMP_ERR_INVALID;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int chunks = col_sums_chunks(rows);
+  double* partial = reinterpret_cast<double*>(workspace);
   dim3 grid((unsigned)((cols + 127) / 128), (unsigned)chunks);
   col_sums_kernel<<<grid, 128, 0, st>>>(A, lda, rows, cols, partial, chunks);
   col_sums_finish_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(partial, cols, chunks, scale, out);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(partial, st);
-  return check_cuda(e, "col_sums");
+  return check_cuda(cudaGetLastError(), "col_sums");
 }
 
 int decomp_row_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,

@@ -163,6 +163,7 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
     else:
         S = zeros2d(k, k, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
+        sweep_ws = ops.dl_sweep_workspace(k, f, cplx, dev)
     dist = torch.distributed if group is not None else None
     if dist is not None:
         world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -238,7 +239,7 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                     ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
                 if not masked:
                     Dn.copy_(D)
-                    ops.dl_sweep(rview(S), rview(T), rview(Dn), cplx)                                  # :154-159
+                    ops.dl_sweep(rview(S), rview(T), rview(Dn), cplx, ws=sweep_ws)                            # :154-159
                 else:
                     ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)                # :216-222
                 if checks:

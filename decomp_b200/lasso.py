@@ -321,6 +321,11 @@ class LassoSolver(object):
         # that costs little (<= 1.3x the flops) or when the iteration is launch-bound anyway
         n_real = k * cw
         self.rows_total = rows_hint or B          # rows of the whole batch when this solver runs one chunk of it
+        if group is not None and rows_hint is None:
+            # the kernel choice below must not depend on the size of this rank's shard: use the largest shard
+            rows = torch.tensor([B], dtype=torch.int64, device=dev)
+            torch.distributed.all_reduce(rows, op=torch.distributed.ReduceOp.MAX, group=group)
+            self.rows_total = int(rows.item())
         self.npad = next((w for w in (32, 64, 128, 256) if w >= n_real), 0)
         self.resident = bool(USE_RESIDENT and not self.tf32 and not full_mask and rule in ('ista', 'fista', 'acc_ista')
                              and self.npad and ops.lasso_resident_supported(self.npad)
@@ -409,7 +414,6 @@ class LassoSolver(object):
         else:
             self.W = [empty2d(B, k, cplx, dev), empty2d(B, k, cplx, dev)]
             self.W[0].copy_(X)
-        self.poll_at = POLL_EVERY
         self.wi = 0                                                # W[wi] holds the current extrapolated point
         self.mom = _momentum_schedule(rule, maxiter)
         # acc_ista returns the *previous* iterate on exhaustion (lasso.py:357,385): its last iteration only
@@ -470,17 +474,23 @@ class LassoSolver(object):
         if check and self.group is not None:
             torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
 
+    def _poll(self, last_done):
+        """Host read of the latch, on the same schedule in both loops: right after checking iteration ``last_done``
+        has been enqueued, every POLL_EVERY iterations.  (With a group every rank must leave the loop at the same
+        iteration, whatever kernel path its shard size selected: the latch is MIN-all-reduced on checking iterations,
+        so ranks that poll after the same iterations read the same value.)"""
+        if self.checks and last_done > 0 and last_done % POLL_EVERY == 0 and int(self.latch.item()) != 0:
+            self.stopped = True
+        return self.stopped
+
     def iterate(self, begin, end):
         """Enqueue iterations ``begin <= i < end`` (in place on X)."""
         end = min(end, self.n_inplace)
+        if self.stopped:
+            return
         if self.resident:
             i = begin
             while i < end:
-                if self.checks and i >= self.poll_at:
-                    if int(self.latch.item()) != 0:
-                        self.stopped = True
-                        break
-                    self.poll_at = i + POLL_EVERY
                 stop = min(end, i + ops.RESIDENT_MAX_ITERS)
                 if self.checks:
                     stop = min(stop, (i + 9) // 10 * 10 + 1)       # a launch ends on the next checking iteration
@@ -492,12 +502,13 @@ class LassoSolver(object):
                 else:
                     self._launch_resident(i, stop)
                 i = stop
+                if self._poll(stop - 1):
+                    break
             return
         for i in range(begin, end):
-            if self.checks and i > 0 and i % POLL_EVERY == 0 and int(self.latch.item()) != 0:
-                self.stopped = True
-                break
             self._launch(i, rview(self.X))
+            if self._poll(i):
+                break
 
     def finish(self, out=None):
         """x / s (lasso.py:189) into ``out``; returns a ``LassoState``."""

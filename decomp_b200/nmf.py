@@ -156,6 +156,7 @@ class MuSolver(object):
         self.NEG = empty2d(n, k, False, dev)
         self.ws = ops.gemm_tn_workspace_for([(k, f, n), (k, k, n)], dev)
         self.checks = tol > 0.0
+        self.comm_events = None   # set to [] to collect (start, end) CUDA event pairs around each sweep's all-reduces
         self.latch = torch.zeros(1, dtype=torch.int32, device=dev) if self.checks else None
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.maxdiff = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -177,6 +178,16 @@ class MuSolver(object):
     def fired(self):
         return int(self.latch.item()) if self.latch is not None else 0
 
+    def _comm_mark(self, start=None):
+        """Timing hook of bench.py: CUDA events around the all-reduces of a sweep (only when comm_events is a list)."""
+        if self.comm_events is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if start is not None:
+            self.comm_events.append([(start, ev)])
+        return ev
+
     def sweep(self, it):
         E = ops.epilogue
         y, ym, X, mask, latch, ws, group = self.y, self.ym, self.X, self.mask, self.latch, self.ws, self.group
@@ -192,8 +203,10 @@ class MuSolver(object):
             ops.gemm_tn(X, y, POS, workspace=ws, skip=latch)
             ops.gemm_tn(X, X, S, workspace=ws, skip=latch)
             if group is not None:
+                t0 = self._comm_mark()
                 _allreduce2d(POS, group)
                 _allreduce2d(S, group)
+                self._comm_mark(t0)
             ops.make_rhs(D, False, False, out=Dt, skip=latch)
             ops.gemm_nt(S, Dt, E(ops.EPI_MU_DEN, Draw, x=D, other=POS), skip=latch)
         else:
@@ -228,9 +241,11 @@ class MuSolver(object):
                 else:
                     ops.gemm_tn(X, mask, NEGD, workspace=ws, skip=latch)
             if group is not None:
+                t0 = self._comm_mark()
                 _allreduce2d(POS, group)
                 if not (self.kl and mask is None):
                     _allreduce2d(NEGD, group)
+                self._comm_mark(t0)
             ops.mu_update(D, POS, NEGD, Draw, skip=latch)
         # ---- l2_strict + max|D - D_new| < tol (batch_mu.py:21-23)
         ops.normalize_rows(Draw, Dn, False, True, D_ref=D if self.checks else None, tol=self.tol, latch=latch,
@@ -242,11 +257,14 @@ class _PinnedRows(object):
     """Host rows page-locked in place (cudaHostRegister) for asynchronous block copies; released on close()."""
 
     def __init__(self, a):
-        a = np.ascontiguousarray(a, dtype=np.float64)
+        # float32 rows are staged as they are and widened by the device-side copy: no float64 host copy of the data
+        a = np.ascontiguousarray(a)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
         self.t = torch.from_numpy(a)
         self.registered = False
         if not self.t.is_pinned():
-            rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), self.t.numel() * 8, 0)
+            rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), self.t.numel() * self.t.element_size(), 0)
             self.registered = int(rc) == 0
         self.cols = a.shape[1]
 
@@ -275,6 +293,9 @@ def mu_streamed(y, D0, X, tol, maxiter, mask, block_rows):
     freed = [torch.cuda.Event() for _ in range(NB)]      # compute has finished with ybuf[i]
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
+    # the staging buffers come from the caching allocator of the main stream: earlier users of those blocks that are
+    # still queued there must have finished before the copy stream writes into them
+    copy_stream.wait_stream(main)
     E = ops.epilogue
 
     Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]

@@ -138,11 +138,19 @@ def mask_mul(A, mask, out, cwidth=1):
     return out
 
 
-def col_sums(A, scale_=1.0, out=None):
+def workspace(nbytes, device):
+    """Caller-owned scratch for the entry points that take (workspace, workspace_bytes)."""
+    return torch.empty(max((int(nbytes) + 7) // 8, 1), dtype=torch.float64, device=device)
+
+
+def col_sums(A, scale_=1.0, out=None, ws=None):
     rows, cols = A.shape
     if out is None:
         out = torch.empty(cols, dtype=torch.float64, device=A.device)
-    rc = _lib.lib().decomp_col_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _lib.stream_ptr())
+    if ws is None:
+        ws = workspace(_lib.lib().decomp_col_sums_workspace_bytes(rows, cols), A.device)
+    rc = _lib.lib().decomp_col_sums_f64(_p(A), ld(A), rows, cols, float(scale_), _p(out), _p(ws), ws.numel() * 8,
+                                        _lib.stream_ptr())
     _lib.check(rc, 'decomp_col_sums_f64')
     _count(2)
     return out
@@ -196,11 +204,17 @@ def gather_rows(src, index, out):
     return out
 
 
-def dl_sweep(S, T, D, is_complex):
+def dl_sweep_workspace(k, f, is_complex, device):
+    return workspace(_lib.lib().decomp_dl_sweep_workspace_bytes(k, f, int(is_complex)), device)
+
+
+def dl_sweep(S, T, D, is_complex, ws=None):
     cw = 2 if is_complex else 1
     k, f = D.shape[0], D.shape[1] // cw
-    rc = _lib.lib().decomp_dl_sweep_f64(_p(S), ld(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex),
-                                        _lib.stream_ptr())
+    if ws is None:
+        ws = dl_sweep_workspace(k, f, is_complex, D.device)
+    rc = _lib.lib().decomp_dl_sweep_f64(_p(S), ld(S), _p(T), ld(T), _p(D), ld(D), k, f, int(is_complex), _p(ws),
+                                        ws.numel() * 8, _lib.stream_ptr())
     _lib.check(rc, 'decomp_dl_sweep_f64')
     _count(1)
     return D

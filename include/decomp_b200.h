@@ -33,7 +33,7 @@ extern "C" {
 #define DECOMP_ERR_CUDA (-2)
 #define DECOMP_ERR_UNSUPPORTED (-3)
 
-#define DECOMP_ABI_VERSION 1
+#define DECOMP_ABI_VERSION 2
 
 /* ---- epilogue fused into the NT GEMM ------------------------------------------------ */
 enum decomp_epilogue_kind {
@@ -134,8 +134,9 @@ int decomp_mask_mul_f64(const double* A, int64_t lda, const double* mask, int64_
                         int32_t cwidth, double* out, int64_t ldo, void* stream);
 /* out[j] = sum_i A[i][j] * scale   (column sums: mean over the batch of the mask, lasso.py:300-303;
  * with rows<->cols swapped by the caller it is also the per-row mask count of lasso.py:163) */
+size_t decomp_col_sums_workspace_bytes(int64_t rows, int64_t cols);
 int decomp_col_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
-                        void* stream);
+                        void* workspace, size_t workspace_bytes, void* stream);
 int decomp_row_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, double scale, double* out,
                         void* stream);
 /* Lipschitz bound: *step_out = 1 / max_j sum_i |G[i][j]| for a [k,k] (complex: interleaved) matrix
@@ -212,9 +213,12 @@ int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N
 /* ---- dictionary-learning basis update ------------------------------------------------- */
 /* Gauss-Seidel atom sweep, dictionary_learning.py:154-159:
  *   for a in 0..k-1: u = (T[a] - S[a].D) / (S[a][a] + eps) + D[a];  D[a] = u / sqrt(max(|u|^2, 1))
- * in place on D (initialised by the caller with the old dictionary). One cooperative launch. */
+ * in place on D (initialised by the caller with the old dictionary). One cooperative launch; `workspace` (block
+ * partials of |u|^2 and the grid barrier counter) is sized by decomp_dl_sweep_workspace_bytes(). */
+size_t decomp_dl_sweep_workspace_bytes(int64_t k, int64_t f, int32_t is_complex);
 int decomp_dl_sweep_f64(const double* S, int64_t lds, const double* T, int64_t ldt, double* D, int64_t ldd,
-                        int64_t k, int64_t f, int32_t is_complex, void* stream);
+                        int64_t k, int64_t f, int32_t is_complex, void* workspace, size_t workspace_bytes,
+                        void* stream);
 /* Masked statistics, dictionary_learning.py:210-213:  S[a][j][b] = beta*S[a][j][b] + sum_i conj(x_ia) x_ib m_ij.
  * Per atom a this is the TN product  Mask^T . W_a  with  W_a[i][b] = conj(x_ia) x_ib ; this entry point forms W_a
  * (interleaved complex when is_complex) and the caller feeds it to decomp_gemm_tn_f64(combine=1, beta) with

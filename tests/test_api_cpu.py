@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     lib.decomp_abi_version.restype = ctypes.c_int
-    assert lib.decomp_abi_version() == 1
+    assert lib.decomp_abi_version() == 2
 
 
 def test_epilogue_struct_matches_header_layout(tmp_path):

@@ -136,7 +136,8 @@ def test_staged_upload_of_pageable_arrays(cplx, monkeypatch):
     monkeypatch.setattr(_device, 'STAGE_PIECE_BYTES', 4096)
     monkeypatch.setattr(_device, '_stage', {})
     rng = np.random.RandomState(2)
-    for rows, cols in [(1, 2), (37, 6), (1000, 30), (513, 128)]:
+    # (4, 5000): one row is several pieces long (short-and-wide arrays used to raise in the worker thread)
+    for rows, cols in [(1, 2), (37, 6), (1000, 30), (513, 128), (4, 5000), (1, 2050)]:
         a = rng.randn(rows, cols) + (1j * rng.randn(rows, cols) if cplx else 0.0)
         d = _device.to_device2d(a, torch.device('cuda', 0))
         torch.cuda.synchronize()

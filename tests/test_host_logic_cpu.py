@@ -41,7 +41,7 @@ def test_pageable_batches_get_uniform_short_chunks(b200):
 def _bare_solver(B, npad, checks, pad=False, n_inplace=10 ** 9, group=None):
     s = object.__new__(lasso.LassoSolver)
     s.resident, s.checks, s.pad, s.B, s.rows_total, s.npad, s.group = True, checks, pad, B, B, npad, group
-    s.n_inplace, s.poll_at, s.stopped = n_inplace, 10 ** 9, False
+    s.n_inplace, s.stopped = n_inplace, False
     s.X = torch.zeros((1, 2), dtype=torch.float64)
     s.calls = []
     s._launch_resident = lambda i0, i1: s.calls.append(('resident', i0, i1))
@@ -92,3 +92,50 @@ def test_momentum_schedules():
     b1 = 0.5 * (1 + 5 ** 0.5)
     b2 = 0.5 * (1 + (1 + 4 * b1 * b1) ** 0.5)
     assert m[0] == 0.0 and abs(m[1] - (b1 - 1) / b2) < 1e-15
+
+
+def test_latch_is_polled_after_the_same_iterations_in_both_loops():
+    """With a process group, ranks whose shard sizes select different kernel paths must leave the loop together
+    (ADVICE r1): both loops read the latch right after checking iterations 50, 100, ... and nowhere else."""
+    polled = {}
+    for resident in (True, False):
+        s = _bare_solver(1000, 32, checks=True)
+        s.resident = resident
+        reads = []
+
+        class Latch(object):
+            def item(self_inner):
+                reads.append(s.calls[-1][2] - 1)          # last iteration enqueued when the host reads the latch
+                return 0
+
+        s.latch = Latch()
+        s.iterate(0, 130)
+        polled[resident] = reads
+    assert polled[True] == polled[False] == [50, 100]
+
+    # a latch that fires stops both loops after the same iteration
+    for resident in (True, False):
+        s = _bare_solver(1000, 32, checks=True)
+        s.resident = resident
+
+        class Fired(object):
+            def item(self_inner):
+                return 41
+
+        s.latch = Fired()
+        s.iterate(0, 130)
+        assert s.stopped and s.calls[-1][2] == 51
+        s.iterate(51, 130)                                  # re-entry after a stop enqueues nothing
+        assert s.calls[-1][2] == 51
+
+
+def test_numpy_views_torch_cannot_alias_are_copied():
+    import numpy as np
+    from decomp_b200 import _device
+    a = np.arange(24.0).reshape(4, 6)
+    for view in (a[::-1], a[:, ::-1], a[::2, ::3]):
+        t = _device._from_numpy(view)
+        assert t.shape == view.shape and np.array_equal(t.numpy(), view)
+    ro = a.copy()
+    ro.flags.writeable = False
+    assert np.array_equal(_device._from_numpy(ro).numpy(), a)
