@@ -53,7 +53,7 @@ def test_nmf_full_width_two_sweeps_vs_oracle():
     from oracle import decomp_oracle as orc
     dev = torch.device('cuda', 0)
     n, f, k = 131072, 4096, 256
-    y, D0 = bench.nmf_data_device(torch, n, f, k, 1, dev)
+    y, D0, _ = bench.nmf_data_device(torch, n, f, k, 1, dev)
     it, D, x = nmf.solve(y, D0, tol=0.0, maxiter=3)
     yh, Dh = y.cpu().numpy(), D0.cpu().numpy()
     it0, D_ref, x_ref = orc.nmf_mu(yh, Dh, tol=0.0, maxiter=3)

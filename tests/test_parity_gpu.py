@@ -59,8 +59,8 @@ def test_nmf_minibatch_golden(name):
                          maxiter=case['maxiter'], method=case['method'], likelihood=case['likelihood'],
                          mask=case['mask'], random_seed=case['random_seed'])
     assert it == int(g['it'])
-    assert_close(D, g['D'], rtol=1.0e-9, what='D')
-    assert_close(x, g['x'], rtol=1.0e-9, what='x')
+    assert_close(D, g['D'], what='D')
+    assert_close(x, g['x'], what='x')
 
 
 # ----------------------------------------------------------------------------------- golden: Lasso
@@ -92,8 +92,8 @@ def test_dictionary_learning_golden(name):
     kw = {k: v for k, v in case.items() if k not in ('y', 'D', 'alpha')}
     it, D, x = dictionary_learning.solve(case['y'], case['D'].copy(), case['alpha'], **kw)
     assert it == int(g['it'])
-    assert_close(D, g['D'], rtol=1.0e-9, what='D')
-    assert_close(x, g['x'], rtol=1.0e-9, what='x')
+    assert_close(D, g['D'], what='D')
+    assert_close(x, g['x'], what='x')
 
 
 # ----------------------------------------------------------------------------------- oracle on larger inputs
@@ -152,8 +152,8 @@ def test_dictionary_learning_vs_oracle(cplx, masked):
     it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, **kw)
     it, D, x = dictionary_learning.solve(yy, D0.copy(), 0.05, **kw)
     assert it == it0
-    assert_close(D, D_ref, rtol=1.0e-9, what='D')
-    assert_close(x, x_ref, rtol=1.0e-9, what='x')
+    assert_close(D, D_ref, what='D')
+    assert_close(x, x_ref, what='x')
 
 
 # ----------------------------------------------------------------------------------- API behaviour

@@ -6,7 +6,7 @@ import torch
 import bench
 from decomp_b200 import nmf
 dev = torch.device('cuda', 0)
-y, D0 = bench.nmf_data_device(torch, 131072, 4096, 256, 0, dev)
+y, D0, _ = bench.nmf_data_device(torch, 131072, 4096, 256, 0, dev)
 X = torch.ones((131072, 256), dtype=torch.float64, device=dev)
 s = nmf.MuSolver(y, D0, X, 0.0)
 for it in range(1, 4):
