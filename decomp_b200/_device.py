@@ -5,6 +5,7 @@ even row pitch, which is what the TMA tensor maps of the GEMM need (16-byte row 
 float32 / complex64 inputs are widened on entry and narrowed on exit: the hot path computes
 in FP64 throughout.
 """
+import os
 import threading
 import warnings
 
@@ -55,9 +56,21 @@ def full2d(rows, cols, value, cplx=False, device=None):
 
 _STAGED_DTYPES = (torch.float32, torch.float64, torch.complex64, torch.complex128)
 STAGE_MIN_BYTES = 64 << 20    # pageable arrays from this size on go up through the staged path below
-STAGE_PIECE_BYTES = 32 << 20
-STAGE_SLOTS = 4
-STAGE_THREADS = 4
+STAGE_PIECE_BYTES = int(os.environ.get('DECOMP_STAGE_PIECE_MB', '8')) << 20
+
+
+def _stage_threads():
+    """memcpy threads of the staged upload: the cores this process may use, shared between the ranks of one box."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 4
+    ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+    return max(2, min(6, cores // ranks - 1))
+
+
+STAGE_THREADS = int(os.environ.get('DECOMP_STAGE_THREADS', '0')) or _stage_threads()
+STAGE_SLOTS = STAGE_THREADS + 2
 _stage = {}
 _stage_lock = threading.Lock()    # one staged upload at a time per process: the ring of pinned buffers is shared
 

@@ -7,11 +7,16 @@
 //     accumulator fragment in every iteration)
 //   * only Q = (I - G/L)^T streams, from L2, through a TMA ring
 // so HBM sees one read of (w, c, x) and one write of (x, w) per launch instead of per iteration, and there is one
-// launch per `iters` iterations.  BM * N = 8192 elements: N = 256 -> 32 rows, 1 x 8 warps of 32 x 32; N = 128 -> 64
-// rows, 2 x 4 warps; ...  Scalar FP64 instructions run on the same pipe as the DMMAs (about one DMMA slot per warp
-// instruction), so the update is kept to 3 of them per element: the accumulators start from c instead of zero
-// (no z = acc + c), |z| - t, and the two of the extrapolation.  (gemm_f64_proxq_kernel adds c after the sum, so the
-// two kernels agree to rounding, not to the bit.)
+// launch per `iters` iterations.  BM * N = 8192 elements; 16 MMA warps, each owning a 16 x 32 piece of the block
+// (N = 256 -> 32 rows, 2 x 8 warps; N = 128 -> 64 rows, 4 x 4 warps; ...): four warps per SM sub-partition take
+// turns on the FP64 tensor pipe, so the latency of one warp's fragment loads, barrier waits and update is covered
+// by the DMMAs of the other three, and a thread carries 32 accumulator + 32 x_prev registers instead of 64 + 64
+// (the 8-warp version of round 1 sat at 168 registers with spills and could not overlap its fragment loads with
+// its DMMAs: 84 % of the DMMA issue rate).  The k-loop is straight-line code per number of live 8-row groups.
+// Scalar FP64 instructions run on the same pipe as the DMMAs (about one DMMA slot per warp instruction), so the
+// update is kept to 3 of them per element: the accumulators start from c instead of zero (no z = acc + c), |z| - t,
+// and the two of the extrapolation.  (gemm_f64_proxq_kernel adds c after the sum, so the two kernels agree to
+// rounding, not to the bit.)
 #pragma once
 #include <type_traits>
 
@@ -19,7 +24,9 @@
 
 namespace dcp {
 
-constexpr int RES_THREADS = 288;   // 8 MMA warps + 1 producer warp
+constexpr int RES_MMA_WARPS = 16;
+constexpr int RES_MMA_THREADS = RES_MMA_WARPS * 32;
+constexpr int RES_THREADS = RES_MMA_THREADS + 128;   // + the producer warp group (one active thread)
 constexpr int RES_MAX_ITERS = 32;
 constexpr int RES_MAX_STAGES = 8;
 
@@ -47,7 +54,55 @@ struct ResidentArgs {
   double momentum[RES_MAX_ITERS];
 };
 
-__device__ __forceinline__ void mma_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mma_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// One iteration's GEMM for a warp with MI live 8-row groups (its 16 rows x 32 columns): KB k-blocks of
+// LDS.64 -> DMMA.8x8x4, straight-line so that the fragment loads of a k-step are scheduled under the DMMAs of the
+// one before.  MI = 0: the warp only walks the ring (its arrivals are part of every stage's hand-over).
+template <int MI>
+__device__ __forceinline__ void resident_gemm(double (&acc)[2][4][2], const unsigned char* Wt,
+                                              const unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar,
+                                              int KB, int kb_bytes, int stage_bytes, int stages,
+                                              const int (&offA)[4], const int (&offB)[4], int& s, uint32_t& ph,
+                                              int lane, int zero) {
+  int held = -1;
+#pragma unroll 1
+  for (int kb = 0; kb < KB; ++kb) {
+    mbar_wait(&full_bar[s], ph);
+    // late release of the stage read one k-block ago, see MmaPipe::run
+    if (held >= 0 && lane == 0) mbar_arrive(&empty_bar[held]);
+    if constexpr (MI > 0) {
+      const unsigned char* sa = Wt + kb * kb_bytes;
+      const unsigned char* sb = ring + s * stage_bytes;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        double fa[MI], fb[4];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) fa[i] = *reinterpret_cast<const double*>(sa + offA[s4] + i * 1024);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[j] = *reinterpret_cast<const double*>(sb + offB[s4] + j * 1024);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    }
+    held = s;
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+  // last k-block: the arrival waits for the accumulators computed from the stage
+  int dep = 0;
+  if constexpr (MI > 0) {
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dep |= __double2hiint(acc[i][j][0]);
+  }
+  if (lane == after(dep, zero)) mbar_arrive(&empty_bar[held]);
+}
 
 template <int SHRINK>
 __global__ void __launch_bounds__(RES_THREADS, 1)
@@ -63,7 +118,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint64_t* empty_bar = full_bar + RES_MAX_STAGES;
   uint64_t* wbar = empty_bar + RES_MAX_STAGES;
 
-  const int N = a.N, KB = N >> 4, WN = N >> 5, WM = 8 / WN, BM = 32 * WM;
+  const int N = a.N, KB = N >> 4, WN = N >> 5, WM = RES_MMA_WARPS / WN, BM = 16 * WM;
   const int stage_bytes = N * 128;
   const int stages = S::RING_BYTES / stage_bytes < RES_MAX_STAGES ? S::RING_BYTES / stage_bytes : RES_MAX_STAGES;
   const int kb_bytes = BM * 128;   // one k-block of the resident w tile
@@ -78,7 +133,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 8);
+      mbar_init(&empty_bar[s], RES_MMA_WARPS);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
@@ -88,9 +143,12 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   __syncthreads();
 
   bool violated = false;
-  if (warp == 8) {
+  // Registers are allocated to warps in groups of four: 640 threads leave 96 each.  The producer group hands most of
+  // its share to the four MMA groups (4 x 128 x 112 + 128 x 24 = 60416 of the 640 x 96 = 61440 the CTA was launched with).
+  if (warp >= RES_MMA_WARPS) {
     // ================================================================ producer: Q k-blocks, round and round
-    if (lane == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == RES_MMA_WARPS && lane == 0) {
       const long long total = (long long)tiles * a.iters * KB;
       int s = 0, kb = 0;
       uint32_t ph = 0;
@@ -127,24 +185,30 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     }
   } else {
     // ================================================================ MMA warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int wn = warp % WN, wm = warp / WN, g = lane >> 2, q = lane & 3, tid = threadIdx.x;
     int offA[4], offB[4];
 #pragma unroll
     for (int s4 = 0; s4 < 4; ++s4) {
       const int o = (((s4 + 4 * (q >> 1)) ^ g) << 4) | ((q & 1) << 3);
-      offA[s4] = (wm * 32 + g) * 128 + o;
+      offA[s4] = (wm * 16 + g) * 128 + o;
       offB[s4] = (wn * 32 + g) * 128 + o;
     }
     const int col_lane = wn * 32 + 2 * q;   // + 8 j
+    // w_next goes back into the swizzled tile as 16-byte stores; a quarter warp (rows g = 2a, 2a + 1) would hit every
+    // bank twice if all its lanes stored the same column pair j, so odd rows store pair j ^ 1 first (chunks
+    // (q + 4 (j & 1)) ^ g: the two rows then cover all eight 16-byte chunks of the 128-byte line)
+    const int odd = g & 1;
+    const int chunk_a = ((q + 4 * odd) ^ g) << 4, chunk_b = ((q + 4 * (1 - odd)) ^ g) << 4;
 
     int s = 0;
     uint32_t ph = 0, wph = 0;
 #pragma unroll 1
     for (int tile = 0; tile < tiles; ++tile) {
       const long long m0 = row_begin + (long long)tile * BM;
-      // 8-row groups of this warp's 32 rows that lie inside the CTA's range
-      const long long left = row_end - (m0 + wm * 32);
-      const int mi = left >= 32 ? 4 : (left <= 0 ? 0 : (int)((left + 7) >> 3));
+      // 8-row groups of this warp's 16 rows that lie inside the CTA's range
+      const long long left = row_end - (m0 + wm * 16);
+      const int mi = left >= 16 ? 2 : (left <= 0 ? 0 : (int)((left + 7) >> 3));
       if (tid == 0) {
         // the previous tile's w was read and written through the generic proxy; TMA overwrites it now
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -153,16 +217,17 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       }
       // this thread's fragment of x_prev (registers) and c (private shared-memory column): rows beyond M are clamped
       // into the matrix, computed on and never stored
-      const long long row_lane = m0 + wm * 32 + g;
-      double2 prev[4][4];
+      const long long row_lane = m0 + wm * 16 + g;
+      double2 prev[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         long long r = row_lane + 8 * i;
         if (r > a.M - 1) r = a.M - 1;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           prev[i][j] = *reinterpret_cast<const double2*>(a.x + r * a.ldx + col_lane + 8 * j);
-          Ct[(i * 4 + j) * 256 + tid] = *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
+          Ct[(i * 4 + j) * RES_MMA_THREADS + tid] =
+              *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
         }
       }
       mbar_wait(wbar, wph);
@@ -171,64 +236,30 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 #pragma unroll 1
       for (int it = 0; it < a.iters; ++it) {
         // the accumulators start from c, so the mainloop ends with z = c + w Q
-        double acc[4][4][2];
+        double acc[2][4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const double2 cc = Ct[(i * 4 + j) * 256 + tid];
+            const double2 cc = Ct[(i * 4 + j) * RES_MMA_THREADS + tid];
             acc[i][j][0] = cc.x;
             acc[i][j][1] = cc.y;
           }
-        int held = -1;
-#pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          // late release of the stage read one k-block ago, see MmaPipe::run
-          if (held >= 0 && lane == 0) mbar_arrive(&empty_bar[held]);
-          const unsigned char* sa = Wt + kb * kb_bytes;
-          const unsigned char* sb = ring + s * stage_bytes;
-#pragma unroll
-          for (int s4 = 0; s4 < 4; ++s4) {
-            double fa[4], fb[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) fa[i] = *reinterpret_cast<const double*>(sa + offA[s4] + i * 1024);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) fb[j] = *reinterpret_cast<const double*>(sb + offB[s4] + j * 1024);
-            if (mi == 4) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-                if (i < mi) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-                }
-            }
-          }
-          held = s;
-          if (++s == stages) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-        {
-          int dep = 0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dep |= __double2hiint(acc[i][j][0]);
-          if (lane == after(dep, a.zero)) mbar_arrive(&empty_bar[held]);
-        }
+        if (mi == 2)
+          resident_gemm<2>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero);
+        else if (mi == 1)
+          resident_gemm<1>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero);
+        else
+          resident_gemm<0>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero);
         mma_warps_sync();   // every warp is done reading w
 
         const bool last = it == a.iters - 1;
         const double mom = a.momentum[it];
         // Three straight-line variants (inner iteration / last / last with the convergence test): with the mode
-        // tested per element the compiler kept one basic block per column pair and the 16 dependency chains of a
+        // tested per element the compiler kept one basic block per column pair and the dependency chains of a
         // thread ran one after the other.
         auto update = [&](auto LAST, auto CHECK) {
           constexpr bool kLast = decltype(LAST)::value, kCheck = decltype(CHECK)::value;
@@ -239,8 +270,9 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
               thr0[j] = thr1[j] = __ldg(a.thr + (col >> 1));
             } else {
-              thr0[j] = __ldg(a.thr + col);
-              thr1[j] = __ldg(a.thr + col + 1);
+              const double2 t = __ldg(reinterpret_cast<const double2*>(a.thr + col));   // col is even
+              thr0[j] = t.x;
+              thr1[j] = t.y;
             }
           }
           unsigned long long tb0[4], tb1[4];
@@ -257,14 +289,14 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             }
           }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             const long long row = row_lane + 8 * i;
             const bool row_ok = row < row_end;
-            unsigned char* wrow = Wt + (wm * 32 + g + 8 * i) * 128;
+            unsigned char* wrow = Wt + (wm * 16 + g + 8 * i) * 128;
             double* grow = a.w + row * a.ldw + col_lane;
+            double2 wv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int col = col_lane + 8 * j;
               const double z0 = acc[i][j][0], z1 = acc[i][j][1];
               double x0, x1, d0, d1;
               if constexpr (SHRINK == DECOMP_SHRINK_COMPLEX) {
@@ -294,11 +326,22 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
               }
               prev[i][j] = make_double2(x0, x1);
               // w_next = x_new + momentum * (x_new - x_prev)   (lasso.py:412)
-              const double2 wv = make_double2(x0 + mom * d0, x1 + mom * d1);
-              if constexpr (!kLast) {
-                *reinterpret_cast<double2*>(wrow + (col >> 4) * kb_bytes + ((((col & 15) >> 1) ^ g) << 4)) = wv;
-              } else {
-                if (row_ok) *reinterpret_cast<double2*>(grow + 8 * j) = wv;
+              wv[j] = make_double2(x0 + mom * d0, x1 + mom * d1);
+            }
+            if constexpr (!kLast) {
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                // columns 16 m .. 16 m + 15 of this warp's 32 = k-block 2 wn + m of the tile
+                unsigned char* blk = wrow + (2 * wn + m) * kb_bytes;
+                const double2 va = odd ? wv[2 * m + 1] : wv[2 * m];
+                const double2 vb = odd ? wv[2 * m] : wv[2 * m + 1];
+                *reinterpret_cast<double2*>(blk + chunk_a) = va;
+                *reinterpret_cast<double2*>(blk + chunk_b) = vb;
+              }
+            } else {
+              if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(grow + 8 * j) = wv[j];
               }
             }
           }
@@ -312,7 +355,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         if (!last) mma_warps_sync();   // w_next is complete
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         const long long row = row_lane + 8 * i;
         if (row < row_end) {
 #pragma unroll

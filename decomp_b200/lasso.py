@@ -22,6 +22,8 @@ set and every later launch returns immediately, so the host never has to synchro
 reference's result.  Host arrays with ``tol <= 0`` are solved in row chunks whose copies overlap the iterations.
 """
 import math
+import queue
+import threading
 
 import numpy as np
 import torch
@@ -187,7 +189,11 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     (lasso.py:293/409 never fires), so the batch is solved chunk by chunk with the upload of the next chunk and the
     download of the previous one overlapping the iterations of the current one.  Row results are bitwise those of the
     one-piece solve: a row's dot products do not depend on which tile it sits in.  Only PIPELINE_DEPTH chunks of at
-    most PIPELINE_MAX_CHUNK_BYTES are on the device at a time, so the host batch may exceed the device memory."""
+    most PIPELINE_MAX_CHUNK_BYTES are on the device at a time, so the host batch may exceed the device memory.
+
+    Uploads from ordinary (pageable) memory keep the host busy (memcpy into page-locked staging buffers, see
+    _device._staged_upload), so they run in a helper thread that works ahead of the thread enqueuing the iterations;
+    page-locked inputs are copied asynchronously from the enqueuing thread itself."""
     cur = torch.cuda.current_stream(device)
     up, down = _copy_streams(device)
     up.wait_stream(cur)
@@ -200,7 +206,7 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
     # At most PIPELINE_DEPTH chunks live on the device (uploading / iterating / downloading), so the batch may be
     # larger than HBM: chunk j is uploaded once chunk j - PIPELINE_DEPTH has been downloaded and its buffers dropped.
     n = len(chunks)
-    staged, finished = {}, {}
+    finished = {}
 
     def upload(j):
         r0, r1 = chunks[j]
@@ -209,31 +215,74 @@ def _solve_pipelined(y, A, alpha, x, maxiter, rule, positive, mask, precision, c
             xc = to_device2d(x[r0:r1], device, copy=False) if x is not None else None
             ev = torch.cuda.Event()
             ev.record(up)
-        staged[j] = (yc, xc, ev)
+        return yc, xc, ev
 
-    upload(0)
-    for c, (r0, r1) in enumerate(chunks):
-        yc, xc, ev = staged.pop(c)
-        cur.wait_event(ev)
-        state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision,
-                             rows_hint=y.shape[0])      # same kernel choice as the one-piece solve
-        res = state.result.to(dtype=tdt)
-        done = torch.cuda.Event()
-        done.record(cur)
-        down.wait_event(done)
-        with torch.cuda.stream(down):
-            host[r0:r1].copy_(res, non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(down)
-        finished[c] = (copied, yc, xc, state, res)      # the buffers stay referenced until the copy has finished
-        del yc, xc, state, res
-        # the next chunk goes up while this one iterates (from pageable memory the copy blocks this thread, which
-        # is why it comes after the launches above)
-        if c + 1 < n:
-            if c + 1 - PIPELINE_DEPTH >= 0:
-                finished.pop(c + 1 - PIPELINE_DEPTH)[0].synchronize()
-            upload(c + 1)
+    def retire(j):
+        """Blocks until chunk j has been downloaded, then drops its device buffers."""
+        if j >= 0:
+            finished.pop(j)[0].synchronize()
+
+    threaded = not _is_pinned(y)
+    if threaded:
+        ready, issued = queue.Queue(), [threading.Event() for _ in chunks]
+        abort = threading.Event()
+
+        def uploader():
+            try:
+                torch.cuda.set_device(device)
+                for j in range(n):
+                    if j - PIPELINE_DEPTH >= 0:
+                        while not issued[j - PIPELINE_DEPTH].wait(0.05):
+                            if abort.is_set():
+                                return
+                        retire(j - PIPELINE_DEPTH)
+                    if abort.is_set():
+                        return
+                    ready.put(upload(j))
+            except BaseException as exc:           # surfaces in the enqueuing thread
+                ready.put(exc)
+
+        worker = threading.Thread(target=uploader, name='decomp-upload', daemon=True)
+        worker.start()
+    else:
+        staged = {0: upload(0)}
+
+    try:
+        for c, (r0, r1) in enumerate(chunks):
+            if threaded:
+                item = ready.get()
+                if isinstance(item, BaseException):
+                    raise item
+                yc, xc, ev = item
+            else:
+                yc, xc, ev = staged.pop(c)
+            cur.wait_event(ev)
+            state = lasso_device(yc, A2, alpha, xc, 0.0, maxiter, rule, positive, m1, precision=precision,
+                                 rows_hint=y.shape[0])      # same kernel choice as the one-piece solve
+            res = state.result.to(dtype=tdt)
+            done = torch.cuda.Event()
+            done.record(cur)
+            down.wait_event(done)
+            with torch.cuda.stream(down):
+                host[r0:r1].copy_(res, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(down)
+            finished[c] = (copied, yc, xc, state, res)      # the buffers stay referenced until the copy has finished
+            del yc, xc, state, res
+            if threaded:
+                issued[c].set()
+            elif c + 1 < n:
+                # the next chunk goes up while this one iterates
+                retire(c + 1 - PIPELINE_DEPTH)
+                staged[c + 1] = upload(c + 1)
+    except BaseException:
+        if threaded:
+            abort.set()
+        raise
+    if threaded:
+        worker.join()
     down.synchronize()
+    finished.clear()
     return maxiter - 1, host.numpy()
 
 
