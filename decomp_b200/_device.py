@@ -5,6 +5,7 @@ even row pitch, which is what the TMA tensor maps of the GEMM need (16-byte row 
 float32 / complex64 inputs are widened on entry and narrowed on exit: the hot path computes
 in FP64 throughout.
 """
+import ctypes
 import os
 import threading
 import warnings
@@ -80,55 +81,70 @@ def _staged_upload(src, out):
 
     torch's own copy from pageable memory stages through one buffer on the calling thread (11 GB/s measured on the
     B200 boxes); several memcpy threads feeding asynchronous copies get closer to what the link carries.  ``src`` is a
-    C-contiguous numpy array, ``out`` a contiguous device tensor with the same number of elements (float32 /
-    complex64 sources are widened on the device, piece by piece).  The array is cut into pieces of STAGE_PIECE_BYTES
-    over its flat element range, whatever its row length.
+    C-contiguous numpy array, ``out`` a contiguous device tensor with the same number of elements.  float64 /
+    complex128 sources go through ``decomp_staged_upload`` (native threads, no GIL); float32 / complex64 sources are
+    staged by Python threads and widened on the device, piece by piece.
     Enqueues on the current stream and returns when the last piece has been handed to the copy engine."""
-    from concurrent.futures import ThreadPoolExecutor
     with _stage_lock:
-        if 'pool' not in _stage:
-            _stage['pool'] = ThreadPoolExecutor(max_workers=STAGE_THREADS)
-            _stage['bufs'] = [torch.empty(STAGE_PIECE_BYTES, dtype=torch.uint8, pin_memory=True)
-                              for _ in range(STAGE_SLOTS)]
-        pool, bufs = _stage['pool'], _stage['bufs']
-        src_dtype = getattr(torch, src.dtype.name)
-        flat = src.reshape(-1)
-        out_flat = out.view(-1)
-        total = flat.shape[0]
-        step = max(1, STAGE_PIECE_BYTES // src.itemsize)
-        pieces = [(e0, min(total, e0 + step)) for e0 in range(0, total, step)]
-        stream = torch.cuda.current_stream(out.device)
-        events, futures = [None] * STAGE_SLOTS, {}
+        if 'ring' not in _stage:
+            _stage['ring'] = torch.empty(STAGE_PIECE_BYTES * STAGE_SLOTS, dtype=torch.uint8, pin_memory=True)
+        ring = _stage['ring']
+        if src.dtype in (np.float64, np.complex128):
+            from . import _lib
+            rc = _lib.lib().decomp_staged_upload(
+                ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(src.ctypes.data), src.nbytes,
+                ctypes.c_void_p(ring.data_ptr()), STAGE_PIECE_BYTES, STAGE_SLOTS, STAGE_THREADS,
+                ctypes.c_void_p(torch.cuda.current_stream(out.device).cuda_stream))
+            _lib.check(rc, 'decomp_staged_upload')
+            return
+        _staged_upload_widening(src, out, ring)
 
-        def fill(q):
-            e0, e1 = pieces[q]
-            np.copyto(bufs[q % STAGE_SLOTS].numpy()[:(e1 - e0) * src.itemsize].view(src.dtype), flat[e0:e1])
 
-        submitted = 0
-        try:
-            for p, (e0, e1) in enumerate(pieces):
-                while submitted < len(pieces) and submitted < p + STAGE_SLOTS:
-                    slot = submitted % STAGE_SLOTS
-                    if events[slot] is not None and submitted >= STAGE_SLOTS:
-                        events[slot].synchronize()        # the copy out of this slot (piece submitted - SLOTS) is done
-                    futures[submitted] = pool.submit(fill, submitted)
-                    submitted += 1
-                futures.pop(p).result()
-                slot = p % STAGE_SLOTS
-                piece = bufs[slot][:(e1 - e0) * src.itemsize].view(src_dtype)
-                out_flat[e0:e1].copy_(piece, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(stream)
-                events[slot] = ev
-        finally:
-            for fut in futures.values():                  # after an error: nobody may still be writing into the ring
-                try:
-                    fut.result()
-                except Exception:
-                    pass
-            for ev in events:
-                if ev is not None:
-                    ev.synchronize()                      # the staging buffers are reused by the next call
+def _staged_upload_widening(src, out, ring):
+    """float32 / complex64 pieces are staged by Python threads and converted by the device-side copy."""
+    from concurrent.futures import ThreadPoolExecutor
+    if 'pool' not in _stage:
+        _stage['pool'] = ThreadPoolExecutor(max_workers=STAGE_THREADS)
+    pool = _stage['pool']
+    bufs = [ring[i * STAGE_PIECE_BYTES:(i + 1) * STAGE_PIECE_BYTES] for i in range(STAGE_SLOTS)]
+    src_dtype = getattr(torch, src.dtype.name)
+    flat = src.reshape(-1)
+    out_flat = out.view(-1)
+    total = flat.shape[0]
+    step = max(1, STAGE_PIECE_BYTES // src.itemsize)
+    pieces = [(e0, min(total, e0 + step)) for e0 in range(0, total, step)]
+    stream = torch.cuda.current_stream(out.device)
+    events, futures = [None] * STAGE_SLOTS, {}
+
+    def fill(q):
+        e0, e1 = pieces[q]
+        np.copyto(bufs[q % STAGE_SLOTS].numpy()[:(e1 - e0) * src.itemsize].view(src.dtype), flat[e0:e1])
+
+    submitted = 0
+    try:
+        for p, (e0, e1) in enumerate(pieces):
+            while submitted < len(pieces) and submitted < p + STAGE_SLOTS:
+                slot = submitted % STAGE_SLOTS
+                if events[slot] is not None and submitted >= STAGE_SLOTS:
+                    events[slot].synchronize()        # the copy out of this slot (piece submitted - SLOTS) is done
+                futures[submitted] = pool.submit(fill, submitted)
+                submitted += 1
+            futures.pop(p).result()
+            slot = p % STAGE_SLOTS
+            piece = bufs[slot][:(e1 - e0) * src.itemsize].view(src_dtype)
+            out_flat[e0:e1].copy_(piece, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            events[slot] = ev
+    finally:
+        for fut in futures.values():                  # after an error: nobody may still be writing into the ring
+            try:
+                fut.result()
+            except Exception:
+                pass
+        for ev in events:
+            if ev is not None:
+                ev.synchronize()                      # the staging buffers are reused by the next call
 
 
 def _from_numpy(a):

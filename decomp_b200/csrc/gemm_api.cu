@@ -313,7 +313,7 @@ int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N
     set_error("decomp_lasso_resident_f64: x and c must be 16-byte aligned with even leading dimensions");
     return DECOMP_ERR_INVALID;
   }
-  const int bm = (int)(8192 / N);
+  const int bm = (int)(4096 / N);   // rows of one warp group's half of the row block (one TMA box)
   CUtensorMap tw, tq;
   int rc = make_tensor_map(&tw, epi->x, (uint64_t)N, (uint64_t)M, (uint64_t)epi->ldx, BK, (uint32_t)bm);
   if (rc != DECOMP_OK) return rc;

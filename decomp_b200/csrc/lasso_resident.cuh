@@ -13,6 +13,12 @@
 // by the DMMAs of the other three, and a thread carries 32 accumulator + 32 x_prev registers instead of 64 + 64
 // (the 8-warp version of round 1 sat at 168 registers with spills and could not overlap its fragment loads with
 // its DMMAs: 84 % of the DMMA issue rate).  The k-loop is straight-line code per number of live 8-row groups.
+// The 16 warps form two groups of 8 that own the two halves of the row block and share nothing but the Q ring
+// (rows are independent): each group has its own w tile, TMA barrier and named barrier, and group 1 starts every
+// iteration two k-blocks behind group 0 (the lead the 3-stage ring allows).  When group 0 reaches its update --
+// scalar FP64 work plus two barriers during which its warps issue no DMMA -- group 1 still has two k-blocks to go and
+// has the tensor pipe to itself, and vice versa at the start of the next iteration: the update of one half runs
+// under the DMMAs of the other instead of idling the pipe (it was 7 % of the iteration with all warps in lockstep).
 // Scalar FP64 instructions run on the same pipe as the DMMAs (about one DMMA slot per warp instruction), so the
 // update is kept to 3 of them per element: the accumulators start from c instead of zero (no z = acc + c), |z| - t,
 // and the two of the extrapolation.  (gemm_f64_proxq_kernel adds c after the sum, so the two kernels agree to
@@ -34,7 +40,7 @@ struct ResidentSmem {
   static constexpr int W_BYTES = 65536, C_BYTES = 65536, RING_BYTES = 98304;
   static constexpr int RING_OFF = W_BYTES + C_BYTES;
   static constexpr int BAR_OFF = RING_OFF + RING_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + (2 * RES_MAX_STAGES + 1) * 8;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * RES_MAX_STAGES + 3) * 8;   // + wbar[2] + the skew counter
 };
 
 struct ResidentArgs {
@@ -54,7 +60,13 @@ struct ResidentArgs {
   double momentum[RES_MAX_ITERS];
 };
 
-__device__ __forceinline__ void mma_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// barrier of one group of 8 MMA warps (named barriers 1 and 2)
+__device__ __forceinline__ void group_sync(int group) {
+  if (group == 0)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  else
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+}
 
 // One iteration's GEMM for a warp with MI live 8-row groups (its 16 rows x 32 columns): KB k-blocks of
 // LDS.64 -> DMMA.8x8x4, straight-line so that the fragment loads of a k-step are scheduled under the DMMAs of the
@@ -64,10 +76,13 @@ __device__ __forceinline__ void resident_gemm(double (&acc)[2][4][2], const unsi
                                               const unsigned char* ring, uint64_t* full_bar, uint64_t* empty_bar,
                                               int KB, int kb_bytes, int stage_bytes, int stages,
                                               const int (&offA)[4], const int (&offB)[4], int& s, uint32_t& ph,
-                                              int lane, int zero) {
+                                              int lane, int zero, volatile int* signal, int signal_kb,
+                                              int signal_value) {
   int held = -1;
 #pragma unroll 1
   for (int kb = 0; kb < KB; ++kb) {
+    // group 0 tells group 1 that it is `signal_kb` k-blocks into this iteration (one warp speaks for the group)
+    if (signal != nullptr && kb == signal_kb && lane == 0) *signal = signal_value;
     mbar_wait(&full_bar[s], ph);
     // late release of the stage read one k-block ago, see MmaPipe::run
     if (held >= 0 && lane == 0) mbar_arrive(&empty_bar[held]);
@@ -118,10 +133,15 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint64_t* empty_bar = full_bar + RES_MAX_STAGES;
   uint64_t* wbar = empty_bar + RES_MAX_STAGES;
 
-  const int N = a.N, KB = N >> 4, WN = N >> 5, WM = RES_MMA_WARPS / WN, BM = 16 * WM;
+  volatile int* skew = reinterpret_cast<volatile int*>(wbar + 2);
+
+  // two groups of 8 warps, each owning BMG rows of the block of BM = 2 BMG rows
+  const int N = a.N, KB = N >> 4, WN = N >> 5, WMG = 8 / WN, BMG = 16 * WMG, BM = 2 * BMG;
   const int stage_bytes = N * 128;
   const int stages = S::RING_BYTES / stage_bytes < RES_MAX_STAGES ? S::RING_BYTES / stage_bytes : RES_MAX_STAGES;
-  const int kb_bytes = BM * 128;   // one k-block of the resident w tile
+  const int kb_bytes = BMG * 128;   // one k-block of a group's resident w tile
+  // group 1 starts an iteration when group 0 is this many k-blocks into it (the ring lets group 0 lead by stages - 1)
+  const int skew_kb = KB - 1 < 2 ? KB - 1 : (stages - 1 < 2 ? stages - 1 : 2);
   // every CTA owns one contiguous range of rows (a multiple of the DMMA row granularity 8) and walks it in blocks of
   // BM rows; the ragged last block only computes the 8-row groups it has, so the grid is loaded evenly to 8 rows
   const long long per_cta = (((a.M + gridDim.x - 1) / gridDim.x) + 7) & ~7LL;
@@ -135,7 +155,9 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], RES_MMA_WARPS);
     }
-    mbar_init(wbar, 1);
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
+    *skew = 0;
     fence_barrier_init();
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmQ);
@@ -164,7 +186,10 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           ++tile;
           if (tile < tiles) {
             const long long m1 = row_begin + (long long)tile * BM;
-            for (int kb2 = 0; kb2 < KB; ++kb2) tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1);
+            for (int kb2 = 0; kb2 < KB; ++kb2) {
+              tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1);
+              tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1 + BMG);   // one box per warp group
+            }
             const long long rows = row_end - m1 < BM ? row_end - m1 : BM;
             for (long long r = 0; r < rows; ++r) {
               bulk_prefetch_l2(a.c + (m1 + r) * a.ldc, (uint32_t)N * 8u);
@@ -186,7 +211,10 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   } else {
     // ================================================================ MMA warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    const int wn = warp % WN, wm = warp / WN, g = lane >> 2, q = lane & 3, tid = threadIdx.x;
+    const int group = warp >> 3, lw = warp & 7;
+    const int wn = lw % WN, wm = lw / WN, g = lane >> 2, q = lane & 3, tid = threadIdx.x;
+    unsigned char* Wg = Wt + group * (S::W_BYTES / 2);
+    int iter_no = 0;   // iterations this CTA has started, over all its row blocks
     int offA[4], offB[4];
 #pragma unroll
     for (int s4 = 0; s4 < 4; ++s4) {
@@ -205,15 +233,16 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     uint32_t ph = 0, wph = 0;
 #pragma unroll 1
     for (int tile = 0; tile < tiles; ++tile) {
-      const long long m0 = row_begin + (long long)tile * BM;
+      const long long m0 = row_begin + (long long)tile * BM + group * BMG;   // first row of this group's half
       // 8-row groups of this warp's 16 rows that lie inside the CTA's range
       const long long left = row_end - (m0 + wm * 16);
       const int mi = left >= 16 ? 2 : (left <= 0 ? 0 : (int)((left + 7) >> 3));
-      if (tid == 0) {
-        // the previous tile's w was read and written through the generic proxy; TMA overwrites it now
+      if (lw == 0 && lane == 0) {
+        // the group's previous w tile was read and written through the generic proxy (every warp of the group is
+        // past its last read: barrier of the last iteration); TMA overwrites it now
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive_expect_tx(wbar, S::W_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(Wt + kb * kb_bytes, &tmW, wbar, kb * BK, (int)m0);
+        mbar_arrive_expect_tx(&wbar[group], S::W_BYTES / 2);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(Wg + kb * kb_bytes, &tmW, &wbar[group], kb * BK, (int)m0);
       }
       // this thread's fragment of x_prev (registers) and c (private shared-memory column): rows beyond M are clamped
       // into the matrix, computed on and never stored
@@ -230,7 +259,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
               *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
         }
       }
-      mbar_wait(wbar, wph);
+      mbar_wait(&wbar[group], wph);
       wph ^= 1u;
 
 #pragma unroll 1
@@ -245,16 +274,23 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             acc[i][j][0] = cc.x;
             acc[i][j][1] = cc.y;
           }
+        ++iter_no;
+        volatile int* signal = nullptr;
+        if (group == 0) {
+          if (lw == 0) signal = skew;
+        } else {
+          while (*skew < iter_no) __nanosleep(32);   // stay skew_kb k-blocks behind group 0
+        }
         if (mi == 2)
-          resident_gemm<2>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
-                           a.zero);
+          resident_gemm<2>(acc, Wg, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero, signal, skew_kb, iter_no);
         else if (mi == 1)
-          resident_gemm<1>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
-                           a.zero);
+          resident_gemm<1>(acc, Wg, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero, signal, skew_kb, iter_no);
         else
-          resident_gemm<0>(acc, Wt, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
-                           a.zero);
-        mma_warps_sync();   // every warp is done reading w
+          resident_gemm<0>(acc, Wg, ring, full_bar, empty_bar, KB, kb_bytes, stage_bytes, stages, offA, offB, s, ph, lane,
+                           a.zero, signal, skew_kb, iter_no);
+        group_sync(group);   // every warp of the group is done reading its w tile
 
         const bool last = it == a.iters - 1;
         const double mom = a.momentum[it];
@@ -292,7 +328,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           for (int i = 0; i < 2; ++i) {
             const long long row = row_lane + 8 * i;
             const bool row_ok = row < row_end;
-            unsigned char* wrow = Wt + (wm * 16 + g + 8 * i) * 128;
+            unsigned char* wrow = Wg + (wm * 16 + g + 8 * i) * 128;
             double* grow = a.w + row * a.ldw + col_lane;
             double2 wv[4];
 #pragma unroll
@@ -352,7 +388,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           update(std::true_type{}, std::false_type{});
         else
           update(std::true_type{}, std::true_type{});
-        if (!last) mma_warps_sync();   // w_next is complete
+        if (!last) group_sync(group);   // the group's w_next is complete
       }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {

@@ -134,9 +134,9 @@ def _row_chunks(B, f, k_cols, device, pinned=True):
     splitting costs no tile quantisation; a short first chunk lets the iterations start early and a short last one
     keeps the final device-to-host copy small (the ragged rest of the batch rides in a long middle chunk).
 
-    Uploads from pageable host memory run at a fifth of the PCIe rate and block the calling thread, which makes them
-    about as long as the iterations they are supposed to hide behind: such a batch is cut into uniform short chunks,
-    so that the host uploads chunk c+1 while the device iterates on chunk c."""
+    Uploads from pageable host memory keep host threads busy (memcpy into page-locked staging buffers) and take about
+    as long as the iterations they are supposed to hide behind: such a batch is cut into a short first chunk and
+    uniform chunks of four rounds, uploaded by a helper thread while the calling thread enqueues the iterations."""
     if B * f * 8 < PIPELINE_MIN_BYTES:
         return None
     sms = torch.cuda.get_device_properties(device).multi_processor_count
@@ -146,8 +146,13 @@ def _row_chunks(B, f, k_cols, device, pinned=True):
     if units < 4:
         return None
     if not pinned:
-        step = 2 * unit
-        out = [(r0, min(B, r0 + step)) for r0 in range(0, B, step)]
+        # a short first chunk (its upload is the only one nothing hides), then chunks of four rounds: the uploads run in
+        # a helper thread, so the chunk count only costs enqueuing work
+        out, r0, step = [], 0, 2 * unit
+        while r0 < B:
+            out.append((r0, min(B, r0 + step)))
+            r0 += step
+            step = 4 * unit
         if len(out) > 1 and out[-1][1] - out[-1][0] < unit:      # a short tail joins its neighbour
             out[-2:] = [(out[-2][0], B)]
         return out

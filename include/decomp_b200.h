@@ -244,6 +244,15 @@ int decomp_dl_masked_update_f64(const double* S, const double* T, int64_t ldt, c
                                 int64_t k, int64_t f, int32_t is_complex, double* D_out, int64_t ldo,
                                 double* workspace, void* stream);
 
+/* ---- host-side staging of pageable inputs -------------------------------------------------- */
+/* dst_device[0:bytes] = src_host[0:bytes] for an ordinary (pageable) host array, the kind of array the reference's
+ * solve() functions receive (decomp/lasso.py:19, decomp/nmf.py:16, decomp/dictionary_learning.py:12): `threads` host
+ * threads memcpy pieces of `slot_bytes` into the caller's page-locked ring (`slots` x `slot_bytes` bytes) while the
+ * calling thread enqueues cudaMemcpyAsync of the filled slots on `stream`.  Returns when the last piece has left the
+ * ring (the device copy itself is complete in stream order).  Touches no Python state. */
+int decomp_staged_upload(void* dst_device, const void* src_host, size_t bytes, void* pinned_ring, size_t slot_bytes,
+                         int32_t slots, int32_t threads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
