@@ -452,7 +452,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- NMF-MU (secondary): weak and strong scaling
-    def nmf_leg(n_rows, label, masked=False, shape=NMF):
+    def nmf_leg(n_rows, label, masked=False, shape=NMF, tf32=False):
         f, k = shape['f'], shape['k']
         Kn, Wn, Rn = max(2, args.nmf_steps), 2, 3
         y, D0, mask = nmf_data_device(torch, n_rows, f, k, rank, device, masked=masked)
@@ -498,12 +498,41 @@ def run_ours(args):
                          'hbm': {'algorithmic_bytes_per_sweep': bytes_sweep,
                                  'achieved_gbs': bytes_sweep / t_sweep / 1e9, 'peak_gbs': hbm_peak}},
         }
+        if tf32:
+            # the same sweeps with the three big contractions on the tcgen05 tensor cores (TF32 split, FP32 accumulate)
+            D64 = D.clone()
+            del solver
+            torch.cuda.empty_cache()
+            X.fill_(1.0)
+            solver = nmf.MuSolver(y, D0, X, 0.0, group=group, precision='tf32x3')
+            for it in range(1, Wn + 1):
+                solver.sweep(it)
+            ms32_list, launches32, c3 = timed_regions(
+                lambda r: [solver.sweep(it) for it in range(Wn + 1 + r * Kn, Wn + 1 + (r + 1) * Kn)], Rn)
+            c2 = merge_clocks(c2, c3)
+            t32 = median(ms32_list) * 1e-3 / Kn
+            D32 = solver.Dbuf[(Wn + Rn * Kn) % 2]
+            err = float(((D32 - D64).abs().max() / D64.abs().max()).item())
+            by32 = 2.0 * n_rows * f * 8 + 4.0 * n_rows * k * 8     # y and y^T as TF32 pairs (8 B per element each), x
+            fl32 = 3.0 * (4.0 * n_rows * k * f + 4.0 * n_rows * k * k)
+            res['tf32x3'] = {
+                'value': n_total / t32, 'unit': 'row-iters/s', 'iters_per_s': 1.0 / t32, 'ms_per_step': t32 * 1e3,
+                'launches': launches32, 'dtype': 'tf32x3 GEMMs (tcgen05, FP32 accumulate in TMEM, FP64 slab sums) + f64 updates',
+                'max_rel_diff_D_vs_fp64': err, 'sweeps_compared': Wn + Rn * Kn,
+                'speedup_vs_fp64': t_sweep / t32,
+                'roofline': {'bound': 'hbm', 'achieved': by32 / t32 / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                             'frac': by32 / t32 / 1e9 / hbm_peak, 'traffic': traffic.get('nmf_tf32x3_sweep_dram_bytes'),
+                             'algorithmic_bytes_per_sweep': by32,
+                             'note': 'y is read once row-major (y D^T) and once transposed (x^T y), both as TF32 pairs; '
+                                     'tensor side: %.3g TF32 flop per sweep = %.1f TFLOP/s' % (fl32, fl32 / t32 / 1e12),
+                             'kernel': 'tf32x3_gemm_kernel<XUPD> (y D^T + ratio) and tf32x3_gemm_kernel<PARTIAL> (x^T y)'}}
+            del D64, D32
         del solver, y, X, D0, D, mask
         torch.cuda.empty_cache()
         return res, c2
 
     if 'nmf' in legs:
-        res, c2 = nmf_leg(args.rows, 'weak')
+        res, c2 = nmf_leg(args.rows, 'weak', tf32='tf32' in legs)
         res['config'] = {'workload': 'NMF-MU l2, %d rows per GPU x %d features, k=%d, float64, tol=0 '
                                      '(BASELINE.json configs[2] shape, weak scaling)' % (args.rows, NMF['f'], NMF['k'])}
         res['scaling'] = 'weak'
@@ -516,7 +545,7 @@ def run_ours(args):
             res = dict(out['nmf'])
             res['same_run_as_secondary'] = True
         else:
-            res, c2 = nmf_leg(hi - lo, 'strong')
+            res, c2 = nmf_leg(hi - lo, 'strong', tf32='tf32' in legs)
             clocks = merge_clocks(clocks, c2)
         res['config'] = {'workload': 'NMF-MU l2, %d rows IN TOTAL x %d features, k=%d, float64, tol=0, sample axis '
                                      'sharded over %d GPU(s) with all-reduce of X^T Y [k,f] and X^T X [k,k] per sweep '

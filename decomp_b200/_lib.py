@@ -77,6 +77,13 @@ def _declare(lib):
     lib.decomp_split_tf32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_dp]
     lib.decomp_gemm_nt_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp,
                                           c_dp]
+    lib.decomp_gemm_nt_tf32x3_splitk_workspace_bytes.argtypes = [c_i64, c_i64, c_i64, c_i64]
+    lib.decomp_gemm_nt_tf32x3_splitk_workspace_bytes.restype = ctypes.c_size_t
+    lib.decomp_gemm_nt_tf32x3_splitk_f64.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_i64, c_dp,
+                                                     c_i64, c_dp, ctypes.c_size_t, c_dp, c_dp]
+    lib.decomp_nmf_xupdate_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp,
+                                              c_i64, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_dp, c_dp]
+    lib.decomp_split_transpose_tf32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_dp]
     lib.decomp_proxq_apply_f64.argtypes = [c_dp, c_i64, ctypes.POINTER(Epilogue), c_dp, c_dp, c_i64, c_i64, c_i64, c_dp,
                                            c_dp]
     lib.decomp_lasso_resident_supported.argtypes = [c_i64]
@@ -109,6 +116,8 @@ EXPORTS = (
     'decomp_gather_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_axpby_f64', 'decomp_svrmu_update_f64', 'decomp_lasso_q_f64', 'decomp_scale_scalar_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',
     'decomp_dl_sweep_workspace_bytes', 'decomp_dl_sweep_f64', 'decomp_dl_atom_weighted_f64', 'decomp_dl_pair_products_t_f64', 'decomp_dl_scatter_stats_f64', 'decomp_dl_mirror_f64', 'decomp_dl_masked_update_f64',
     'decomp_split_tf32_f64', 'decomp_gemm_nt_tf32x3', 'decomp_proxq_apply_f64',
+    'decomp_gemm_nt_tf32x3_splitk_workspace_bytes', 'decomp_gemm_nt_tf32x3_splitk_f64', 'decomp_nmf_xupdate_tf32x3',
+    'decomp_split_transpose_tf32_f64',
     'decomp_lasso_resident_supported', 'decomp_lasso_resident_f64', 'decomp_staged_upload',
 )
 

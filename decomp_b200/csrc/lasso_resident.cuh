@@ -188,7 +188,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             const long long m1 = row_begin + (long long)tile * BM;
             for (int kb2 = 0; kb2 < KB; ++kb2) {
               tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1);
-              tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1 + BMG);   // one box per warp group
+              if (m1 + BMG < a.M) tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1 + BMG);   // one box per warp group
             }
             const long long rows = row_end - m1 < BM ? row_end - m1 : BM;
             for (long long r = 0; r < rows; ++r) {

@@ -20,6 +20,7 @@
 // Per iteration: GEMM reads 2 x 4 B and writes 4 B per element, the pass reads 4 + 8 + 8 B and writes 8 + 4 + 4 B:
 // 48 B per element against 40 B for the fused FP64 launch, but nothing is bound by the FP64 tensor pipe any more.
 #include <cudaTypedefs.h>
+#include <string.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -98,10 +99,36 @@ constexpr int TB_BYTES = TNMAX * TBK * 4;        // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;   // 96 KB
 constexpr int TSMEM_BYTES = TSTAGES * TSTAGE_BYTES + 16 * 8;
 
+// what the epilogue warps do with a finished 128 x mma_n accumulator tile
+constexpr int TF_STORE = 0;     // P[row][n0 + c] = acc                              (FP32)
+constexpr int TF_PARTIAL = 1;   // P[(z * M + row)][n0 + c] = acc of K-split z        (FP32 slabs, reduced in FP64 later)
+constexpr int TF_XUPD = 2;      // NMF x update: x <- x * max(acc, 0) / max(neg, eps)  (grads.py:84) in FP64, written as
+                                // FP64 x, its TF32 pair row-major and its TF32 pair transposed
+
+struct Tf32Args {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  int mma_n;              // N of one MMA = rows of one B box (multiple of 32, <= 256); tiles_n boxes cover N
+  float* P;               // STORE / PARTIAL destination
+  long long ldp;
+  // XUPD
+  double* X;              // [M, N] in / out
+  long long ldx;
+  const float* NEG;       // [M, N] x (D D^T)
+  long long ldneg;
+  float* Xh;              // [M, N] TF32 pair of the new x, row-major (A operand of the next x G)
+  float* Xl;
+  long long ldxh;
+  float* XTh;             // [N, M] TF32 pair of the new x, transposed (A operand of x^T y, K-major)
+  float* XTl;
+  long long ldxt;
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                   float* __restrict__ P, long long ldp, int M, int N, int K, const int* __restrict__ skip_if) {
+                   const Tf32Args a, const int* __restrict__ skip_if) {
   if (skip_if != nullptr && *skip_if != 0) return;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TSTAGES * TSTAGE_BYTES);
@@ -111,8 +138,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = (M + TBM - 1) / TBM;
-  const int nkb = (K + TBK - 1) / TBK;
+  const int N = a.mma_n;
+  const int tiles_mn = a.tiles_m * a.tiles_n;
+  const int items = tiles_mn * a.splits;
   // two accumulators of N columns each; allocation is a power of two >= 32 columns
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * N)) cols <<= 1;
@@ -122,9 +150,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);   // one arrival per epilogue warp
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 4);   // one arrival per epilogue warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmAh);
@@ -143,23 +171,36 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // item -> (m tile, n tile, K split): consecutive items share the split and the B tile, so that CTAs running side by
+  // side hit the same operand lines in L2
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb, int& z) {
+    const int tm = item % a.tiles_m;
+    const int tn = (item / a.tiles_m) % a.tiles_n;
+    z = item / tiles_mn;
+    m0 = tm * TBM;
+    n0 = tn * N;
+    kb0 = z * a.kb_per_split;
+    nkb = a.kb_total - kb0 < a.kb_per_split ? a.kb_total - kb0 : a.kb_per_split;
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = 2u * TA_BYTES + 2u * (uint32_t)N * TBK * 4u;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = tile * TBM;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int m0, n0, kb0, nkb, z;
+        decode(item, m0, n0, kb0, nkb, z);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           unsigned char* st = smem + s * TSTAGE_BYTES;
-          const int k0 = kb * TBK;
+          const int k0 = (kb0 + kb) * TBK;
           tma_load_2d(st, &tmAh, &full_bar[s], k0, m0);
           tma_load_2d(st + TA_BYTES, &tmAl, &full_bar[s], k0, m0);
-          tma_load_2d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, 0);
-          tma_load_2d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, 0);
+          tma_load_2d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, n0);
+          tma_load_2d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, n0);
           if (++s == TSTAGES) {
             s = 0;
             ph ^= 1u;
@@ -175,7 +216,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     uint32_t ph = 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int m0, n0, kb0, nkb, z;
+      decode(item, m0, n0, kb0, nkb, z);
       mbar_wait(&acc_empty[acc], acc_ph ^ 1u);   // the epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
@@ -211,24 +254,62 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> P
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> memory
     const int e = warp - 4;                 // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const long long row = (long long)tile * TBM + e * 32 + lane;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int m0, n0, kb0, nkb, z;
+      decode(item, m0, n0, kb0, nkb, z);
+      const long long row = (long long)m0 + e * 32 + lane;
       mbar_wait(&acc_full[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * N);
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
-        if (row < M) {
-          float4* dst = reinterpret_cast<float4*>(P + row * ldp + c0);
+        if (row >= a.M || n0 + c0 >= a.N) continue;
+        if constexpr (MODE == TF_STORE || MODE == TF_PARTIAL) {
+          const long long prow = MODE == TF_PARTIAL ? (long long)z * a.M + row : row;
+          float* dst = a.P + prow * a.ldp + n0 + c0;
+          if (n0 + c0 + 32 <= a.N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                 __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
+          }
+        } else {
+          // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here
+          double* xr = a.X + row * a.ldx + c0;
+          const float* ng = a.NEG + row * a.ldneg + c0;
+          float* xh = a.Xh + row * a.ldxh + c0;
+          float* xl = a.Xl + row * a.ldxh + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
+            const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
+            const float4 n4 = *reinterpret_cast<const float4*>(ng + j);
+            const double xin[4] = {x01.x, x01.y, x23.x, x23.y};
+            const float nin[4] = {n4.x, n4.y, n4.z, n4.w};
+            double r[4];
+            float h[4], l[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const double pos = (double)__uint_as_float(v[j + t]);
+              r[t] = __ddiv_rn(__dmul_rn(xin[t], fmax(pos, 0.0)), fmax((double)nin[t], kEpsT));
+              split_tf32(r[t], h[t], l[t]);
+              a.XTh[(long long)(c0 + j + t) * a.ldxt + row] = h[t];   // a warp writes 32 consecutive rows: 128 bytes
+              a.XTl[(long long)(c0 + j + t) * a.ldxt + row] = l[t];
+            }
+            *reinterpret_cast<double2*>(xr + j) = make_double2(r[0], r[1]);
+            *reinterpret_cast<double2*>(xr + j + 2) = make_double2(r[2], r[3]);
+            *reinterpret_cast<float4*>(xh + j) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(xl + j) = make_float4(l[0], l[1], l[2], l[3]);
+          }
         }
       }
       tc_fence_before();
@@ -245,6 +326,50 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
+// out[m][n] = sum_z P[(z * M + m)][n] in FP64, fixed order (deterministic): the K-split slabs of TF_PARTIAL
+__global__ void reduce_partials_f32_kernel(const float* __restrict__ P, long long ldp, int splits, long long M,
+                                           long long N, double* __restrict__ out, long long ldo,
+                                           const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;
+  const long long total = M * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long m = idx / N, n = idx % N;
+    double acc = 0.0;
+    for (int z = 0; z < splits; ++z) acc += (double)P[((long long)z * M + m) * ldp + n];
+    out[m * ldo + n] = acc;
+  }
+}
+
+// A (float64 [rows, cols]) -> TF32 pair of A^T (float32 [cols, rows]): 32 x 32 tiles through shared memory
+__global__ void split_transpose_tf32_kernel(const double* __restrict__ A, long long lda, long long rows, long long cols,
+                                            float* __restrict__ hiT, float* __restrict__ loT, long long ldt) {
+  __shared__ float th[32][33], tl[32][33];
+  const long long tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
+  for (long long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
+    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = r0 + ty + 8 * i, c = c0 + tx;
+      float h = 0.f, l = 0.f;
+      if (r < rows && c < cols) split_tf32(A[r * lda + c], h, l);
+      th[ty + 8 * i][tx] = h;
+      tl[ty + 8 * i][tx] = l;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long c = c0 + ty + 8 * i, r = r0 + tx;
+      if (r < rows && c < cols) {
+        hiT[c * ldt + r] = th[tx][ty + 8 * i];
+        loT[c * ldt + r] = tl[tx][ty + 8 * i];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -371,6 +496,46 @@ static int make_map_f32(CUtensorMap* map, const float* base, uint64_t inner, uin
 
 using namespace dcp;
 
+// shared launcher of the three epilogue modes
+template <int MODE>
+static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
+                       int64_t ldb, Tf32Args& a, int64_t k_per_split, const int32_t* skip_if, void* stream) {
+  if (a.M <= 0 || a.N <= 0) return DECOMP_OK;
+  if (a.K <= 0) {
+    set_error("tf32x3 GEMM: K must be positive");
+    return DECOMP_ERR_INVALID;
+  }
+  a.mma_n = a.N >= TNMAX ? TNMAX : (int)((a.N + 31) / 32 * 32);
+  a.tiles_m = (a.M + TBM - 1) / TBM;
+  a.tiles_n = (a.N + a.mma_n - 1) / a.mma_n;
+  a.kb_total = (a.K + TBK - 1) / TBK;
+  a.kb_per_split = k_per_split > 0 ? (int)((k_per_split + TBK - 1) / TBK) : a.kb_total;
+  if (a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
+  a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  CUtensorMap tah, tal, tbh, tbl;
+  int rc = make_map_f32(&tah, A_hi, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+  if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+  if (rc != DECOMP_OK) return rc;
+  auto kern = tf32x3_gemm_kernel<MODE>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 smem)");
+    configured = true;
+  }
+  const long long items = (long long)a.tiles_m * a.tiles_n * a.splits;
+  if (items > 2147483647LL) {
+    set_error("tf32x3 GEMM: too many tiles");
+    return DECOMP_ERR_INVALID;
+  }
+  long long ctas = num_sms();
+  if (ctas > items) ctas = items;
+  kern<<<(unsigned)ctas, 256, TSMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
+  return check_cuda(cudaGetLastError(), "tf32x3 gemm launch");
+}
+
 extern "C" {
 
 int decomp_split_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ldh,
@@ -388,29 +553,98 @@ int decomp_gemm_nt_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, con
                           int64_t ldb, int64_t M, int64_t N, int64_t K, float* P, int64_t ldp, const int32_t* skip_if,
                           void* stream) {
   if (M <= 0) return DECOMP_OK;
-  if (N <= 0 || N > TNMAX || (N % 32) != 0 || K <= 0 || (ldp & 3) != 0) {
-    set_error("decomp_gemm_nt_tf32x3: needs 32 <= N <= 256, N %% 32 == 0, K > 0, ldp %% 4 == 0 (N=%lld K=%lld)",
-              (long long)N, (long long)K);
+  if (N <= 0 || K <= 0 || (ldp & 3) != 0 || M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) {
+    set_error("decomp_gemm_nt_tf32x3: needs N > 0, K > 0, ldp %% 4 == 0 (N=%lld K=%lld)", (long long)N, (long long)K);
     return DECOMP_ERR_UNSUPPORTED;
   }
-  CUtensorMap tah, tal, tbh, tbl;
-  int rc = make_map_f32(&tah, A_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda, TBM);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)N);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, (uint32_t)N);
-  if (rc != DECOMP_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 smem)");
-    configured = true;
+  Tf32Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = (int)N;
+  a.K = (int)K;
+  a.P = P;
+  a.ldp = ldp;
+  return launch_tf32<TF_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, a, 0, skip_if, stream);
+}
+
+size_t decomp_gemm_nt_tf32x3_splitk_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t k_per_split) {
+  if (M <= 0 || N <= 0 || K <= 0 || k_per_split <= 0) return 0;
+  const int64_t kb_total = (K + TBK - 1) / TBK;
+  int64_t per = (k_per_split + TBK - 1) / TBK;
+  if (per > kb_total) per = kb_total;
+  const int64_t splits = (kb_total + per - 1) / per;
+  const int64_t ldp = (N + 3) / 4 * 4;
+  return (size_t)splits * (size_t)M * (size_t)ldp * sizeof(float);
+}
+
+int decomp_gemm_nt_tf32x3_splitk_f64(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi,
+                                     const float* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K,
+                                     int64_t k_per_split, double* out, int64_t ldo, void* workspace,
+                                     size_t workspace_bytes, const int32_t* skip_if, void* stream) {
+  if (M <= 0 || N <= 0) return DECOMP_OK;
+  if (K <= 0 || k_per_split <= 0 || out == nullptr || M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) {
+    set_error("decomp_gemm_nt_tf32x3_splitk_f64: invalid argument");
+    return DECOMP_ERR_INVALID;
   }
-  long long tiles = (M + TBM - 1) / TBM;
-  long long ctas = num_sms();
-  if (ctas > tiles) ctas = tiles;
-  tf32x3_gemm_kernel<<<(unsigned)ctas, 256, TSMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, P, ldp, (int)M, (int)N,
-                                                                             (int)K, skip_if);
-  return check_cuda(cudaGetLastError(), "tf32x3 gemm launch");
+  const size_t need = decomp_gemm_nt_tf32x3_splitk_workspace_bytes(M, N, K, k_per_split);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("decomp_gemm_nt_tf32x3_splitk_f64: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DECOMP_ERR_INVALID;
+  }
+  Tf32Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = (int)N;
+  a.K = (int)K;
+  a.P = reinterpret_cast<float*>(workspace);
+  a.ldp = (N + 3) / 4 * 4;
+  int rc = launch_tf32<TF_PARTIAL>(A_hi, A_lo, lda, B_hi, B_lo, ldb, a, k_per_split, skip_if, stream);
+  if (rc != DECOMP_OK) return rc;
+  long long b = (M * N + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  reduce_partials_f32_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(a.P, a.ldp, a.splits, M, N, out, ldo, skip_if);
+  return check_cuda(cudaGetLastError(), "reduce_partials_f32 launch");
+}
+
+int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy, const float* D_hi, const float* D_lo,
+                              int64_t ldd, int64_t n, int64_t k, int64_t f, double* X, int64_t ldx, const float* NEG,
+                              int64_t ldneg, float* X_hi, float* X_lo, int64_t ldxh, float* XT_hi, float* XT_lo,
+                              int64_t ldxt, const int32_t* skip_if, void* stream) {
+  if (n <= 0) return DECOMP_OK;
+  if (k <= 0 || k > TNMAX || (k % 32) != 0 || f <= 0 || X == nullptr || NEG == nullptr || X_hi == nullptr ||
+      X_lo == nullptr || XT_hi == nullptr || XT_lo == nullptr || (ldx & 1) || (ldneg & 3) || (ldxh & 3) ||
+      n > 2147483647LL || f > 2147483647LL) {
+    set_error("decomp_nmf_xupdate_tf32x3: needs k %% 32 == 0, k <= 256, even ldx, ldneg and ldxh multiples of 4");
+    return DECOMP_ERR_UNSUPPORTED;
+  }
+  Tf32Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)n;
+  a.N = (int)k;
+  a.K = (int)f;
+  a.X = X;
+  a.ldx = ldx;
+  a.NEG = NEG;
+  a.ldneg = ldneg;
+  a.Xh = X_hi;
+  a.Xl = X_lo;
+  a.ldxh = ldxh;
+  a.XTh = XT_hi;
+  a.XTl = XT_lo;
+  a.ldxt = ldxt;
+  return launch_tf32<TF_XUPD>(Y_hi, Y_lo, ldy, D_hi, D_lo, ldd, a, 0, skip_if, stream);
+}
+
+int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hiT, float* loT,
+                                    int64_t ldt, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  const long long cap = (long long)num_sms() * 32;
+  if (tiles > cap) tiles = cap;
+  split_transpose_tf32_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(A, lda, rows, cols, hiT, loT, ldt);
+  DCP_CHECK_LAUNCH("split_transpose_tf32");
+  return DECOMP_OK;
 }
 
 int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,

@@ -33,13 +33,19 @@ POLL_EVERY = 25
 
 
 def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', likelihood='l2', mask=None,
-          random_seed=None, group=None, host_block_rows=None, **kwargs):
+          random_seed=None, group=None, host_block_rows=None, precision='fp64', **kwargs):
     """NMF, see the module docstring. ``likelihood``: 'l2' | 'gaussian' | 'kl' | 'poisson'.
 
     ``host_block_rows`` (not in the reference; numpy inputs, 'l2' only): out-of-core mode for data larger than the
     GPU memory.  ``y`` (and ``mask``) stay in host memory, are page-locked in place and streamed through three
     rotating device buffers of that many rows by a copy stream while the previous block is being processed
     (the role of the reference's ``AsyncMinibatchData``, utils/data.py:212-313); ``x`` and ``D`` live on the device.
+
+    ``precision`` (not in the reference): 'fp64' (default; matches the numpy path to ~1e-13) or 'tf32x3' -- full-batch
+    unmasked 'l2' MU with the three large contractions (y D^T, x (D D^T), x^T y / x^T x) on the tcgen05 tensor cores,
+    operands split into two TF32 pieces, FP32 accumulation in tensor memory (sample-axis sums in slabs of 4096 rows
+    added up in FP64); the ratios, the D update and the normalisation stay FP64.  Agrees with the FP64 path to ~1e-5
+    relative on D and x (tests/test_tf32x3_gpu.py states the tolerance).  Needs k a multiple of 32 up to 256.
 
     ``group``: optional ``torch.distributed`` process group. Each rank passes its own contiguous block of
     rows of ``y`` / ``x`` / ``mask`` and the same ``D``; per sweep only the [k, f] and [k, k] statistics
@@ -71,6 +77,12 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
         kl = True
     else:
         raise NotImplementedError('Likelihood {} is not implemented for nmf'.format(likelihood))
+    if precision not in ('fp64', 'tf32x3'):
+        raise ValueError("precision must be 'fp64' or 'tf32x3', given " + str(precision))
+    if precision == 'tf32x3' and (kl or mask is not None or minibatch is not None or host_block_rows is not None
+                                  or D.shape[0] % 32 != 0 or D.shape[0] > 256):
+        raise NotImplementedError("precision='tf32x3' covers the full-batch unmasked 'l2' update with k a multiple of "
+                                  "32 up to 256; use precision='fp64'")
     if host_block_rows is not None:
         if minibatch is not None or method != 'mu' or kl or group is not None or is_torch(y) or kwargs:
             raise NotImplementedError("host_block_rows streams numpy data through the full-batch 'mu' / 'l2' solver "
@@ -92,7 +104,7 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
     md = to_device2d(mask, device, copy=False) if mask is not None else None
     Dd = to_device2d(D, device, copy=True)
     xd = to_device2d(x, device, copy=True)       # updated in place: always our own copy
-    it, Dd, xd = mu_device(yd, Dd, xd, float(tol), int(maxiter), kl, md, group=group)
+    it, Dd, xd = mu_device(yd, Dd, xd, float(tol), int(maxiter), kl, md, group=group, precision=precision)
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
@@ -122,9 +134,9 @@ def _solve_minibatch(y, D, x, tol, minibatch, maxiter, method, kl, mask, random_
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
-def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None):
+def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None, precision='fp64'):
     """Full-batch MU on device tensors; ``X`` [n, k] is updated in place. Returns ``(it, D, X)``."""
-    solver = MuSolver(y, D0, X, tol, kl=kl, mask=mask, group=group)
+    solver = MuSolver(y, D0, X, tol, kl=kl, mask=mask, group=group, precision=precision)
     stopped_at = 0
     for it in range(1, maxiter):
         if solver.checks and it % POLL_EVERY == 0:
@@ -143,9 +155,12 @@ class MuSolver(object):
     """Device state of a full-batch MU run; ``sweep(it)`` enqueues sweep number ``it`` (1-based, reading
     ``Dbuf[(it - 1) % 2]`` and writing ``Dbuf[it % 2]``) on the current stream without synchronising."""
 
-    def __init__(self, y, D0, X, tol, kl=False, mask=None, group=None):
+    def __init__(self, y, D0, X, tol, kl=False, mask=None, group=None, precision='fp64'):
         dev = y.device
         self.y, self.X, self.mask, self.kl, self.tol, self.group = y, X, mask, kl, tol, group
+        self.tf32 = precision == 'tf32x3'
+        if self.tf32 and (kl or mask is not None or D0.shape[0] % 32 != 0 or D0.shape[0] > 256):
+            raise NotImplementedError("precision='tf32x3': unmasked 'l2' update, k a multiple of 32 up to 256")
         self.n, self.f = n, f = y.shape
         self.k = k = D0.shape[0]
         self.Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]
@@ -153,8 +168,20 @@ class MuSolver(object):
         self.Draw = empty2d(k, f, False, dev)
         self.Dt = empty2d(f, k, False, dev)
         self.POS = empty2d(k, f, False, dev)
-        self.NEG = empty2d(n, k, False, dev)
-        self.ws = ops.gemm_tn_workspace_for([(k, f, n), (k, k, n)], dev)
+        if not self.tf32:
+            self.NEG = empty2d(n, k, False, dev)
+            self.ws = ops.gemm_tn_workspace_for([(k, f, n), (k, k, n)], dev)
+        else:
+            # TF32 pairs (float32 hi + lo) of everything the tensor cores read: y and y^T once, x / x^T / D / D D^T
+            # per sweep.  All operands are K-major: x^T y is the NT product of x^T [k, n] and y^T [f, n].
+            self.Yh, self.Yl = ops.split_tf32(y)
+            self.YTh, self.YTl = ops.split_transpose_tf32(y)
+            self.Xh, self.Xl = ops.split_tf32(X)
+            self.XTh, self.XTl = ops.empty_f32(k, n, dev), ops.empty_f32(k, n, dev)
+            self.Dh, self.Dl = ops.empty_f32(k, f, dev), ops.empty_f32(k, f, dev)
+            self.Gh, self.Gl = ops.empty_f32(k, k, dev), ops.empty_f32(k, k, dev)
+            self.NEG32 = ops.empty_f32(n, k, dev)
+            self.ws32 = ops.gemm_nt_tf32x3_splitk_workspace(k, max(f, k), n, dev)
         self.checks = tol > 0.0
         self.comm_events = None   # set to [] to collect (start, end) CUDA event pairs around each sweep's all-reduces
         self.latch = torch.zeros(1, dtype=torch.int32, device=dev) if self.checks else None
@@ -192,8 +219,28 @@ class MuSolver(object):
         E = ops.epilogue
         y, ym, X, mask, latch, ws, group = self.y, self.ym, self.X, self.mask, self.latch, self.ws, self.group
         D, Dn = self.Dbuf[(it - 1) % 2], self.Dbuf[it % 2]
-        Dt, POS, NEG, Draw = self.Dt, self.POS, self.NEG, self.Draw
-        if not self.kl and mask is None:
+        Dt, POS, Draw = self.Dt, self.POS, self.Draw
+        NEG = None if self.tf32 else self.NEG
+        if self.tf32:
+            G, S = self.G, self.S
+            # ---- x update (grads.py:108-111, f.dot(d.T) re-associated) on the tcgen05 tensor cores
+            ops.gemm_nt(D, D, E(ops.EPI_STORE, G), skip=latch)
+            ops.split_tf32(G, self.Gh, self.Gl)
+            ops.split_tf32(D, self.Dh, self.Dl)
+            ops.gemm_nt_tf32x3(self.Xh, self.Xl, self.Gh, self.Gl, self.NEG32, skip=latch)
+            ops.nmf_xupdate_tf32x3(self.Yh, self.Yl, self.Dh, self.Dl, X, self.NEG32, self.Xh, self.Xl, self.XTh,
+                                   self.XTl, skip=latch)
+            # ---- D update (grads.py:117-121): statistics over the sample axis, FP32 slabs of 4096 rows summed in FP64
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.YTh, self.YTl, POS, self.ws32, skip=latch)
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.XTh, self.XTl, S, self.ws32, skip=latch)
+            if group is not None:
+                t0 = self._comm_mark()
+                _allreduce2d(POS, group)
+                _allreduce2d(S, group)
+                self._comm_mark(t0)
+            ops.make_rhs(D, False, False, out=Dt, skip=latch)
+            ops.gemm_nt(S, Dt, E(ops.EPI_MU_DEN, Draw, x=D, other=POS), skip=latch)
+        elif not self.kl and mask is None:
             G, S = self.G, self.S
             # ---- x update (grads.py:108-111 with f.dot(d.T) re-associated)
             ops.gemm_nt(D, D, E(ops.EPI_STORE, G), skip=latch)

@@ -367,6 +367,48 @@ def gemm_nt_tf32x3(A_hi, A_lo, B_hi, B_lo, P, skip=None):
     return P
 
 
+def split_transpose_tf32(A, hiT=None, loT=None):
+    """TF32 pair of A^T: float32 [cols, rows] pieces of the float64 [rows, cols] matrix A."""
+    rows, cols = A.shape
+    if hiT is None:
+        hiT, loT = empty_f32(cols, rows, A.device), empty_f32(cols, rows, A.device)
+    rc = _lib.lib().decomp_split_transpose_tf32_f64(_p(A), ld(A), rows, cols, _p(hiT), _p(loT), ld(hiT),
+                                                    _lib.stream_ptr())
+    _lib.check(rc, 'decomp_split_transpose_tf32_f64')
+    _count(1)
+    return hiT, loT
+
+
+TF32_K_PER_SPLIT = 4096   # FP32 accumulation length of the split-K statistics (rows per slab)
+
+
+def gemm_nt_tf32x3_splitk_workspace(M, N, K, device, k_per_split=TF32_K_PER_SPLIT):
+    return workspace(_lib.lib().decomp_gemm_nt_tf32x3_splitk_workspace_bytes(M, N, K, k_per_split), device)
+
+
+def gemm_nt_tf32x3_splitk(A_hi, A_lo, B_hi, B_lo, out, ws, k_per_split=TF32_K_PER_SPLIT, skip=None):
+    """out (float64 [M, N]) = A . B^T in split TF32, the contraction cut into FP32-accumulated slabs summed in FP64."""
+    M, K = A_hi.shape
+    N = B_hi.shape[0]
+    rc = _lib.lib().decomp_gemm_nt_tf32x3_splitk_f64(_p(A_hi), _p(A_lo), ld(A_hi), _p(B_hi), _p(B_lo), ld(B_hi), M, N, K,
+                                                     k_per_split, _p(out), ld(out), _p(ws), ws.numel() * 8, _p(skip),
+                                                     _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_nt_tf32x3_splitk_f64')
+    _count(2)
+    return out
+
+
+def nmf_xupdate_tf32x3(Y_hi, Y_lo, D_hi, D_lo, X, NEG, X_hi, X_lo, XT_hi, XT_lo, skip=None):
+    """X <- X * max(Y D^T, 0) / max(NEG, eps) with the GEMM on tcgen05 (TF32 split); see decomp_b200.h."""
+    n, f = Y_hi.shape
+    k = D_hi.shape[0]
+    rc = _lib.lib().decomp_nmf_xupdate_tf32x3(_p(Y_hi), _p(Y_lo), ld(Y_hi), _p(D_hi), _p(D_lo), ld(D_hi), n, k, f, _p(X),
+                                              ld(X), _p(NEG), ld(NEG), _p(X_hi), _p(X_lo), ld(X_hi), _p(XT_hi), _p(XT_lo),
+                                              ld(XT_hi), _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_nmf_xupdate_tf32x3')
+    _count(1)
+
+
 RESIDENT_MAX_ITERS = 32
 
 

@@ -70,3 +70,115 @@ def test_lasso_tf32x3_unsupported_shapes():
         lasso.solve(y, A, 0.05, mask=mask, precision='tf32x3')          # masked iteration is FP64 only
     with pytest.raises(ValueError):
         lasso.solve(y, A, 0.05, precision='fp16')
+
+
+# ------------------------------------------------------------------------------------------------ NMF on tcgen05
+NMF_RTOL = 1.0e-4        # D and x after a full solve, relative max-norm, against the FP64 path
+NMF_OBJ_RTOL = 1.0e-5    # objective 1/2 |y - x D|^2
+
+
+@pytest.mark.parametrize('M,N,K', [(500, 300, 100), (260, 1024, 96), (129, 520, 33)])
+def test_gemm_nt_tf32x3_tiles_over_n(M, N, K):
+    """N beyond one 256-wide MMA: several B boxes, the last one partly outside the matrix (zero-filled by TMA)."""
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d
+    rng = np.random.RandomState(M + N + K)
+    A, B = rng.randn(M, K), rng.randn(N, K)
+    Ah, Al = ops.split_tf32(to_device2d(A))
+    Bh, Bl = ops.split_tf32(to_device2d(B))
+    P = ops.empty_f32(M, N, 'cuda')
+    P.fill_(float('nan'))
+    ops.gemm_nt_tf32x3(Ah, Al, Bh, Bl, P)
+    torch.cuda.synchronize()
+    err = np.max(np.abs(P.double().cpu().numpy() - A.dot(B.T))) / np.abs(A).dot(np.abs(B.T)).max()
+    assert err <= GEMM_RTOL, 'rel err %g' % err
+
+
+@pytest.mark.parametrize('M,N,K,per', [(64, 300, 10000, 4096), (256, 256, 5000, 1024), (40, 70, 100, 4096)])
+def test_gemm_nt_tf32x3_splitk(M, N, K, per):
+    """Contraction cut into FP32-accumulated slabs that are summed in FP64 (x^T y, x^T x of the NMF sweep)."""
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d, empty2d
+    rng = np.random.RandomState(M + N + K)
+    A, B = np.abs(rng.randn(M, K)), np.abs(rng.randn(N, K))          # same-sign terms: the hard case for FP32 sums
+    Ah, Al = ops.split_tf32(to_device2d(A))
+    Bh, Bl = ops.split_tf32(to_device2d(B))
+    out = empty2d(M, N, False, torch.device('cuda', 0))
+    ws = ops.gemm_nt_tf32x3_splitk_workspace(M, N, K, 'cuda', per)
+    ops.gemm_nt_tf32x3_splitk(Ah, Al, Bh, Bl, out, ws, per)
+    torch.cuda.synchronize()
+    ref = A.dot(B.T)
+    err = np.max(np.abs(out.cpu().numpy() - ref) / ref)
+    print('split-K tf32x3 M=%d N=%d K=%d slab=%d: max rel err %.3g' % (M, N, K, per, err))
+    assert err <= 5.0e-6, 'rel err %g' % err
+
+
+def test_split_transpose_tf32():
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d
+    rng = np.random.RandomState(3)
+    for rows, cols in [(1, 1), (33, 65), (300, 40), (64, 1000)]:
+        A = rng.randn(rows, cols)
+        hT, lT = ops.split_transpose_tf32(to_device2d(A))
+        h, l = ops.split_tf32(to_device2d(A))
+        torch.cuda.synchronize()
+        assert hT.shape == (cols, rows)
+        assert torch.equal(hT, h.t()) and torch.equal(lT, l.t())
+
+
+@pytest.mark.parametrize('n,f,k', [(300, 96, 32), (1000, 200, 64), (257, 4100, 256)])
+def test_nmf_xupdate_tf32x3_kernel(n, f, k):
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d
+    rng = np.random.RandomState(n + f + k)
+    y, D, x = np.abs(rng.randn(n, f)), np.abs(rng.randn(k, f)), np.abs(rng.randn(n, k)) + 0.1
+    neg = x.dot(D.dot(D.T))
+    Yh, Yl = ops.split_tf32(to_device2d(y))
+    Dh, Dl = ops.split_tf32(to_device2d(D))
+    X = to_device2d(x)
+    NEG = ops.empty_f32(n, k, 'cuda')
+    NEG.copy_(torch.from_numpy(neg.astype(np.float32)))
+    Xh, Xl = ops.empty_f32(n, k, 'cuda'), ops.empty_f32(n, k, 'cuda')
+    XTh, XTl = ops.empty_f32(k, n, 'cuda'), ops.empty_f32(k, n, 'cuda')
+    ops.nmf_xupdate_tf32x3(Yh, Yl, Dh, Dl, X, NEG, Xh, Xl, XTh, XTl)
+    torch.cuda.synchronize()
+    ref = x * np.maximum(y.dot(D.T), 0.0) / np.maximum(neg, 1e-15)
+    got = X.cpu().numpy()
+    assert np.max(np.abs(got - ref) / ref) <= 5.0e-6
+    rec = Xh.double().cpu().numpy() + Xl.double().cpu().numpy()
+    assert np.max(np.abs(rec - got)) <= 2.0 ** -21 * np.max(np.abs(got))
+    assert torch.equal(XTh, Xh.t()) and torch.equal(XTl, Xl.t())
+
+
+@pytest.mark.parametrize('n,f,k,sweeps', [(3001, 517, 64, 20), (9000, 260, 256, 10)])
+def test_nmf_tf32x3_vs_fp64(n, f, k, sweeps):
+    """Whole solves: the TF32-split path against the FP64 path (which matches the reference to 1e-10)."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, _ = gc._nmf_data(n, f, k, 11)
+    it64, D64, x64 = nmf.solve(y, D0.copy(), tol=0.0, maxiter=sweeps + 1)
+    it32, D32, x32 = nmf.solve(y, D0.copy(), tol=0.0, maxiter=sweeps + 1, precision='tf32x3')
+    assert it64 == it32 == sweeps + 1
+    eD = np.max(np.abs(D32 - D64)) / np.max(np.abs(D64))
+    ex = np.max(np.abs(x32 - x64)) / np.max(np.abs(x64))
+    o64, o32 = orc.nmf_objective(y, x64, D64), orc.nmf_objective(y, x32, D32)
+    print('nmf tf32x3 n=%d f=%d k=%d sweeps=%d: err_D %.3g err_x %.3g objective %.3g'
+          % (n, f, k, sweeps, eD, ex, abs(o32 - o64) / abs(o64)))
+    assert eD <= NMF_RTOL and ex <= NMF_RTOL
+    assert abs(o32 - o64) <= NMF_OBJ_RTOL * abs(o64)
+
+
+def test_nmf_tf32x3_convergence_and_unsupported():
+    from decomp_b200 import nmf
+    y, D0, mask = gc._nmf_data(1501, 130, 32, 5)
+    it64, D64, _ = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=400)
+    it32, D32, _ = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=400, precision='tf32x3')
+    assert 1 < it32 < 400 and abs(it32 - it64) <= 3
+    assert np.max(np.abs(D32 - D64)) / np.max(np.abs(D64)) <= 1.0e-3
+    with pytest.raises(NotImplementedError):
+        nmf.solve(y, D0.copy(), mask=mask, precision='tf32x3')
+    y2, D2, _ = gc._nmf_data(100, 20, 3, 0)
+    with pytest.raises(NotImplementedError):
+        nmf.solve(y2, D2.copy(), precision='tf32x3')                     # k = 3
+    with pytest.raises(ValueError):
+        nmf.solve(y, D0.copy(), precision='bf16')
