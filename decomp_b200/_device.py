@@ -57,7 +57,8 @@ def full2d(rows, cols, value, cplx=False, device=None):
 
 _STAGED_DTYPES = (torch.float32, torch.float64, torch.complex64, torch.complex128)
 STAGE_MIN_BYTES = 64 << 20    # pageable arrays from this size on go up through the staged path below
-STAGE_PIECE_BYTES = int(os.environ.get('DECOMP_STAGE_PIECE_MB', '8')) << 20
+STAGE_PIECE_BYTES = (int(os.environ['DECOMP_STAGE_PIECE_KB']) << 10 if 'DECOMP_STAGE_PIECE_KB' in os.environ
+                     else int(os.environ.get('DECOMP_STAGE_PIECE_MB', '4')) << 20)
 
 
 def _stage_threads():

@@ -287,7 +287,14 @@ __global__ void normalize_rows_kernel(const double* __restrict__ Din, long long 
       const unsigned long long bits = atomicMax(reinterpret_cast<unsigned long long*>(maxdiff), 0ull);
       const double m = __longlong_as_double((long long)bits);
       maxdiff[1] = m;
-      if (tol_latch != nullptr && m < tol) *tol_latch = latch_value;
+      // latch_value < 0: the value is the number of this call, counted in scratch[1] (launches replayed from a CUDA
+      // graph cannot carry a different value per replay)
+      int value = latch_value;
+      if (latch_value < 0) {
+        value = scratch[1] + 1;
+        scratch[1] = value;
+      }
+      if (tol_latch != nullptr && m < tol) *tol_latch = value;
       maxdiff[0] = 0.0;
       scratch[0] = 0;
     }
@@ -335,7 +342,14 @@ __global__ void normalize_rows_complex_kernel(const double* __restrict__ Din, lo
       const unsigned long long bits = atomicMax(reinterpret_cast<unsigned long long*>(maxdiff), 0ull);
       const double m = __longlong_as_double((long long)bits);
       maxdiff[1] = m;
-      if (tol_latch != nullptr && m < tol) *tol_latch = latch_value;
+      // latch_value < 0: the value is the number of this call, counted in scratch[1] (launches replayed from a CUDA
+      // graph cannot carry a different value per replay)
+      int value = latch_value;
+      if (latch_value < 0) {
+        value = scratch[1] + 1;
+        scratch[1] = value;
+      }
+      if (tol_latch != nullptr && m < tol) *tol_latch = value;
       maxdiff[0] = 0.0;
       scratch[0] = 0;
     }

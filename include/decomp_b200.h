@@ -144,7 +144,9 @@ int decomp_row_sums_f64(const double* A, int64_t lda, int64_t rows, int64_t cols
 int decomp_gershgorin_step_f64(const double* G, int64_t ldg, int64_t k, int32_t is_complex,
                                const double* alpha_scaled, double* step_out, double* thr_out, void* stream);
 /* D_out[i] = D_in[i] / ||D_in[i]|| (strict) or / sqrt(max(||.||^2, 1)) (soft); *maxdiff = max |D_ref - D_out|;
- * if tol_latch != NULL and maxdiff < tol: *tol_latch = latch_value  (normalize.py:2-21; batch_mu.py:21-23) */
+ * if tol_latch != NULL and maxdiff < tol: *tol_latch = latch_value  (normalize.py:2-21; batch_mu.py:21-23).
+ * `scratch`: two zero-initialised int32 (a ticket counter and a call counter); with latch_value < 0 the value written
+ * is the running number of the call (1, 2, ...), for launches replayed from a CUDA graph. */
 int decomp_normalize_rows_f64(const double* D_in, int64_t ldi, int64_t rows, int64_t cols, int32_t is_complex,
                               int32_t strict, double* D_out, int64_t ldo, const double* D_ref, int64_t ldr,
                               double tol, int32_t* tol_latch, int32_t latch_value, double* maxdiff,

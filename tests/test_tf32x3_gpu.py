@@ -100,17 +100,29 @@ def test_gemm_nt_tf32x3_splitk(M, N, K, per):
     from decomp_b200 import ops
     from decomp_b200._device import to_device2d, empty2d
     rng = np.random.RandomState(M + N + K)
-    A, B = np.abs(rng.randn(M, K)), np.abs(rng.randn(N, K))          # same-sign terms: the hard case for FP32 sums
-    Ah, Al = ops.split_tf32(to_device2d(A))
-    Bh, Bl = ops.split_tf32(to_device2d(B))
     out = empty2d(M, N, False, torch.device('cuda', 0))
     ws = ops.gemm_nt_tf32x3_splitk_workspace(M, N, K, 'cuda', per)
+    # mixed signs: rounding errors of the FP32 accumulation average out
+    A, B = rng.randn(M, K), rng.randn(N, K)
+    Ah, Al = ops.split_tf32(to_device2d(A))
+    Bh, Bl = ops.split_tf32(to_device2d(B))
+    ops.gemm_nt_tf32x3_splitk(Ah, Al, Bh, Bl, out, ws, per)
+    torch.cuda.synchronize()
+    err = np.max(np.abs(out.cpu().numpy() - A.dot(B.T))) / np.abs(A).dot(np.abs(B.T)).max()
+    assert err <= GEMM_RTOL, 'rel err %g' % err
+    # same-sign terms (what NMF feeds it): the tensor core truncates its FP32 accumulator, about half an ulp per
+    # accumulator update, 3 updates per 8 contraction elements -> a systematic relative deficit of
+    # ~ slab / 8 * 3 * 2^-25 (4.6e-5 for slabs of 4096 rows), which is why the slabs are bounded and summed in FP64
+    A, B = np.abs(A), np.abs(B)
+    Ah, Al = ops.split_tf32(to_device2d(A))
+    Bh, Bl = ops.split_tf32(to_device2d(B))
     ops.gemm_nt_tf32x3_splitk(Ah, Al, Bh, Bl, out, ws, per)
     torch.cuda.synchronize()
     ref = A.dot(B.T)
     err = np.max(np.abs(out.cpu().numpy() - ref) / ref)
-    print('split-K tf32x3 M=%d N=%d K=%d slab=%d: max rel err %.3g' % (M, N, K, per, err))
-    assert err <= 5.0e-6, 'rel err %g' % err
+    bound = max(2.0e-6, 1.5 * min(per, K) / 8 * 3 * 2.0 ** -25)
+    print('split-K tf32x3 M=%d N=%d K=%d slab=%d: same-sign max rel err %.3g (bound %.3g)' % (M, N, K, per, err, bound))
+    assert err <= bound, 'rel err %g > %g' % (err, bound)
 
 
 def test_split_transpose_tf32():
@@ -144,7 +156,9 @@ def test_nmf_xupdate_tf32x3_kernel(n, f, k):
     torch.cuda.synchronize()
     ref = x * np.maximum(y.dot(D.T), 0.0) / np.maximum(neg, 1e-15)
     got = X.cpu().numpy()
-    assert np.max(np.abs(got - ref) / ref) <= 5.0e-6
+    err = np.max(np.abs(got - ref) / ref)
+    print('nmf x update tf32x3 n=%d f=%d k=%d: max rel err %.3g' % (n, f, k, err))
+    assert err <= max(5.0e-6, 1.5 * f / 8 * 3 * 2.0 ** -25)      # same-sign sums over f terms, see the split-K test
     rec = Xh.double().cpu().numpy() + Xl.double().cpu().numpy()
     assert np.max(np.abs(rec - got)) <= 2.0 ** -21 * np.max(np.abs(got))
     assert torch.equal(XTh, Xh.t()) and torch.equal(XTl, Xl.t())

@@ -1,15 +1,19 @@
-"""Short NMF-MU run for ncu: 131072 rows x 4096 features, k=256 (the per-GPU shape of BASELINE configs[2] cut in rows)."""
+"""Short NMF-MU run for ncu: configs[2] shape at a reduced row count, a few sweeps.
+usage: python tools/prof_nmf.py [rows] [sweeps] [fp64|tf32x3]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import bench
 from decomp_b200 import nmf
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
+sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+precision = sys.argv[3] if len(sys.argv) > 3 else 'fp64'
 dev = torch.device('cuda', 0)
-y, D0, _ = bench.nmf_data_device(torch, 131072, 4096, 256, 0, dev)
-X = torch.ones((131072, 256), dtype=torch.float64, device=dev)
-s = nmf.MuSolver(y, D0, X, 0.0)
-for it in range(1, 4):
-    s.sweep(it)
+y, D0, _ = bench.nmf_data_device(torch, rows, 4096, 256, 0, dev)
+X = torch.ones((rows, 256), dtype=torch.float64, device=dev)
+solver = nmf.MuSolver(y, D0, X, 0.0, precision=precision)
+for it in range(1, sweeps + 1):
+    solver.sweep(it)
 torch.cuda.synchronize()
-print('ok', float(X.sum().item()))
+print('ok', float(solver.Dbuf[sweeps % 2].sum().item()))
