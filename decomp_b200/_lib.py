@@ -79,11 +79,11 @@ def _declare(lib):
                                           c_dp]
     lib.decomp_gemm_nt_tf32x3_splitk_workspace_bytes.argtypes = [c_i64, c_i64, c_i64, c_i64]
     lib.decomp_gemm_nt_tf32x3_splitk_workspace_bytes.restype = ctypes.c_size_t
-    lib.decomp_gemm_nt_tf32x3_splitk_f64.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_i64, c_dp,
-                                                     c_i64, c_dp, ctypes.c_size_t, c_dp, c_dp]
+    lib.decomp_gemm_nt_tf32x3_splitk_f64.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32,
+                                                     c_dp, c_i64, c_dp, ctypes.c_size_t, c_dp, c_dp]
     lib.decomp_nmf_xupdate_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp,
-                                              c_i64, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_dp, c_dp]
-    lib.decomp_split_transpose_tf32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_dp]
+                                              c_i64, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp, c_dp]
+    lib.decomp_split_transpose_tf32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp]
     lib.decomp_proxq_apply_f64.argtypes = [c_dp, c_i64, ctypes.POINTER(Epilogue), c_dp, c_dp, c_i64, c_i64, c_i64, c_dp,
                                            c_dp]
     lib.decomp_lasso_resident_supported.argtypes = [c_i64]

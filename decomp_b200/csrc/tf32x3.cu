@@ -109,6 +109,10 @@ struct Tf32Args {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
   int mma_n;              // N of one MMA = rows of one B box (multiple of 32, <= 256); tiles_n boxes cover N
+  int blocked;            // operands stored K-blocked, [K / kblock][rows][kblock] with kblock = 32 kb_per_split: split z
+                          // reads block z (3-D tensor maps).  A sample-axis contraction over row-major x^T, y^T would
+                          // touch one 128-byte piece per row 4 n bytes apart -- hundreds of pages per TMA box
+  long long xt_block;     // XUPD: block length of the K-blocked transposed output (0: plain [N][ldxt])
   float* P;               // STORE / PARTIAL destination
   long long ldp;
   // XUPD
@@ -196,11 +200,19 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           unsigned char* st = smem + s * TSTAGE_BYTES;
-          const int k0 = (kb0 + kb) * TBK;
-          tma_load_2d(st, &tmAh, &full_bar[s], k0, m0);
-          tma_load_2d(st + TA_BYTES, &tmAl, &full_bar[s], k0, m0);
-          tma_load_2d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, n0);
-          tma_load_2d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, n0);
+          if (a.blocked) {
+            const int k0 = kb * TBK;   // inside block z
+            tma_load_3d(st, &tmAh, &full_bar[s], k0, m0, z);
+            tma_load_3d(st + TA_BYTES, &tmAl, &full_bar[s], k0, m0, z);
+            tma_load_3d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, n0, z);
+            tma_load_3d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, n0, z);
+          } else {
+            const int k0 = (kb0 + kb) * TBK;
+            tma_load_2d(st, &tmAh, &full_bar[s], k0, m0);
+            tma_load_2d(st + TA_BYTES, &tmAl, &full_bar[s], k0, m0);
+            tma_load_2d(st + 2 * TA_BYTES, &tmBh, &full_bar[s], k0, n0);
+            tma_load_2d(st + 2 * TA_BYTES + TB_BYTES, &tmBl, &full_bar[s], k0, n0);
+          }
           if (++s == TSTAGES) {
             s = 0;
             ph ^= 1u;
@@ -302,8 +314,12 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
               const double pos = (double)__uint_as_float(v[j + t]);
               r[t] = __ddiv_rn(__dmul_rn(xin[t], fmax(pos, 0.0)), fmax((double)nin[t], kEpsT));
               split_tf32(r[t], h[t], l[t]);
-              a.XTh[(long long)(c0 + j + t) * a.ldxt + row] = h[t];   // a warp writes 32 consecutive rows: 128 bytes
-              a.XTl[(long long)(c0 + j + t) * a.ldxt + row] = l[t];
+              // a warp writes 32 consecutive rows: 128 contiguous bytes in either layout
+              const long long ti = a.xt_block > 0
+                                       ? ((row / a.xt_block) * a.N + (c0 + j + t)) * a.xt_block + row % a.xt_block
+                                       : (long long)(c0 + j + t) * a.ldxt + row;
+              a.XTh[ti] = h[t];
+              a.XTl[ti] = l[t];
             }
             *reinterpret_cast<double2*>(xr + j) = make_double2(r[0], r[1]);
             *reinterpret_cast<double2*>(xr + j + 2) = make_double2(r[2], r[3]);
@@ -345,10 +361,13 @@ __global__ void reduce_partials_f32_kernel(const float* __restrict__ P, long lon
 }
 
 // A (float64 [rows, cols]) -> TF32 pair of A^T (float32 [cols, rows]): 32 x 32 tiles through shared memory
+// block > 0: K-blocked output [ceil(rows / block)][cols][block], the rows beyond `rows` of the last block zero-filled
 __global__ void split_transpose_tf32_kernel(const double* __restrict__ A, long long lda, long long rows, long long cols,
-                                            float* __restrict__ hiT, float* __restrict__ loT, long long ldt) {
+                                            float* __restrict__ hiT, float* __restrict__ loT, long long ldt,
+                                            long long block) {
   __shared__ float th[32][33], tl[32][33];
-  const long long tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+  const long long rows_out = block > 0 ? (rows + block - 1) / block * block : rows;
+  const long long tiles_c = (cols + 31) / 32, tiles_r = (rows_out + 31) / 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads
   for (long long t = blockIdx.x; t < tiles_r * tiles_c; t += gridDim.x) {
     const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
@@ -364,9 +383,10 @@ __global__ void split_transpose_tf32_kernel(const double* __restrict__ A, long l
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const long long c = c0 + ty + 8 * i, r = r0 + tx;
-      if (r < rows && c < cols) {
-        hiT[c * ldt + r] = th[tx][ty + 8 * i];
-        loT[c * ldt + r] = tl[tx][ty + 8 * i];
+      if (r < rows_out && c < cols) {
+        const long long o = block > 0 ? ((r / block) * cols + c) * block + r % block : c * ldt + r;
+        hiT[o] = th[tx][ty + 8 * i];
+        loT[o] = tl[tx][ty + 8 * i];
       }
     }
     __syncthreads();
@@ -492,6 +512,32 @@ static int make_map_f32(CUtensorMap* map, const float* base, uint64_t inner, uin
   return DECOMP_OK;
 }
 
+// K-blocked FP32 operand [blocks][rows][block]: 3-D map {block, rows, blocks}, box {32, box_rows, 1}
+static int make_map_f32_blocked(CUtensorMap* map, const float* base, uint64_t block, uint64_t rows, uint64_t blocks,
+                                uint32_t box_rows) {
+  auto enc = encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return DECOMP_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (block & 31u) != 0) {
+    set_error("K-blocked TF32 operand must be 16-byte aligned with a block length that is a multiple of 32");
+    return DECOMP_ERR_INVALID;
+  }
+  cuuint64_t gdim[3] = {block, rows, blocks};
+  cuuint64_t gstride[2] = {block * sizeof(float), rows * block * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (f32, blocked) failed with CUresult %d", (int)r);
+    return DECOMP_ERR_CUDA;
+  }
+  return DECOMP_OK;
+}
+
 }  // namespace dcp
 
 using namespace dcp;
@@ -513,10 +559,19 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   if (a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
   a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   CUtensorMap tah, tal, tbh, tbl;
-  int rc = make_map_f32(&tah, A_hi, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
-  if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+  int rc;
+  if (a.blocked) {
+    const uint64_t block = (uint64_t)a.kb_per_split * TBK, blocks = (uint64_t)a.splits;
+    rc = make_map_f32_blocked(&tah, A_hi, block, (uint64_t)a.M, blocks, TBM);
+    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tal, A_lo, block, (uint64_t)a.M, blocks, TBM);
+    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbh, B_hi, block, (uint64_t)a.N, blocks, (uint32_t)a.mma_n);
+    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbl, B_lo, block, (uint64_t)a.N, blocks, (uint32_t)a.mma_n);
+  } else {
+    rc = make_map_f32(&tah, A_hi, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
+    if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
+    if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+    if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+  }
   if (rc != DECOMP_OK) return rc;
   auto kern = tf32x3_gemm_kernel<MODE>;
   static bool configured = false;   // per instantiation
@@ -579,11 +634,12 @@ size_t decomp_gemm_nt_tf32x3_splitk_workspace_bytes(int64_t M, int64_t N, int64_
 
 int decomp_gemm_nt_tf32x3_splitk_f64(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi,
                                      const float* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                                     int64_t k_per_split, double* out, int64_t ldo, void* workspace,
+                                     int64_t k_per_split, int32_t k_blocked, double* out, int64_t ldo, void* workspace,
                                      size_t workspace_bytes, const int32_t* skip_if, void* stream) {
   if (M <= 0 || N <= 0) return DECOMP_OK;
-  if (K <= 0 || k_per_split <= 0 || out == nullptr || M > 2147483647LL || N > 2147483647LL || K > 2147483647LL) {
-    set_error("decomp_gemm_nt_tf32x3_splitk_f64: invalid argument");
+  if (K <= 0 || k_per_split <= 0 || out == nullptr || M > 2147483647LL || N > 2147483647LL || K > 2147483647LL ||
+      (k_blocked && (k_per_split % TBK) != 0)) {
+    set_error("decomp_gemm_nt_tf32x3_splitk_f64: invalid argument (a K-blocked layout needs k_per_split %% 32 == 0)");
     return DECOMP_ERR_INVALID;
   }
   const size_t need = decomp_gemm_nt_tf32x3_splitk_workspace_bytes(M, N, K, k_per_split);
@@ -598,6 +654,7 @@ int decomp_gemm_nt_tf32x3_splitk_f64(const float* A_hi, const float* A_lo, int64
   a.K = (int)K;
   a.P = reinterpret_cast<float*>(workspace);
   a.ldp = (N + 3) / 4 * 4;
+  a.blocked = k_blocked ? 1 : 0;
   int rc = launch_tf32<TF_PARTIAL>(A_hi, A_lo, lda, B_hi, B_lo, ldb, a, k_per_split, skip_if, stream);
   if (rc != DECOMP_OK) return rc;
   long long b = (M * N + 255) / 256;
@@ -610,13 +667,17 @@ int decomp_gemm_nt_tf32x3_splitk_f64(const float* A_hi, const float* A_lo, int64
 int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy, const float* D_hi, const float* D_lo,
                               int64_t ldd, int64_t n, int64_t k, int64_t f, double* X, int64_t ldx, const float* NEG,
                               int64_t ldneg, float* X_hi, float* X_lo, int64_t ldxh, float* XT_hi, float* XT_lo,
-                              int64_t ldxt, const int32_t* skip_if, void* stream) {
+                              int64_t ldxt, int64_t xt_block, const int32_t* skip_if, void* stream) {
   if (n <= 0) return DECOMP_OK;
   if (k <= 0 || k > TNMAX || (k % 32) != 0 || f <= 0 || X == nullptr || NEG == nullptr || X_hi == nullptr ||
       X_lo == nullptr || XT_hi == nullptr || XT_lo == nullptr || (ldx & 1) || (ldneg & 3) || (ldxh & 3) ||
       n > 2147483647LL || f > 2147483647LL) {
     set_error("decomp_nmf_xupdate_tf32x3: needs k %% 32 == 0, k <= 256, even ldx, ldneg and ldxh multiples of 4");
     return DECOMP_ERR_UNSUPPORTED;
+  }
+  if (xt_block > 0 && (xt_block % 128) != 0) {
+    set_error("decomp_nmf_xupdate_tf32x3: the block length of the transposed output must be a multiple of 128");
+    return DECOMP_ERR_INVALID;
   }
   Tf32Args a;
   memset(&a, 0, sizeof(a));
@@ -633,16 +694,19 @@ int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy,
   a.XTh = XT_hi;
   a.XTl = XT_lo;
   a.ldxt = ldxt;
+  a.xt_block = xt_block > 0 ? xt_block : 0;
   return launch_tf32<TF_XUPD>(Y_hi, Y_lo, ldy, D_hi, D_lo, ldd, a, 0, skip_if, stream);
 }
 
 int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hiT, float* loT,
-                                    int64_t ldt, void* stream) {
+                                    int64_t ldt, int64_t block, void* stream) {
   if (rows <= 0 || cols <= 0) return DECOMP_OK;
-  long long tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  const long long rows_out = block > 0 ? (rows + block - 1) / block * block : rows;
+  long long tiles = ((rows_out + 31) / 32) * ((cols + 31) / 32);
   const long long cap = (long long)num_sms() * 32;
   if (tiles > cap) tiles = cap;
-  split_transpose_tf32_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(A, lda, rows, cols, hiT, loT, ldt);
+  split_transpose_tf32_kernel<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(A, lda, rows, cols, hiT, loT, ldt,
+                                                                              block > 0 ? block : 0);
   DCP_CHECK_LAUNCH("split_transpose_tf32");
   return DECOMP_OK;
 }

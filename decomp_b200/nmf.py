@@ -215,14 +215,20 @@ class MuSolver(object):
         else:
             # TF32 pairs (float32 hi + lo) of everything the tensor cores read: y and y^T once, x / x^T / D / D D^T
             # per sweep.  All operands are K-major: x^T y is the NT product of x^T [k, n] and y^T [f, n].
+            # x^T and y^T are stored K-blocked ([n / 4096][rows][4096]) so that a slab of the sample-axis contraction
+            # is a compact piece of memory instead of one 128-byte line per row, 4 n bytes apart.
+            blk = ops.TF32_K_PER_SPLIT
             self.Yh, self.Yl = ops.split_tf32(y)
-            self.YTh, self.YTl = ops.split_transpose_tf32(y)
+            self.YTh, self.YTl = ops.split_transpose_tf32(y, block=blk)
             self.Xh, self.Xl = ops.split_tf32(X)
-            self.XTh, self.XTl = ops.empty_f32(k, n, dev), ops.empty_f32(k, n, dev)
+            self.XTh = ops.empty_f32_blocked(n, k, blk, dev, zero_tail=True)
+            self.XTl = ops.empty_f32_blocked(n, k, blk, dev, zero_tail=True)
             self.Dh, self.Dl = ops.empty_f32(k, f, dev), ops.empty_f32(k, f, dev)
             self.Gh, self.Gl = ops.empty_f32(k, k, dev), ops.empty_f32(k, k, dev)
             self.NEG32 = ops.empty_f32(n, k, dev)
-            self.ws32 = ops.gemm_nt_tf32x3_splitk_workspace(k, max(f, k), n, dev)
+            ws_bytes = max(ops._lib.lib().decomp_gemm_nt_tf32x3_splitk_workspace_bytes(k, max(f, k), n, blk),
+                           ops._lib.lib().decomp_gemm_nt_tf32x3_splitk_workspace_bytes(k, k, f, 512))
+            self.ws32 = ops.workspace(ws_bytes, dev)
             self.ws = None
         self.checks = tol > 0.0
         self.comm_events = None   # set to [] to collect (start, end) CUDA event pairs around each sweep's all-reduces
@@ -267,15 +273,15 @@ class MuSolver(object):
         if self.tf32:
             G, S = self.G, self.S
             # ---- x update (grads.py:108-111, f.dot(d.T) re-associated) on the tcgen05 tensor cores
-            ops.gemm_nt(D, D, E(ops.EPI_STORE, G), skip=latch)
-            ops.split_tf32(G, self.Gh, self.Gl)
             ops.split_tf32(D, self.Dh, self.Dl)
+            ops.gemm_nt_tf32x3_splitk(self.Dh, self.Dl, self.Dh, self.Dl, G, self.ws32, k_per_split=512, skip=latch)
+            ops.split_tf32(G, self.Gh, self.Gl)
             ops.gemm_nt_tf32x3(self.Xh, self.Xl, self.Gh, self.Gl, self.NEG32, skip=latch)
             ops.nmf_xupdate_tf32x3(self.Yh, self.Yl, self.Dh, self.Dl, X, self.NEG32, self.Xh, self.Xl, self.XTh,
                                    self.XTl, skip=latch)
             # ---- D update (grads.py:117-121): statistics over the sample axis, FP32 slabs of 4096 rows summed in FP64
-            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.YTh, self.YTl, POS, self.ws32, skip=latch)
-            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.XTh, self.XTl, S, self.ws32, skip=latch)
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.YTh, self.YTl, POS, self.ws32, skip=latch, K=self.n)
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.XTh, self.XTl, S, self.ws32, skip=latch, K=self.n)
             if group is not None:
                 t0 = self._comm_mark()
                 _allreduce2d(POS, group)

@@ -367,44 +367,65 @@ def gemm_nt_tf32x3(A_hi, A_lo, B_hi, B_lo, P, skip=None):
     return P
 
 
-def split_transpose_tf32(A, hiT=None, loT=None):
-    """TF32 pair of A^T: float32 [cols, rows] pieces of the float64 [rows, cols] matrix A."""
+TF32_K_PER_SPLIT = 4096   # FP32 accumulation length of the split-K statistics (rows per slab / K block)
+
+
+def empty_f32_blocked(rows, cols, block, device, zero_tail=False):
+    """K-blocked FP32 storage of a [cols, rows] (transposed) operand: [ceil(rows / block), cols, block]."""
+    nblk = (rows + block - 1) // block
+    t = torch.empty((nblk, cols, block), dtype=torch.float32, device=device)
+    if zero_tail and rows % block:
+        t[nblk - 1, :, rows % block:].zero_()
+    return t
+
+
+def split_transpose_tf32(A, hiT=None, loT=None, block=0):
+    """TF32 pair of A^T from the float64 [rows, cols] matrix A: float32 [cols, rows], or with ``block`` > 0 the
+    K-blocked [ceil(rows / block), cols, block] layout (tail of the last block zero-filled)."""
     rows, cols = A.shape
     if hiT is None:
-        hiT, loT = empty_f32(cols, rows, A.device), empty_f32(cols, rows, A.device)
-    rc = _lib.lib().decomp_split_transpose_tf32_f64(_p(A), ld(A), rows, cols, _p(hiT), _p(loT), ld(hiT),
-                                                    _lib.stream_ptr())
+        if block:
+            hiT, loT = empty_f32_blocked(rows, cols, block, A.device), empty_f32_blocked(rows, cols, block, A.device)
+        else:
+            hiT, loT = empty_f32(cols, rows, A.device), empty_f32(cols, rows, A.device)
+    rc = _lib.lib().decomp_split_transpose_tf32_f64(_p(A), ld(A), rows, cols, _p(hiT), _p(loT), 0 if block else ld(hiT),
+                                                    block, _lib.stream_ptr())
     _lib.check(rc, 'decomp_split_transpose_tf32_f64')
     _count(1)
     return hiT, loT
-
-
-TF32_K_PER_SPLIT = 4096   # FP32 accumulation length of the split-K statistics (rows per slab)
 
 
 def gemm_nt_tf32x3_splitk_workspace(M, N, K, device, k_per_split=TF32_K_PER_SPLIT):
     return workspace(_lib.lib().decomp_gemm_nt_tf32x3_splitk_workspace_bytes(M, N, K, k_per_split), device)
 
 
-def gemm_nt_tf32x3_splitk(A_hi, A_lo, B_hi, B_lo, out, ws, k_per_split=TF32_K_PER_SPLIT, skip=None):
-    """out (float64 [M, N]) = A . B^T in split TF32, the contraction cut into FP32-accumulated slabs summed in FP64."""
-    M, K = A_hi.shape
-    N = B_hi.shape[0]
-    rc = _lib.lib().decomp_gemm_nt_tf32x3_splitk_f64(_p(A_hi), _p(A_lo), ld(A_hi), _p(B_hi), _p(B_lo), ld(B_hi), M, N, K,
-                                                     k_per_split, _p(out), ld(out), _p(ws), ws.numel() * 8, _p(skip),
-                                                     _lib.stream_ptr())
+def gemm_nt_tf32x3_splitk(A_hi, A_lo, B_hi, B_lo, out, ws, k_per_split=TF32_K_PER_SPLIT, skip=None, K=None):
+    """out (float64 [M, N]) = A . B^T in split TF32, the contraction cut into FP32-accumulated slabs summed in FP64.
+    Operands: [rows, K] row-major, or (3-D tensors, ``K`` given) K-blocked [ceil(K / k_per_split), rows, k_per_split]."""
+    blocked = A_hi.dim() == 3
+    if blocked:
+        assert K is not None and A_hi.shape[2] == k_per_split == B_hi.shape[2]
+        M, N, lda, ldb = A_hi.shape[1], B_hi.shape[1], 0, 0
+    else:
+        M, K = A_hi.shape
+        N, lda, ldb = B_hi.shape[0], ld(A_hi), ld(B_hi)
+    rc = _lib.lib().decomp_gemm_nt_tf32x3_splitk_f64(_p(A_hi), _p(A_lo), lda, _p(B_hi), _p(B_lo), ldb, M, N, K,
+                                                     k_per_split, int(blocked), _p(out), ld(out), _p(ws), ws.numel() * 8,
+                                                     _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_gemm_nt_tf32x3_splitk_f64')
     _count(2)
     return out
 
 
 def nmf_xupdate_tf32x3(Y_hi, Y_lo, D_hi, D_lo, X, NEG, X_hi, X_lo, XT_hi, XT_lo, skip=None):
-    """X <- X * max(Y D^T, 0) / max(NEG, eps) with the GEMM on tcgen05 (TF32 split); see decomp_b200.h."""
+    """X <- X * max(Y D^T, 0) / max(NEG, eps) with the GEMM on tcgen05 (TF32 split); see decomp_b200.h.
+    XT_hi / XT_lo: [k, n] float32, or K-blocked [ceil(n / block), k, block]."""
     n, f = Y_hi.shape
     k = D_hi.shape[0]
+    xt_block = XT_hi.shape[2] if XT_hi.dim() == 3 else 0
     rc = _lib.lib().decomp_nmf_xupdate_tf32x3(_p(Y_hi), _p(Y_lo), ld(Y_hi), _p(D_hi), _p(D_lo), ld(D_hi), n, k, f, _p(X),
                                               ld(X), _p(NEG), ld(NEG), _p(X_hi), _p(X_lo), ld(X_hi), _p(XT_hi), _p(XT_lo),
-                                              ld(XT_hi), _p(skip), _lib.stream_ptr())
+                                              0 if xt_block else ld(XT_hi), xt_block, _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_nmf_xupdate_tf32x3')
     _count(1)
 

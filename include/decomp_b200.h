@@ -196,24 +196,29 @@ int decomp_gemm_nt_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, con
 /* out[M,N] (FP64) = A . B^T as above with the contraction cut into pieces of `k_per_split`: every piece is
  * accumulated in FP32 in tensor memory, written to an FP32 slab of `workspace`, and the slabs are summed in FP64 in a
  * fixed order (deterministic; the FP32 accumulation length is bounded by k_per_split whatever K is).
- * The sample-axis contractions x^T y, x^T x of grads.py:119-121 with A = x^T, B = y^T (both K-major). */
+ * The sample-axis contractions x^T y, x^T x of grads.py:119-121 with A = x^T, B = y^T (both K-major).
+ * k_blocked != 0: the operands are stored K-blocked, [ceil(K / k_per_split)][rows][k_per_split] FP32 with the tail of
+ * the last block zero-filled (lda / ldb unused): piece z then reads block z, rows k_per_split * 4 bytes apart instead
+ * of K * 4 -- the layout decomp_split_transpose_tf32_f64 and decomp_nmf_xupdate_tf32x3 produce for x^T and y^T. */
 size_t decomp_gemm_nt_tf32x3_splitk_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t k_per_split);
 int decomp_gemm_nt_tf32x3_splitk_f64(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi,
                                      const float* B_lo, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                                     int64_t k_per_split, double* out, int64_t ldo, void* workspace,
-                                     size_t workspace_bytes, const int32_t* skip_if, void* stream);
+                                     int64_t k_per_split, int32_t k_blocked, double* out, int64_t ldo,
+                                     void* workspace, size_t workspace_bytes, const int32_t* skip_if, void* stream);
 /* NMF x update (grads.py:77-84, 108-111) with y D^T on the tcgen05 tensor cores:
  *   X <- X * max(Y D^T, 0) / max(NEG, 1e-15)    Y_* [n,f], D_* [k,f] TF32 pairs, NEG = X (D D^T) [n,k] FP32,
  * evaluated in FP64 from the FP32 accumulator; the new X is written as FP64 [n,k], as its TF32 pair row-major
- * (X_hi, X_lo: next sweep's x (D D^T)) and transposed (XT_hi, XT_lo [k,n]: this sweep's x^T y, x^T x).
- * k % 32 == 0, k <= 256. */
+ * (X_hi, X_lo: next sweep's x (D D^T)) and transposed (XT_hi, XT_lo: this sweep's x^T y, x^T x) -- [k][ldxt] when
+ * xt_block == 0, else K-blocked [ceil(n / xt_block)][k][xt_block] (xt_block % 128 == 0; the caller zero-fills the
+ * tail of the last block once).  k % 32 == 0, k <= 256. */
 int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy, const float* D_hi, const float* D_lo,
                               int64_t ldd, int64_t n, int64_t k, int64_t f, double* X, int64_t ldx, const float* NEG,
                               int64_t ldneg, float* X_hi, float* X_lo, int64_t ldxh, float* XT_hi, float* XT_lo,
-                              int64_t ldxt, const int32_t* skip_if, void* stream);
-/* TF32 pair of A^T: hiT/loT [cols, rows] FP32 from A [rows, cols] FP64 (y^T, once per solve). */
+                              int64_t ldxt, int64_t xt_block, const int32_t* skip_if, void* stream);
+/* TF32 pair of A^T from A [rows, cols] FP64 (y^T, once per solve): hiT/loT [cols][ldt] FP32 when block == 0, else
+ * K-blocked [ceil(rows / block)][cols][block] with the tail of the last block zero-filled. */
 int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hiT, float* loT,
-                                    int64_t ldt, void* stream);
+                                    int64_t ldt, int64_t block, void* stream);
 /* The FP64 part of the iteration in one streaming pass (lasso.py:192-256, 405-414 with z = other + P):
  * uses epi->{out, other, prev, colvec (= step*alpha), colvec2, momentum, shrink, check, latch, scratch, latch_value};
  * w_next is written as the TF32 pair (w_hi, w_lo) the next decomp_gemm_nt_tf32x3 reads. */

@@ -196,3 +196,58 @@ def test_nmf_tf32x3_convergence_and_unsupported():
         nmf.solve(y2, D2.copy(), precision='tf32x3')                     # k = 3
     with pytest.raises(ValueError):
         nmf.solve(y, D0.copy(), precision='bf16')
+
+
+@pytest.mark.parametrize('M,N,K,block', [(64, 300, 1000, 256), (256, 520, 9000, 4096), (32, 32, 100, 128)])
+def test_tf32x3_splitk_k_blocked_layout(M, N, K, block):
+    """x^T / y^T stored K-blocked ([K / block][rows][block], zero-filled tail): split-K reads block z for piece z;
+    the blocked transpose and the blocked x-update output agree with the plain layouts."""
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d, empty2d
+    rng = np.random.RandomState(M + N + K)
+    At, Bt = rng.randn(K, M), rng.randn(K, N)                        # the operands arrive as [K, rows] (x, y)
+    Ah, Al = ops.split_transpose_tf32(to_device2d(At), block=block)
+    Bh, Bl = ops.split_transpose_tf32(to_device2d(Bt), block=block)
+    nblk = -(-K // block)
+    assert Ah.shape == (nblk, M, block) and Bh.shape == (nblk, N, block)
+    plain_h, _ = ops.split_transpose_tf32(to_device2d(At))
+    torch.cuda.synchronize()
+    full = Ah.permute(1, 0, 2).reshape(M, nblk * block)
+    assert torch.equal(full[:, :K], plain_h) and float(full[:, K:].abs().sum().item()) == 0.0
+    out = empty2d(M, N, False, torch.device('cuda', 0))
+    ws = ops.gemm_nt_tf32x3_splitk_workspace(M, N, K, 'cuda', block)
+    ops.gemm_nt_tf32x3_splitk(Ah, Al, Bh, Bl, out, ws, block, K=K)
+    torch.cuda.synchronize()
+    ref = At.T.dot(Bt)
+    err = np.max(np.abs(out.cpu().numpy() - ref)) / np.abs(At.T).dot(np.abs(Bt)).max()
+    assert err <= GEMM_RTOL, 'rel err %g' % err
+
+
+def test_nmf_xupdate_tf32x3_blocked_transpose():
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d
+    n, f, k, block = 1000, 96, 64, 256
+    rng = np.random.RandomState(7)
+    y, D, x = np.abs(rng.randn(n, f)), np.abs(rng.randn(k, f)), np.abs(rng.randn(n, k)) + 0.1
+    Yh, Yl = ops.split_tf32(to_device2d(y))
+    Dh, Dl = ops.split_tf32(to_device2d(D))
+    NEG = ops.empty_f32(n, k, 'cuda')
+    NEG.copy_(torch.from_numpy(x.dot(D.dot(D.T)).astype(np.float32)))
+    res = []
+    for blocked in (False, True):
+        X = to_device2d(x)
+        Xh, Xl = ops.empty_f32(n, k, 'cuda'), ops.empty_f32(n, k, 'cuda')
+        if blocked:
+            XTh = ops.empty_f32_blocked(n, k, block, 'cuda', zero_tail=True)
+            XTl = ops.empty_f32_blocked(n, k, block, 'cuda', zero_tail=True)
+        else:
+            XTh, XTl = ops.empty_f32(k, n, 'cuda'), ops.empty_f32(k, n, 'cuda')
+        ops.nmf_xupdate_tf32x3(Yh, Yl, Dh, Dl, X, NEG, Xh, Xl, XTh, XTl)
+        torch.cuda.synchronize()
+        res.append((X, XTh, XTl))
+    (X0, Th0, Tl0), (X1, Th1, Tl1) = res
+    assert torch.equal(X0, X1)
+    nblk = -(-n // block)
+    assert torch.equal(Th1.permute(1, 0, 2).reshape(k, nblk * block)[:, :n], Th0)
+    assert torch.equal(Tl1.permute(1, 0, 2).reshape(k, nblk * block)[:, :n], Tl0)
+    assert float(Th1.permute(1, 0, 2).reshape(k, nblk * block)[:, n:].abs().sum().item()) == 0.0
