@@ -625,9 +625,13 @@ def run_ours(args):
         y4 += 0.1 * crandn(n4, f4)
         D04 = Dt + 0.2 * crandn(k4, f4)
         m4 = (torch.rand((n4, f4), dtype=torch.float64, device=device, generator=g) > 0.1).double()
+        if world > 1:                        # row-sharded inputs: every rank keeps its block of the same data
+            lo4, hi4 = rank * n4 // world, (rank + 1) * n4 // world
+            y4, m4 = y4[lo4:hi4].contiguous(), m4[lo4:hi4].contiguous()
         kw4 = dict(tol=0.0, minibatch=mb, maxiter=2, lasso_method='fista', lasso_iter=10, mask=m4, random_seed=0,
                    group=group)
-        dictionary_learning.solve(y4[:2 * mb], D04, 0.1, **dict(kw4, mask=m4[:2 * mb]))        # warm-up
+        nw = min(2 * mb // world, y4.shape[0])
+        dictionary_learning.solve(y4[:nw], D04, 0.1, **dict(kw4, mask=m4[:nw], minibatch=mb // world))   # warm-up
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         before = ops.LAUNCHES
@@ -649,7 +653,7 @@ def run_ours(args):
                                  'statistics (2 k^2 f per row) + atom update; frac is per GPU'},
             'config': {'workload': 'dictionary learning block_cd, complex128 y %dx%d (one epoch of %d minibatch steps '
                                    'of %d rows; BASELINE.json configs[3] has n=200000), k=%d, 10 %% mask, fista x10, '
-                                   '%d GPU(s) sharing each minibatch' % (n4, f4, steps4, mb, k4, world)}}
+                                   'rows sharded over %d GPU(s), statistics reduce-scattered along f' % (n4, f4, steps4, mb, k4, world)}}
         del y4, D04, m4, Dt, D4, x4
         torch.cuda.empty_cache()
         # configs[0]: NMF-MU 1000 x 200, k = 20, 100 sweeps through nmf.solve with host arrays (launch-bound: CUDA graph)
@@ -766,10 +770,11 @@ def parity_check(np, torch, dist, world, rank, group, device):
             yy = yd * md if masked else yd
             kw = dict(tol=0.0, minibatch=63, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
                       mask=md if masked else None, random_seed=4)
-            it, D, x = dictionary_learning.solve(yy, Dd.copy(), 0.05, group=group, **kw)
+            kw_local = dict(kw, mask=shard(md) if masked else None)
+            it, D, x = dictionary_learning.solve(shard(yy), Dd.copy(), 0.05, group=group, **kw_local)
             it0, D_ref, x_ref = orc.dictionary_learning(yy, Dd.copy(), 0.05, **kw)
             name = 'dl_%s_%s' % ('c128' if cplx else 'f64', 'mask' if masked else 'nomask')
-            res[name] = {'it': it, 'it_oracle': it0, 'err_D': rel(D, D_ref), 'err_x': rel(x, x_ref)}
+            res[name] = {'it': it, 'it_oracle': it0, 'err_D': rel(D, D_ref), 'err_x': rel(x, shard(x_ref))}
             worst = max(worst, res[name]['err_D'], res[name]['err_x'], float(it != it0))
     if world > 1:
         t = torch.tensor([worst], dtype=torch.float64, device=device)

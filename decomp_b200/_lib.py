@@ -66,6 +66,7 @@ def _declare(lib):
     lib.decomp_normalize_rows_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_i32, c_i32, c_dp, c_i64, c_dp, c_i64,
                                               ctypes.c_double, c_dp, c_i32, c_dp, c_dp, c_dp, c_dp]
     lib.decomp_gather_rows_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_dp, c_i64, c_dp]
+    lib.decomp_scatter_rows_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_dp, c_i64, c_dp]
     lib.decomp_lasso_vectors_f64.argtypes = [c_dp, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_dp, c_dp,
                                              c_dp, c_dp]
     lib.decomp_axpby_f64.argtypes = [ctypes.c_double, c_dp, c_i64, ctypes.c_double, c_dp, c_i64, c_i64, c_i64, c_dp, c_i64,
@@ -98,7 +99,9 @@ def _declare(lib):
     lib.decomp_dl_atom_weighted_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_i32, c_i64, c_dp, c_i64, c_dp]
     lib.decomp_dl_pair_products_t_f64.argtypes = [c_dp, c_i64, c_i64, c_i32, c_dp, c_dp, c_i64, c_dp, c_i64, c_dp]
     lib.decomp_dl_scatter_stats_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_i32, c_dp, c_dp, c_i64, ctypes.c_double, c_dp,
-                                                c_dp]
+                                                c_i64, c_dp]
+    lib.decomp_dl_masked_update_phase_f64.argtypes = [c_i32, c_dp, c_i64, c_i64, c_dp, c_i64, c_dp, c_i64, c_i64, c_i64,
+                                                      c_i32, c_dp, c_dp, c_dp, c_dp]
     lib.decomp_dl_mirror_f64.argtypes = [c_dp, c_i64, c_i64, c_i32, c_dp]
     lib.decomp_dl_masked_update_f64.argtypes = [c_dp, c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i32, c_dp, c_i64,
                                                 c_dp, c_dp]
@@ -113,8 +116,8 @@ EXPORTS = (
     'decomp_last_error', 'decomp_abi_version', 'decomp_probe_dmma_tflops', 'decomp_gemm_nt_f64', 'decomp_gemm_tn_workspace_bytes',
     'decomp_gemm_tn_f64', 'decomp_make_rhs_f64', 'decomp_row_norms_f64', 'decomp_scale_f64', 'decomp_mask_mul_f64',
     'decomp_col_sums_workspace_bytes', 'decomp_col_sums_f64', 'decomp_row_sums_f64', 'decomp_gershgorin_step_f64', 'decomp_normalize_rows_f64',
-    'decomp_gather_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_axpby_f64', 'decomp_svrmu_update_f64', 'decomp_lasso_q_f64', 'decomp_scale_scalar_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',
-    'decomp_dl_sweep_workspace_bytes', 'decomp_dl_sweep_f64', 'decomp_dl_atom_weighted_f64', 'decomp_dl_pair_products_t_f64', 'decomp_dl_scatter_stats_f64', 'decomp_dl_mirror_f64', 'decomp_dl_masked_update_f64',
+    'decomp_gather_rows_f64', 'decomp_scatter_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_axpby_f64', 'decomp_svrmu_update_f64', 'decomp_lasso_q_f64', 'decomp_scale_scalar_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',
+    'decomp_dl_sweep_workspace_bytes', 'decomp_dl_sweep_f64', 'decomp_dl_atom_weighted_f64', 'decomp_dl_pair_products_t_f64', 'decomp_dl_scatter_stats_f64', 'decomp_dl_mirror_f64', 'decomp_dl_masked_update_f64', 'decomp_dl_masked_update_phase_f64',
     'decomp_split_tf32_f64', 'decomp_gemm_nt_tf32x3', 'decomp_proxq_apply_f64',
     'decomp_gemm_nt_tf32x3_splitk_workspace_bytes', 'decomp_gemm_nt_tf32x3_splitk_f64', 'decomp_nmf_xupdate_tf32x3',
     'decomp_split_transpose_tf32_f64',

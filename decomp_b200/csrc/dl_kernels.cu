@@ -159,11 +159,12 @@ __global__ void pair_products_t_kernel(const double* __restrict__ Xt, long long 
   }
 }
 
-// S[colA[c]][j][colB[c]] = beta * S[...] + P[j][c]
+// S[colA[c]][j][colB[c]] = beta * S[...] + P[j][c].  S is cut into channel slabs of `fs` channels, each a contiguous
+// [k][fs][k] tensor (fs = f: the plain [k][f][k] layout; fs = ceil(f / ranks): the input of a reduce-scatter along f)
 template <bool CPLX>
 __global__ void scatter_stats_kernel(const double* __restrict__ P, long long ldp, int f, int width,
                                      const int* __restrict__ colA, const int* __restrict__ colB, int k, double beta,
-                                     double* __restrict__ S) {
+                                     double* __restrict__ S, int fs) {
   constexpr int CW = CPLX ? 2 : 1;
   const long long total = (long long)f * width;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -171,7 +172,7 @@ __global__ void scatter_stats_kernel(const double* __restrict__ P, long long ldp
     const long long j = idx / width;
     const int c = (int)(idx % width);
     const int a = __ldg(colA + c), b = __ldg(colB + c);
-    double* dst = S + (((long long)a * f + j) * k + b) * CW;
+    double* dst = S + ((((j / fs) * k + a) * fs + j % fs) * k + b) * CW;
     const double* src = P + j * ldp + (long long)c * CW;
     if (CPLX) {
       const double2 o = *reinterpret_cast<const double2*>(dst);
@@ -317,6 +318,110 @@ __global__ void __launch_bounds__(256) dl_masked_update_kernel(const double* __r
   const double nrm = bc[0];
   for (int j = threadIdx.x; j < f; j += blockDim.x) {
     double* o = Dout + (long long)a * ldo + CW * j;
+    o[0] = o[0] / nrm;
+    if (CPLX) o[1] = o[1] / nrm;
+  }
+}
+
+// The masked Jacobi update on a channel slab (the statistics reduce-scattered along f over the ranks): the same
+// arithmetic as dl_masked_update_kernel in three phases, separated by the two [k] sums over all channels that the ranks
+// exchange (sum_j S[a][j][a] and |u_a|^2).  S: [k][fs][k] slab holding channels j0 .. j0 + fs; fv valid channels.
+// stats[a] = {Re saa, Im saa, |u|^2, -}.  Dt: the slab of D transposed, [fs][k].  One CTA per atom.
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_masked_phase1_kernel(const double* __restrict__ S, int fs, int fv, int j0,
+                                                               const double* __restrict__ T, long long ldt,
+                                                               const double* __restrict__ Dt, int k,
+                                                               double* __restrict__ out, double* __restrict__ stats) {
+  constexpr int CW = CPLX ? 2 : 1;
+  __shared__ double red[2][8];
+  const int a = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double* Sa = S + (long long)a * fs * k * CW;
+  double saa_r = 0.0, saa_i = 0.0;
+  for (int jj = w; jj < fv; jj += 8) {
+    const double* srow = Sa + (long long)jj * k * CW;
+    const double* drow = Dt + (long long)jj * k * CW;
+    double pr = 0.0, pi = 0.0;
+    for (int b = lane; b < k; b += 32) {
+      if (CPLX) {
+        const double2 sv = *reinterpret_cast<const double2*>(srow + 2 * b);
+        const double2 d = *reinterpret_cast<const double2*>(drow + 2 * b);
+        pr += sv.x * d.x - sv.y * d.y;
+        pi += sv.x * d.y + sv.y * d.x;
+      } else {
+        pr += srow[b] * drow[b];
+      }
+    }
+    pr = warp_sum_dl(pr);
+    if (CPLX) pi = warp_sum_dl(pi);
+    if (lane == 0) {
+      out[((long long)a * fs + jj) * CW] = T[(long long)a * ldt + CW * (j0 + jj)] - pr;
+      if (CPLX) out[((long long)a * fs + jj) * 2 + 1] = T[(long long)a * ldt + 2 * (j0 + jj) + 1] - pi;
+      saa_r += srow[CW * a] + kEpsDl;
+      if (CPLX) saa_i += srow[2 * a + 1];
+    }
+  }
+  if (lane == 0) {
+    red[0][w] = saa_r;
+    red[1][w] = saa_i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0, i = 0.0;
+    for (int t = 0; t < 8; ++t) {
+      r += red[0][t];
+      i += red[1][t];
+    }
+    stats[4 * a] = r;
+    stats[4 * a + 1] = i;
+    stats[4 * a + 2] = 0.0;
+    stats[4 * a + 3] = 0.0;
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_masked_phase2_kernel(int fs, int fv, int j0, const double* __restrict__ D,
+                                                               long long ldd, double* __restrict__ out,
+                                                               double* __restrict__ stats) {
+  constexpr int CW = CPLX ? 2 : 1;
+  __shared__ double red[8];
+  const int a = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double sr = stats[4 * a], si = stats[4 * a + 1];
+  double local = 0.0;
+  for (int jj = threadIdx.x; jj < fv; jj += blockDim.x) {
+    double* o = out + ((long long)a * fs + jj) * CW;
+    const double* d = D + (long long)a * ldd + CW * (j0 + jj);
+    if (CPLX) {
+      const double2 qv = cdiv(o[0], o[1], sr, si);
+      const double ur = qv.x + d[0], ui = qv.y + d[1];
+      o[0] = ur;
+      o[1] = ui;
+      local += ur * ur + ui * ui;
+    } else {
+      const double u = o[0] / sr + d[0];
+      o[0] = u;
+      local += u * u;
+    }
+  }
+  local = warp_sum_dl(local);
+  if (lane == 0) red[w] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r = 0.0;
+    for (int t = 0; t < 8; ++t) r += red[t];
+    stats[4 * a + 2] = r;
+  }
+}
+
+template <bool CPLX>
+__global__ void __launch_bounds__(256) dl_masked_phase3_kernel(int fs, int fv, double* __restrict__ out,
+                                                               const double* __restrict__ stats) {
+  constexpr int CW = CPLX ? 2 : 1;
+  const int a = blockIdx.x;
+  const double nrm = sqrt(fmax(stats[4 * a + 2], 1.0));
+  for (int jj = threadIdx.x; jj < fv; jj += blockDim.x) {
+    double* o = out + ((long long)a * fs + jj) * CW;
     o[0] = o[0] / nrm;
     if (CPLX) o[1] = o[1] / nrm;
   }
@@ -550,17 +655,18 @@ int decomp_dl_pair_products_t_f64(const double* Xt, int64_t ldx, int64_t rows, i
 
 int decomp_dl_scatter_stats_f64(const double* P, int64_t ldp, int64_t f, int64_t width, int32_t is_complex,
                                 const int32_t* colA, const int32_t* colB, int64_t k, double beta, double* S,
-                                void* stream) {
+                                int64_t slab_channels, void* stream) {
   if (f <= 0 || width <= 0) return DECOMP_OK;
+  const int fs = (int)(slab_channels > 0 ? slab_channels : f);
   long long b = (f * width + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (b > cap) b = cap;
   if (is_complex)
     scatter_stats_kernel<true><<<(unsigned)b, 256, 0, as_stream(stream)>>>(P, ldp, (int)f, (int)width, colA, colB, (int)k,
-                                                                           beta, S);
+                                                                           beta, S, fs);
   else
     scatter_stats_kernel<false><<<(unsigned)b, 256, 0, as_stream(stream)>>>(P, ldp, (int)f, (int)width, colA, colB, (int)k,
-                                                                            beta, S);
+                                                                            beta, S, fs);
   DCP_CHECK_LAUNCH("dl_scatter_stats");
   return DECOMP_OK;
 }
@@ -602,6 +708,52 @@ int decomp_dl_masked_update_f64(const double* S, const double* T, int64_t ldt, c
     dl_masked_update_kernel<false><<<(unsigned)k, 256, 0, st>>>(S, T, ldt, D, ldd, workspace, (int)k, (int)f, D_out, ldo);
   }
   DCP_CHECK_LAUNCH("dl_masked_update");
+  return DECOMP_OK;
+}
+
+int decomp_dl_masked_update_phase_f64(int32_t phase, const double* S_slab, int64_t slab_channels, int64_t j0,
+                                      const double* T, int64_t ldt, const double* D, int64_t ldd, int64_t k, int64_t f,
+                                      int32_t is_complex, double* D_slab_out, double* stats, double* workspace,
+                                      void* stream) {
+  if (k <= 0 || f <= 0 || slab_channels <= 0) return DECOMP_OK;
+  if (phase < 1 || phase > 3 || D_slab_out == nullptr || stats == nullptr || (phase == 1 && workspace == nullptr)) {
+    set_error("decomp_dl_masked_update_phase_f64: invalid argument");
+    return DECOMP_ERR_INVALID;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int fs = (int)slab_channels;
+  long long fvl = f - j0;
+  if (fvl > fs) fvl = fs;
+  if (fvl < 0) fvl = 0;
+  const int fv = (int)fvl, cw = is_complex ? 2 : 1;
+  if (phase == 1) {
+    if (fv > 0) {
+      long long b = ((long long)k * fv + 255) / 256;
+      const long long cap = (long long)num_sms() * 16;
+      if (b > cap) b = cap;
+      if (is_complex)
+        transpose_elems_kernel<true><<<(unsigned)b, 256, 0, st>>>(D + cw * j0, ldd, (int)k, fv, workspace);
+      else
+        transpose_elems_kernel<false><<<(unsigned)b, 256, 0, st>>>(D + cw * j0, ldd, (int)k, fv, workspace);
+    }
+    if (is_complex)
+      dl_masked_phase1_kernel<true><<<(unsigned)k, 256, 0, st>>>(S_slab, fs, fv, (int)j0, T, ldt, workspace, (int)k,
+                                                                  D_slab_out, stats);
+    else
+      dl_masked_phase1_kernel<false><<<(unsigned)k, 256, 0, st>>>(S_slab, fs, fv, (int)j0, T, ldt, workspace, (int)k,
+                                                                   D_slab_out, stats);
+  } else if (phase == 2) {
+    if (is_complex)
+      dl_masked_phase2_kernel<true><<<(unsigned)k, 256, 0, st>>>(fs, fv, (int)j0, D, ldd, D_slab_out, stats);
+    else
+      dl_masked_phase2_kernel<false><<<(unsigned)k, 256, 0, st>>>(fs, fv, (int)j0, D, ldd, D_slab_out, stats);
+  } else {
+    if (is_complex)
+      dl_masked_phase3_kernel<true><<<(unsigned)k, 256, 0, st>>>(fs, fv, D_slab_out, stats);
+    else
+      dl_masked_phase3_kernel<false><<<(unsigned)k, 256, 0, st>>>(fs, fv, D_slab_out, stats);
+  }
+  DCP_CHECK_LAUNCH("dl_masked_update_phase");
   return DECOMP_OK;
 }
 

@@ -369,6 +369,19 @@ __global__ void gather_rows_kernel(const double* __restrict__ in, long long ldi,
   }
 }
 
+// out[index[r]] = in[r]: the codes of a minibatch go back to their rows
+__global__ void scatter_rows_kernel(const double* __restrict__ in, long long ldi, const long long* __restrict__ index,
+                                    long long rows, long long cols, double* __restrict__ out, long long ldo) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const double* src = in + r * ldi;
+    double* dst = out + index[r] * ldo;
+    for (long long c = lane; c < cols; c += 32) dst[c] = src[c];
+  }
+}
+
 // ------------------------------------------------------------------------------------ Lasso prologue vectors
 // alpha_out[j] = (alpha / s[j]) * mult ; tol_out[j] = tol * s[j]      (lasso.py:129-130, 136-138)
 __global__ void lasso_vectors_kernel(const double* __restrict__ s, int k, double alpha, double tol, double mult,
@@ -670,6 +683,15 @@ int decomp_gather_rows_f64(const double* in, int64_t ldi, const int64_t* index, 
   gather_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(
       in, ldi, reinterpret_cast<const long long*>(index), rows, cols, out, ldo);
   DCP_CHECK_LAUNCH("gather_rows");
+  return DECOMP_OK;
+}
+
+int decomp_scatter_rows_f64(const double* in, int64_t ldi, const int64_t* index, int64_t rows, int64_t cols, double* out,
+                            int64_t ldo, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  scatter_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, as_stream(stream)>>>(
+      in, ldi, reinterpret_cast<const long long*>(index), rows, cols, out, ldo);
+  DCP_CHECK_LAUNCH("scatter_rows");
   return DECOMP_OK;
 }
 

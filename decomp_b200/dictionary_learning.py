@@ -33,10 +33,12 @@ def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method=
           lasso_iter=10, lasso_tol=1.0e-5, mask=None, random_seed=None, group=None):
     """Learn the dictionary ``D`` and the codes ``x``; see the module docstring.
 
-    ``group`` (not in the reference): optional ``torch.distributed`` process group.  The algorithm is sequential
-    across minibatches, so the ranks share each minibatch: every rank passes the SAME arrays and seed, codes its
-    own block of rows of each minibatch, the new codes are exchanged, the sufficient statistics are all-reduced and
-    the atom update is replicated.  Every rank returns the same ``(it, D, x)``.
+    ``group`` (not in the reference): optional ``torch.distributed`` process group.  Every rank passes its own
+    contiguous block of rows of ``y`` / ``x`` / ``mask`` (rank order = row order), the same ``D`` and the same seed.
+    The algorithm is sequential across minibatches, so the ranks share each minibatch: a rank codes the rows of the
+    minibatch it owns; the statistics are all-reduced (masked: reduce-scattered along the feature axis, each rank
+    updating its own channels, then the new dictionary is all-gathered).  Every rank returns the same ``it`` and
+    ``D`` and its own rows of ``x``; the results are those of the single-process run on the concatenated rows.
 
     ``lasso_method`` must be one of the device rules ('ista', 'fista', 'acc_ista', optionally '_pos'); the
     reference's default 'cd' is a sequential reference-purpose method outside the hot path.
@@ -105,53 +107,73 @@ def _pair_chunks(k, cap, device):
     return out
 
 
-class _ShuffledRows(object):
-    """Device rows under the reference's cumulative shuffle (utils/data.py:124-156): two owned buffers are
-    used alternately as gather targets; the caller's array is only ever read."""
+def _row_layout(n_local, group, device):
+    """(total rows, first global row of this rank, ranks, rank) for row-sharded inputs."""
+    if group is None:
+        return n_local, 0, 1, 0
+    dist = torch.distributed
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = n_local
+    dist.all_reduce(counts, group=group)
+    counts = counts.cpu().numpy()
+    return int(counts.sum()), int(counts[:rank].sum()), world, rank
 
-    def __init__(self, array, cplx):
-        self.cur = array
-        self.cplx = cplx
-        self.spare = [None, None]
-        self.turn = 0
 
-    def shuffle(self, index_dev):
-        n, c = self.cur.shape
-        if self.spare[self.turn] is None:
-            self.spare[self.turn] = empty2d(n, c, self.cplx, self.cur.device)
-        dst = self.spare[self.turn]
-        ops.gather_rows(rview(self.cur), index_dev, rview(dst))
-        self.cur = dst
-        self.turn ^= 1
-
-    def rows(self, r, step):
-        return self.cur[r * step:(r + 1) * step]
+def _epoch_selection(order, steps, minibatch, row0, n_loc):
+    """The rows of each minibatch of one epoch that live on this rank (global rows row0 .. row0 + n_loc), as local row
+    numbers in minibatch order: (concatenated int64 selections, bounds with bounds[r] .. bounds[r+1] = minibatch r).
+    Over the ranks the selections of a minibatch partition ``order[r*mb:(r+1)*mb]``."""
+    sel, bounds = [], [0]
+    for r in range(steps):
+        rows = order[r * minibatch:(r + 1) * minibatch]
+        rows = rows[(rows >= row0) & (rows < row0 + n_loc)] - row0
+        sel.append(rows)
+        bounds.append(bounds[-1] + rows.size)
+    cat = np.concatenate(sel).astype(np.int64) if sel else np.zeros(0, dtype=np.int64)
+    return cat, bounds
 
 
 def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, lasso_iter, lasso_tol, mask, rng,
                     group=None):
-    """``solve_cd`` / ``solve_cd_mask`` on device tensors. Returns ``(it, D, x)`` with x in the caller's row order."""
+    """``solve_cd`` / ``solve_cd_mask`` on device tensors. Returns ``(it, D, x)`` with x in the caller's row order.
+
+    The data never moves: ``order`` (host) is the reference's cumulative permutation (utils/data.py:147-156,
+    dictionary_learning.py:131-133) and minibatch r is the rows ``order[r*mb:(r+1)*mb]``, gathered into a work buffer,
+    coded, and scattered back.  With a ``group`` every rank holds a contiguous block of rows and takes, from each
+    minibatch, the rows it owns (their codes are row-local given D, lasso.py:244-246); what crosses the ranks per
+    minibatch is: unmasked, the all-reduce of x^H x [k,k] and x^H y [k,f], the atom sweep being
+    replicated; masked, the reduce-scatter of the [k,f,k] statistic ALONG f -- the update is channel-local
+    (dictionary_learning.py:218), every rank keeps and updates f / ranks channels -- two [k] all-reduces
+    (sum_j S[a][j][a], |u_a|^2) and the all-gather of the new dictionary."""
     dev = y.device
-    n, f = y.shape
+    n_loc, f = y.shape
     k = D0.shape[0]
     cplx = y.is_complex()
     cw = 2 if cplx else 1
     masked = mask is not None
     stat_combine = 3 if cplx else 1
+    dist = torch.distributed if group is not None else None
+    n, row0, world, rank = _row_layout(n_loc, group, dev)
+    if n < minibatch:
+        raise ValueError('Minibatch size should be smaller than the total size. Given {} < {}'.format(n, minibatch))
+    sharded = world > 1
 
-    ys, xs = _ShuffledRows(y, cplx), _ShuffledRows(x, x.is_complex())
-    ms = _ShuffledRows(mask, False) if masked else None
+    order = np.arange(n)
     index = np.arange(n)
-    restore = np.arange(n)
-
     D = empty2d(k, f, cplx, dev)
     Dn = empty2d(k, f, cplx, dev)
     ops.normalize_rows(rview(D0), rview(D), cplx, True)                       # :125, :182
     T = zeros2d(k, f, cplx, dev)
+    # work buffers of one minibatch (this rank's rows of it: at most all of them)
+    Ymb, Xmb = empty2d(minibatch, f, cplx, dev), empty2d(minibatch, k, x.is_complex(), dev)
+    Mmb = empty2d(minibatch, f, False, dev) if masked else None
     if masked:
-        S = torch.zeros((k, f, k * cw), dtype=torch.float64, device=dev)      # [k][f][k] (interleaved complex)
+        fs = -(-f // world)                       # channels per rank (the last ranks may own fewer, or none)
+        j0 = rank * fs
+        S = torch.zeros((k, fs, k * cw), dtype=torch.float64, device=dev)     # this rank's channel slab [k][fs][k]
         YM = empty2d(minibatch, f, cplx, dev)
-        Dt_ws = torch.empty(f * k * cw, dtype=torch.float64, device=dev)
+        Dt_ws = torch.empty(fs * k * cw, dtype=torch.float64, device=dev)
         # the (atom a, b >= a) pairs of the Hermitian half of S, packed into wide GEMMs
         chunks = _pair_chunks(k, _pair_cols(f, cw, dev), dev)
         widest = max(c[0].numel() for c in chunks)
@@ -160,97 +182,115 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
         Mt = empty2d(f, minibatch, False, dev)
         Ptmp = empty2d(f, widest, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, f * cw, minibatch)], dev)
+        if sharded:
+            S_part = torch.zeros((world, k, fs, k * cw), dtype=torch.float64, device=dev)   # reduce-scatter input
+            S_red = torch.empty((k, fs, k * cw), dtype=torch.float64, device=dev)
+            stats = torch.zeros(k * 4, dtype=torch.float64, device=dev)
+            D_slab = torch.zeros((k, fs * cw), dtype=torch.float64, device=dev)
+            D_all = torch.empty((world, k, fs * cw), dtype=torch.float64, device=dev)
     else:
         S = zeros2d(k, k, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, k * cw, minibatch), (k * cw, f * cw, minibatch)], dev)
         sweep_ws = ops.dl_sweep_workspace(k, f, cplx, dev)
-    dist = torch.distributed if group is not None else None
-    if dist is not None:
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        lo, hi = rank * minibatch // world, (rank + 1) * minibatch // world     # this rank's rows of a minibatch
-        S_part = torch.zeros_like(S)            # local statistics before the all-reduce
+    if sharded:
+        S_loc = zeros2d(k, k, cplx, dev) if not masked else None    # local statistics before the all-reduce
         T_part = zeros2d(k, f, cplx, dev)
-    else:
-        lo, hi = 0, minibatch
     result = torch.zeros(2, dtype=torch.float64, device=dev)
-    scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(2, dtype=torch.int32, device=dev)
     checks = tol > 0.0
-
-    def restored_x():
-        order = torch.from_numpy(np.argsort(restore)).to(dev)
-        out = empty2d(n, k, xs.cplx, dev)
-        ops.gather_rows(rview(xs.cur), order, rview(out))
-        return out
+    steps = n // minibatch                                                      # tail rows are skipped
 
     count = 0
     for it in range(1, maxiter):
         rng.shuffle(index)                                                     # :131-133 (cumulative)
-        index_dev = torch.from_numpy(index).to(dev)
-        ys.shuffle(index_dev)
-        xs.shuffle(index_dev)
-        if masked:
-            ms.shuffle(index_dev)
-        restore = restore[index]
+        order = order[index]
+        # this rank's rows of every minibatch of the epoch, as local row numbers: one upload per epoch
+        sel, bounds = _epoch_selection(order, steps, minibatch, row0, n_loc)
+        sel_dev = torch.from_numpy(sel).to(dev) if sel.size else None
         try:
-            for r in range(n // minibatch):                                    # tail rows are skipped
-                y_mb, x_mb = ys.rows(r, minibatch), xs.rows(r, minibatch)
-                m_mb = ms.rows(r, minibatch) if masked else None
-                if dist is None:
-                    lasso_device(y_mb, D, alpha, x_mb, lasso_tol, lasso_iter, rule, positive, m_mb, out=x_mb)
-                else:
-                    # code this rank's rows, then make the whole minibatch's codes known everywhere
-                    x_own = x_mb[lo:hi]
-                    lasso_device(y_mb[lo:hi], D, alpha, x_own, lasso_tol, lasso_iter, rule, positive,
-                                 m_mb[lo:hi] if masked else None, out=x_own, group=group)
-                    x_mb[:lo].zero_()
-                    x_mb[hi:].zero_()
-                    _allreduce(x_mb, group)
+            for r in range(steps):
+                m = bounds[r + 1] - bounds[r]
+                rows_dev = sel_dev[bounds[r]:bounds[r + 1]] if m else None
+                y_mb, x_mb = Ymb[:m], Xmb[:m]
+                m_mb = Mmb[:m] if masked else None
+                if m:
+                    ops.gather_rows(rview(y), rows_dev, rview(y_mb))
+                    ops.gather_rows(rview(x), rows_dev, rview(x_mb))
+                    if masked:
+                        ops.gather_rows(mask, rows_dev, m_mb)
+                lasso_device(y_mb, D, alpha, x_mb, lasso_tol, lasso_iter, rule, positive, m_mb, out=x_mb, group=group)
+                if m:
+                    ops.scatter_rows(rview(x_mb), rows_dev, rview(x))
 
                 theta = count * minibatch + 1.0                                # equation (11), :143-144
                 beta = (theta - minibatch) / theta
-                # statistics over this rank's rows (all rows without a group); with a group the partial sums are
-                # all-reduced and folded in as  S <- beta S + sum_ranks(partial)
-                xr = rview(x_mb[lo:hi])
-                rows = hi - lo
-                S_dst, T_dst = (S, T) if dist is None else (S_part, T_part)
-                comb = stat_combine if dist is None else stat_combine - 1       # accumulate / overwrite
+                xr = rview(x_mb)
                 if not masked:
-                    ops.gemm_tn(xr, xr, rview(S_dst), combine=comb, beta=beta, workspace=ws)           # :151
-                    ops.gemm_tn(xr, rview(y_mb[lo:hi]), rview(T_dst), combine=comb, beta=beta, workspace=ws)
-                else:
-                    # S[a][j][b] = sum_i conj(x_ia) x_ib m_ij is Hermitian in (a, b): accumulate b >= a, mirror the rest
-                    # as NT GEMMs  mask^T [f, rows] . Wt [pairs, rows]^T  (the NT kernel is the faster one)
-                    ops.make_rhs(xr, False, False, out=Xt[:, :rows])
-                    ops.make_rhs(m_mb[lo:hi], False, False, out=Mt[:, :rows])
-                    for colA, colB in chunks:                                                          # :210-213
-                        wd = colA.numel()
-                        Wc, Pc = Wt[:wd * cw, :rows], rview(Ptmp[:, :wd])
-                        ops.dl_pair_products_t(Xt[:, :rows], cplx, colA, colB, Wc)
-                        ops.gemm_nt(Mt[:, :rows], Wc, ops.epilogue(ops.EPI_STORE, Pc))
-                        ops.dl_scatter_stats(Pc, cplx, colA, colB, k, beta if dist is None else 0.0, S_dst)
-                    ops.dl_mirror(S_dst, k, f, cplx)
-                    ops.mask_mul(rview(y_mb[lo:hi]), m_mb[lo:hi], rview(YM[:rows]), cwidth=cw)
-                    ops.gemm_tn(xr, rview(YM[:rows]), rview(T_dst), combine=comb, beta=beta, workspace=ws)  # :214
-                if dist is not None:
-                    _allreduce(S_part, group)
-                    _allreduce(T_part, group)
-                    S2, P2 = (S.view(k * f, k * cw), S_part.view(k * f, k * cw)) if masked else (rview(S), rview(S_part))
-                    ops.axpby(beta, S2, 1.0, P2, S2)
-                    ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
-                if not masked:
+                    # ---- statistics (:147-152); sharded: local sums, all-reduced, folded in as S <- beta S + sum
+                    S_dst, T_dst = (S, T) if not sharded else (S_loc, T_part)
+                    comb = stat_combine if not sharded else stat_combine - 1    # accumulate / overwrite
+                    if m:
+                        ops.gemm_tn(xr, xr, rview(S_dst), combine=comb, beta=beta, workspace=ws)
+                        ops.gemm_tn(xr, rview(y_mb), rview(T_dst), combine=comb, beta=beta, workspace=ws)
+                    elif sharded:
+                        S_dst.zero_()
+                        T_dst.zero_()
+                    if sharded:
+                        _allreduce(S_loc, group)
+                        _allreduce(T_part, group)
+                        ops.axpby(beta, rview(S), 1.0, rview(S_loc), rview(S))
+                        ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
                     Dn.copy_(D)
-                    ops.dl_sweep(rview(S), rview(T), rview(Dn), cplx, ws=sweep_ws)                            # :154-159
+                    ops.dl_sweep(rview(S), rview(T), rview(Dn), cplx, ws=sweep_ws)                     # :154-159
                 else:
-                    ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)                # :216-222
+                    # ---- S[a][j][b] = sum_i conj(x_ia) x_ib m_ij (:210-213) is Hermitian in (a, b): accumulate b >= a as
+                    # NT GEMMs  mask^T [f, rows] . Wt [pairs, rows]^T, mirror the rest.  Sharded: every rank forms its
+                    # rows' contribution to ALL channels, laid out as one slab per destination rank
+                    S_dst = S if not sharded else S_part
+                    T_dst = T if not sharded else T_part
+                    comb = stat_combine if not sharded else stat_combine - 1
+                    if m:
+                        ops.make_rhs(xr, False, False, out=Xt[:, :m])
+                        ops.make_rhs(m_mb, False, False, out=Mt[:, :m])
+                        for colA, colB in chunks:
+                            wd = colA.numel()
+                            Wc, Pc = Wt[:wd * cw, :m], rview(Ptmp[:, :wd])
+                            ops.dl_pair_products_t(Xt[:, :m], cplx, colA, colB, Wc)
+                            ops.gemm_nt(Mt[:, :m], Wc, ops.epilogue(ops.EPI_STORE, Pc))
+                            ops.dl_scatter_stats(Pc, cplx, colA, colB, k, 0.0 if sharded else beta, S_dst,
+                                                 slab_channels=fs if sharded else 0)
+                        ops.mask_mul(rview(y_mb), m_mb, rview(YM[:m]), cwidth=cw)
+                        ops.gemm_tn(xr, rview(YM[:m]), rview(T_dst), combine=comb, beta=beta, workspace=ws)   # :214
+                    elif sharded:
+                        S_part.zero_()
+                        T_part.zero_()
+                    if not sharded:
+                        ops.dl_mirror(S, k, f, cplx)
+                        ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)            # :216-222
+                    else:
+                        dist.reduce_scatter_tensor(S_red, S_part, group=group)                          # along f
+                        S2, R2 = S.view(k * fs, k * cw), S_red.view(k * fs, k * cw)
+                        ops.axpby(beta, S2, 1.0, R2, S2)
+                        ops.dl_mirror(S, k, fs, cplx)
+                        _allreduce(T_part, group)
+                        ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
+                        # channel-local Jacobi update of this rank's slab, two [k] sums over all channels exchanged
+                        ops.dl_masked_update_phase(1, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
+                        dist.all_reduce(stats, group=group)
+                        ops.dl_masked_update_phase(2, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
+                        dist.all_reduce(stats, group=group)
+                        ops.dl_masked_update_phase(3, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
+                        dist.all_gather_into_tensor(D_all, D_slab, group=group)
+                        rview(Dn).copy_(D_all.permute(1, 0, 2).reshape(k, world * fs * cw)[:, :f * cw])
                 if checks:
                     ops.max_abs_diff(rview(D), rview(Dn), cplx, result, scratch)
                     if float(result[1].item()) < tol:                                                  # :161, :224
-                        return it, Dn, restored_x()
+                        return it, Dn, x
                 D, Dn = Dn, D
                 count += 1
         except KeyboardInterrupt:
-            return it, D, restored_x()
-    return maxiter, D, restored_x()
+            return it, D, x
+    return maxiter, D, x
 
 
 def _allreduce(t, group):

@@ -485,8 +485,7 @@ class LassoSolver(object):
                                scratch=self.scratch, latch_value=i + 1)
             ops.gemm_nt_tf32x3(self.W_hi, self.W_lo, self.Q_hi, self.Q_lo, self.P, skip=latch)
             ops.proxq_apply(self.P, epi, self.W_hi, self.W_lo, skip=latch)
-            if check and self.group is not None:
-                torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            self._exchange_latch(check, i + 1)
             return
         wi = self.wi
         self.wi = 1 - wi
@@ -496,8 +495,7 @@ class LassoSolver(object):
                                flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, momentum=self.mom[i], shrink=self.shrink,
                                check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
             ops.gemm_nt(rview(W[wi]), self.Q_rhs, epi, skip=latch)
-            if check and self.group is not None:
-                torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            self._exchange_latch(check, i + 1)
             return
         epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, out2=rview(W[1 - wi]), x=rview(W[wi]),
                            other=rview(self.yAh), prev=rview(self.X),
@@ -507,9 +505,16 @@ class LassoSolver(object):
         ops.gemm_nt(rview(W[wi]), self.A_rhs,
                     ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
         ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
+        self._exchange_latch(check, i + 1)
+
+    def _exchange_latch(self, check, value):
+        """The latch fires only if every shard passed the test (reference: one max over the whole batch, lasso.py:293):
+        MIN over the ranks.  A rank without rows (a minibatch of dictionary learning may leave it none) launches no
+        kernel that could vote, so it passes by setting its latch itself."""
         if check and self.group is not None:
-            # the latch fires only if every shard passed the test (reference: one max over the whole batch)
-            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            if self.B == 0:
+                self.latch.fill_(value)
+            torch.distributed.all_reduce(self.latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
 
     def _launch_resident(self, i0, i1):
         """Iterations i0 <= i < i1 in one launch; the convergence test may only sit on the last one."""
@@ -525,8 +530,7 @@ class LassoSolver(object):
                            flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD, shrink=self.shrink, check=check, latch=latch,
                            scratch=self.scratch, latch_value=i1)
         ops.lasso_resident(Q, self.B, epi, self.mom[i0:i1], skip=latch)
-        if check and self.group is not None:
-            torch.distributed.all_reduce(latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+        self._exchange_latch(check, i1)
 
     def _poll(self, last_done):
         """Host read of the latch, on the same schedule in both loops: right after checking iteration ``last_done``

@@ -204,6 +204,15 @@ def gather_rows(src, index, out):
     return out
 
 
+def scatter_rows(src, index, out):
+    """out[index[r]] = src[r]."""
+    rows, cols = src.shape
+    rc = _lib.lib().decomp_scatter_rows_f64(_p(src), ld(src), _p(index), rows, cols, _p(out), ld(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_scatter_rows_f64')
+    _count(1)
+    return out
+
+
 def dl_sweep_workspace(k, f, is_complex, device):
     return workspace(_lib.lib().decomp_dl_sweep_workspace_bytes(k, f, int(is_complex)), device)
 
@@ -240,11 +249,12 @@ def dl_pair_products_t(Xt, is_complex, colA, colB, Wt):
     return Wt
 
 
-def dl_scatter_stats(P, is_complex, colA, colB, k, beta, S):
-    """S[colA[c], j, colB[c]] = beta * S[...] + P[j, c]  (S: contiguous [k, f, k*cw] doubles)."""
+def dl_scatter_stats(P, is_complex, colA, colB, k, beta, S, slab_channels=0):
+    """S[colA[c], j, colB[c]] = beta * S[...] + P[j, c]  (S: contiguous [k, f, k*cw] doubles, or channel slabs
+    [f / slab_channels, k, slab_channels, k*cw])."""
     f, width = P.shape[0], colA.numel()
     rc = _lib.lib().decomp_dl_scatter_stats_f64(_p(P), ld(P), f, width, int(is_complex), _p(colA), _p(colB), k,
-                                                float(beta), _p(S), _lib.stream_ptr())
+                                                float(beta), _p(S), int(slab_channels), _lib.stream_ptr())
     _lib.check(rc, 'decomp_dl_scatter_stats_f64')
     _count(1)
     return S
@@ -266,6 +276,18 @@ def dl_masked_update(S, T, D, D_out, is_complex, workspace):
     _lib.check(rc, 'decomp_dl_masked_update_f64')
     _count(2)
     return D_out
+
+
+def dl_masked_update_phase(phase, S_slab, j0, T, D, is_complex, D_slab_out, stats, workspace):
+    """One phase (1, 2, 3) of the masked Jacobi update on the channel slab S_slab [k, fs, k*cw]; see decomp_b200.h."""
+    cw = 2 if is_complex else 1
+    k, f = D.shape[0], D.shape[1] // cw
+    fs = S_slab.shape[1]
+    rc = _lib.lib().decomp_dl_masked_update_phase_f64(int(phase), _p(S_slab), fs, int(j0), _p(T), ld(T), _p(D), ld(D), k, f,
+                                                      int(is_complex), _p(D_slab_out), _p(stats), _p(workspace),
+                                                      _lib.stream_ptr())
+    _lib.check(rc, 'decomp_dl_masked_update_phase_f64')
+    _count(2 if phase == 1 else 1)
 
 
 def lasso_vectors(s, alpha, tol, mult=1.0, mult_dev=None):

@@ -154,6 +154,9 @@ int decomp_normalize_rows_f64(const double* D_in, int64_t ldi, int64_t rows, int
 /* out[r] = in[index[r]] row gather (MinibatchData.shuffle / .array, utils/data.py:147-156) */
 int decomp_gather_rows_f64(const double* in, int64_t ldi, const int64_t* index, int64_t rows, int64_t cols,
                            double* out, int64_t ldo, void* stream);
+/* out[index[r]] = in[r]: the codes of a minibatch back into their rows (x[perm[...]] = x_minibatch, data.py:124-156) */
+int decomp_scatter_rows_f64(const double* in, int64_t ldi, const int64_t* index, int64_t rows, int64_t cols,
+                            double* out, int64_t ldo, void* stream);
 
 /* Lasso prologue vectors: alpha_out[j] = (alpha / s[j]) * mult, tol_out[j] = tol * s[j]; `mult` is read from the
  * device scalar mult_dev when that is non-NULL (sum of a 1-D mask)   (lasso.py:129-130, 136-138) */
@@ -260,9 +263,11 @@ int decomp_dl_atom_weighted_f64(const double* X, int64_t ldx, int64_t rows, int6
  * S[colA[c]][j][colB[c]] = beta * S[..] + P[j][c].  colA / colB: device int32 vectors. */
 int decomp_dl_pair_products_t_f64(const double* Xt, int64_t ldx, int64_t rows, int32_t is_complex, const int32_t* colA,
                                   const int32_t* colB, int64_t width, double* Wt, int64_t ldw, void* stream);
+/* slab_channels: S is stored as channel slabs [f / slab_channels][k][slab_channels][k*cw] (0 or f: the plain
+ * [k][f][k*cw] tensor); with slab_channels = ceil(f / ranks) it is the send buffer of a reduce-scatter along f. */
 int decomp_dl_scatter_stats_f64(const double* P, int64_t ldp, int64_t f, int64_t width, int32_t is_complex,
                                 const int32_t* colA, const int32_t* colB, int64_t k, double beta, double* S,
-                                void* stream);
+                                int64_t slab_channels, void* stream);
 /* S[b][j][a] = conj(S[a][j][b]) for b > a on the [k][f][k*cw] tensor: the statistics of dictionary_learning.py:210-213
  * are Hermitian in (a, b), so the GEMMs accumulate b >= a only (half the flops) and this fills in the rest. */
 int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, void* stream);
@@ -272,6 +277,17 @@ int decomp_dl_mirror_f64(double* S, int64_t k, int64_t f, int32_t is_complex, vo
 int decomp_dl_masked_update_f64(const double* S, const double* T, int64_t ldt, const double* D, int64_t ldd,
                                 int64_t k, int64_t f, int32_t is_complex, double* D_out, int64_t ldo,
                                 double* workspace, void* stream);
+
+/* The same update on ONE channel slab (channels j0 .. j0 + slab_channels of S, [k][slab_channels][k*cw]), for statistics
+ * reduce-scattered along f over several GPUs (the update is channel-local, dictionary_learning.py:218), in three phases
+ * separated by the sums over all channels the ranks all-reduce: phase 1 writes T[a] - S_a D into D_slab_out
+ * [k][slab_channels*cw] and the partial sum_j S[a][j][a] into stats[4a .. 4a+1]; phase 2 (after the all-reduce of
+ * stats) forms u and its partial |u|^2 in stats[4a+2]; phase 3 (after the second all-reduce) divides by
+ * sqrt(max(|u|^2, 1)).  `workspace`: slab_channels * k * cw doubles (phase 1). */
+int decomp_dl_masked_update_phase_f64(int32_t phase, const double* S_slab, int64_t slab_channels, int64_t j0,
+                                      const double* T, int64_t ldt, const double* D, int64_t ldd, int64_t k, int64_t f,
+                                      int32_t is_complex, double* D_slab_out, double* stats, double* workspace,
+                                      void* stream);
 
 /* ---- host-side staging of pageable inputs -------------------------------------------------- */
 /* dst_device[0:bytes] = src_host[0:bytes] for an ordinary (pageable) host array, the kind of array the reference's

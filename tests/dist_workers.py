@@ -74,7 +74,9 @@ def cpu_host_logic(rank, world, port, out):
 
 
 def gpu_sharded_dictionary_learning(rank, world, port, out):
-    """Dictionary learning with each minibatch's rows shared between the ranks (replicated inputs) vs the oracle."""
+    """Dictionary learning on row-sharded inputs (each rank holds a block of rows; masked: statistics reduce-scattered
+    along f) vs the single-process oracle on the concatenated rows.  minibatch 20 of 230 rows over 2 ranks: some
+    minibatches leave a rank few rows; f = 33 is not a multiple of the rank count (ragged channel slabs)."""
     _init(rank, world, port, 'nccl')
     from decomp_b200 import dictionary_learning
     import golden_cases as gc
@@ -87,14 +89,43 @@ def gpu_sharded_dictionary_learning(rank, world, port, out):
     for cplx in (False, True):
         y, D0, mask = gc._dl_data(230, 33, 12, 9, cplx)
         for masked in (False, True):
-            yy = y * mask if masked else y
-            kw = dict(tol=0.0, minibatch=63, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
-                      mask=mask if masked else None, random_seed=4)
-            it, D, x = dictionary_learning.solve(yy, D0.copy(), 0.05, group=dist.group.WORLD, **kw)
-            it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, **kw)
-            res['dl_%s_%s' % ('c' if cplx else 'f', 'mask' if masked else 'nomask')] = (it, it0, rel(D, D_ref),
-                                                                                        rel(x, x_ref))
+            for mb, tol in ((63, 0.0), (20, 1e-3)):
+                yy = y * mask if masked else y
+                kw = dict(tol=tol, minibatch=mb, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
+                          random_seed=4)
+                it, D, x = dictionary_learning.solve(shard(yy, rank, world), D0.copy(), 0.05, group=dist.group.WORLD,
+                                                     mask=shard(mask, rank, world) if masked else None, **kw)
+                it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, mask=mask if masked else None, **kw)
+                res['dl_%s_%s_mb%d' % ('c' if cplx else 'f', 'mask' if masked else 'nomask', mb)] = (
+                    it, it0, rel(D, D_ref), rel(x, shard(x_ref, rank, world)))
     out[rank] = res
+    dist.destroy_process_group()
+
+
+def cpu_dl_row_sharding(rank, world, port, out):
+    """Host logic of the row-sharded dictionary learning over gloo: the row layout exchanged between the ranks and the
+    per-epoch selections (every minibatch is partitioned over the ranks, order preserved)."""
+    _init(rank, world, port, 'gloo')
+    from decomp_b200 import dictionary_learning as dl
+    n_loc = 7 if rank == 0 else 5
+    n, row0, w, r = dl._row_layout(n_loc, dist.group.WORLD, torch.device('cpu'))
+    rng = np.random.RandomState(3)
+    order = np.arange(n)
+    index = np.arange(n)
+    rng.shuffle(index)
+    order = order[index]
+    mb, steps = 5, n // 5
+    sel, bounds = dl._epoch_selection(order, steps, mb, row0, n_loc)
+    mine = [(sel[bounds[i]:bounds[i + 1]] + row0).tolist() for i in range(steps)]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok = (n, w, r) == (12, world, rank) and row0 == (0 if rank == 0 else 7)
+    for i in range(steps):
+        want = order[i * mb:(i + 1) * mb].tolist()
+        got = sorted(sum((g[i] for g in gathered), []))
+        ok = ok and got == sorted(want)
+        ok = ok and mine[i] == [v for v in want if row0 <= v < row0 + n_loc]          # minibatch order kept
+    out[rank] = {'ok': bool(ok)}
     dist.destroy_process_group()
 
 

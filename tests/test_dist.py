@@ -25,6 +25,11 @@ def test_world_size_2_gloo_host_logic():
         assert res['nmf_D'] < 1e-12 and res['nmf_x'] < 1e-12, (rank, res)
 
 
+def test_world_size_2_gloo_dictionary_learning_row_sharding():
+    out = _spawn(dist_workers.cpu_dl_row_sharding, 2)
+    assert set(out) == {0, 1} and all(res['ok'] for res in out.values()), out
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
 def test_world_size_2_nccl_sharded_solves():
