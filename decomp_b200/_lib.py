@@ -50,6 +50,9 @@ def _declare(lib):
     lib.decomp_probe_dmma_tflops.argtypes = [ctypes.POINTER(ctypes.c_double)]
     lib.decomp_gemm_nt_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i64,
                                        ctypes.POINTER(Epilogue), c_dp, c_dp]
+    lib.decomp_gemm_b2b_masked_supported.argtypes = [c_i64]
+    lib.decomp_gemm_b2b_masked_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i64, ctypes.POINTER(Epilogue), c_dp,
+                                               c_dp]
     lib.decomp_gemm_tn_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
     lib.decomp_gemm_tn_workspace_bytes.restype = ctypes.c_size_t
     lib.decomp_gemm_tn_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_i32,
@@ -113,7 +116,8 @@ def _declare(lib):
 
 
 EXPORTS = (
-    'decomp_last_error', 'decomp_abi_version', 'decomp_probe_dmma_tflops', 'decomp_gemm_nt_f64', 'decomp_gemm_tn_workspace_bytes',
+    'decomp_last_error', 'decomp_abi_version', 'decomp_probe_dmma_tflops', 'decomp_gemm_nt_f64', 'decomp_gemm_b2b_masked_supported', 'decomp_gemm_b2b_masked_f64',
+    'decomp_gemm_tn_workspace_bytes',
     'decomp_gemm_tn_f64', 'decomp_make_rhs_f64', 'decomp_row_norms_f64', 'decomp_scale_f64', 'decomp_mask_mul_f64',
     'decomp_col_sums_workspace_bytes', 'decomp_col_sums_f64', 'decomp_row_sums_f64', 'decomp_gershgorin_step_f64', 'decomp_normalize_rows_f64',
     'decomp_gather_rows_f64', 'decomp_scatter_rows_f64', 'decomp_lasso_vectors_f64', 'decomp_axpby_f64', 'decomp_svrmu_update_f64', 'decomp_lasso_q_f64', 'decomp_scale_scalar_f64', 'decomp_mu_update_f64', 'decomp_max_abs_diff_f64',

@@ -9,6 +9,7 @@
 #include "common.h"
 #include "gemm.cuh"
 #include "lasso_resident.cuh"
+#include "masked_b2b.cuh"
 
 namespace dcp {
 
@@ -156,6 +157,45 @@ static int launch_resident(const CUtensorMap& tw, const CUtensorMap& tq, const R
   if (ctas > groups) ctas = groups;
   kern<<<(unsigned)ctas, RES_THREADS, ResidentSmem::SMEM_BYTES, stream>>>(tw, tq, a, skip_if);
   return check_cuda(cudaGetLastError(), "resident lasso launch");
+}
+
+template <int KB1, int EPI>
+static int launch_b2b(const CUtensorMap& tw, const CUtensorMap& tr, const B2bArgs& a, const decomp_epilogue_t& ep,
+                      const int32_t* skip_if, cudaStream_t stream) {
+  auto kern = masked_b2b_kernel<KB1, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2bSmem<KB1>::SMEM_BYTES);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(b2b smem)");
+    configured = true;
+  }
+  long long tiles = (a.M + B2B_BM - 1) / B2B_BM, ctas = num_sms();
+  if (ctas > tiles) ctas = tiles;
+  kern<<<(unsigned)ctas, B2B_THREADS, B2bSmem<KB1>::SMEM_BYTES, stream>>>(tw, tr, a, ep, skip_if);
+  return check_cuda(cudaGetLastError(), "b2b launch");
+}
+
+template <int KB1>
+static int dispatch_b2b(const CUtensorMap& tw, const CUtensorMap& tr, const B2bArgs& a, const decomp_epilogue_t& ep,
+                        const int32_t* skip_if, cudaStream_t st) {
+  switch (ep.kind) {
+    case DECOMP_EPI_STORE:
+      return launch_b2b<KB1, DECOMP_EPI_STORE>(tw, tr, a, ep, skip_if, st);
+    case DECOMP_EPI_PROX:
+      switch (ep.shrink) {
+        case DECOMP_SHRINK_REAL:
+          return launch_b2b<KB1, EPI_PROX_REAL>(tw, tr, a, ep, skip_if, st);
+        case DECOMP_SHRINK_COMPLEX:
+          return launch_b2b<KB1, EPI_PROX_COMPLEX>(tw, tr, a, ep, skip_if, st);
+        case DECOMP_SHRINK_POSITIVE:
+          return launch_b2b<KB1, EPI_PROX_POSITIVE>(tw, tr, a, ep, skip_if, st);
+        default:
+          break;
+      }
+    default:
+      set_error("decomp_gemm_b2b_masked_f64: epilogue must be STORE or PROX");
+      return DECOMP_ERR_INVALID;
+  }
 }
 
 static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
@@ -348,6 +388,48 @@ int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N
     default:
       set_error("decomp_lasso_resident_f64: unknown shrink kind %d", epi->shrink);
       return DECOMP_ERR_INVALID;
+  }
+}
+
+int decomp_gemm_b2b_masked_supported(int64_t K1) { return K1 == 32 || K1 == 64 || K1 == 128; }
+
+int decomp_gemm_b2b_masked_f64(const double* W, int64_t ldw, const double* R, int64_t ldr, int64_t M, int64_t K1,
+                               int64_t F, const decomp_epilogue_t* epi, const int32_t* skip_if, void* stream) {
+  if (epi == nullptr || W == nullptr || R == nullptr || M < 0 || F <= 0 || !decomp_gemm_b2b_masked_supported(K1) ||
+      F > 2147483647LL) {
+    set_error("decomp_gemm_b2b_masked_f64: invalid argument (K1 must be 32, 64 or 128)");
+    return DECOMP_ERR_INVALID;
+  }
+  if (M == 0) return DECOMP_OK;
+  if (epi->mask == nullptr || epi->out == nullptr || (epi->cwidth != 1 && epi->cwidth != 2) ||
+      (epi->cwidth == 1 && ((epi->ldmask & 1) != 0 || (reinterpret_cast<uintptr_t>(epi->mask) & 15u) != 0))) {
+    set_error("decomp_gemm_b2b_masked_f64: needs out and a mask (real data: 16-byte aligned, even ldmask)");
+    return DECOMP_ERR_INVALID;
+  }
+  if (epi->kind == DECOMP_EPI_PROX &&
+      (epi->x == nullptr || epi->other == nullptr || epi->prev == nullptr || epi->colvec == nullptr ||
+       epi->step == nullptr || (epi->check && (epi->latch == nullptr || epi->scratch == nullptr)))) {
+    set_error("decomp_gemm_b2b_masked_f64: PROX epilogue needs x, other, prev, colvec, step (and latch, scratch with check)");
+    return DECOMP_ERR_INVALID;
+  }
+  CUtensorMap tw, tr;
+  int rc = make_tensor_map(&tw, W, (uint64_t)K1, (uint64_t)M, (uint64_t)ldw, BK, B2B_BM);
+  if (rc != DECOMP_OK) return rc;
+  rc = make_tensor_map(&tr, R, (uint64_t)K1, (uint64_t)F, (uint64_t)ldr, BK, B2B_FC);
+  if (rc != DECOMP_OK) return rc;
+  B2bArgs a;
+  a.M = M;
+  a.K1 = (int)K1;
+  a.F = (int)F;
+  a.zero = 0;
+  cudaStream_t st = as_stream(stream);
+  switch (K1) {
+    case 32:
+      return dispatch_b2b<2>(tw, tr, a, *epi, skip_if, st);
+    case 64:
+      return dispatch_b2b<4>(tw, tr, a, *epi, skip_if, st);
+    default:
+      return dispatch_b2b<8>(tw, tr, a, *epi, skip_if, st);
   }
 }
 

@@ -556,7 +556,8 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   a.tiles_n = (a.N + a.mma_n - 1) / a.mma_n;
   a.kb_total = (a.K + TBK - 1) / TBK;
   a.kb_per_split = k_per_split > 0 ? (int)((k_per_split + TBK - 1) / TBK) : a.kb_total;
-  if (a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
+  // (a K-blocked operand keeps its block length whatever K is: the tensor map is built from kb_per_split)
+  if (!a.blocked && a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
   a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
   CUtensorMap tah, tal, tbh, tbl;
   int rc;

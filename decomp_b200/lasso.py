@@ -39,6 +39,7 @@ AVAILABLE_NNLS_METHODS = ['ista_pos', 'cd_pos', 'acc_ista_pos', 'fista_pos', 'pa
 DEVICE_RULES = ('ista', 'fista', 'acc_ista')
 RESIDENT_PAD_WORK = 1.5e8   # rows x width^2 below which one iteration is launch-bound (< ~10 us of DMMA)
 RESIDENT_MIN_ITERS = 7      # launches up to this length run per iteration when the batch is not launch-bound
+USE_B2B = True        # masked iteration: ((w A) * M) A^H fused into one kernel where it covers the width
 USE_RESIDENT = True   # several iterations per launch with the iterate on chip where the kernel covers the shape
 POLL_EVERY = 50   # iterations between (cheap) host reads of the convergence latch
 
@@ -354,6 +355,7 @@ class LassoSolver(object):
         self.rule, self.maxiter, self.group, self.mask = rule, maxiter, group, mask
         yr, Ar = rview(y), rview(A)
         self.full_mask = full_mask = mask is not None and mask.dim() == 2
+        self.b2b = False
         self.shrink = ops.SHRINK_POSITIVE if positive else (ops.SHRINK_COMPLEX if cplx else ops.SHRINK_REAL)
 
         # ---- prologue (lasso.py:120-138, 163)
@@ -426,6 +428,10 @@ class LassoSolver(object):
             ops.mask_mul(yr, mask, rview(T), cwidth=cw)
             ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
             self.A_rhs = ops.make_rhs(Anr, cplx, False)            # NT operand of  w . A
+            # widths the fused back-to-back kernel covers: both masked GEMMs of an iteration in one launch
+            self.b2b = bool(USE_B2B and ops.gemm_b2b_masked_supported(k * cw))
+            if self.b2b:
+                self.T = None                                      # only the set-up needed the [B, f] temporary
         else:
             ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
             # fold the gradient step into the operands:  w + (yAh - w G)/L  =  yAh/L + w (I - G/L)
@@ -501,10 +507,14 @@ class LassoSolver(object):
                            other=rview(self.yAh), prev=rview(self.X),
                            colvec=self.alpha_vec, colvec2=self.tol_vec,
                            rowvec=self.rowvec, step=self.step, momentum=self.mom[i], shrink=self.shrink,
-                           check=check, latch=latch, scratch=self.scratch, latch_value=i + 1)
-        ops.gemm_nt(rview(W[wi]), self.A_rhs,
-                    ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
-        ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
+                           check=check, latch=latch, scratch=self.scratch, latch_value=i + 1, mask=self.mask)
+        if self.b2b:
+            # ((w A) * M) A^H in one kernel, the [B, f] intermediate stays on chip (lasso.py:259-271)
+            ops.gemm_b2b_masked(rview(W[wi]), self.A_rhs, epi, skip=latch)
+        else:
+            ops.gemm_nt(rview(W[wi]), self.A_rhs,
+                        ops.epilogue(ops.EPI_STORE_MASK, rview(self.T), cwidth=cw, mask=self.mask), skip=latch)
+            ops.gemm_nt(rview(self.T), self.AH, epi, skip=latch)
         self._exchange_latch(check, i + 1)
 
     def _exchange_latch(self, check, value):

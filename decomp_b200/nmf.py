@@ -30,6 +30,7 @@ from .utils import assertion
 BATCH_METHODS = ['mu']
 MINIBATCH_METHODS = ['asg-mu', 'gsg-mu', 'asag-mu', 'gsag-mu', 'svrmu', 'svrmu-acc']
 POLL_EVERY = 25
+USE_B2B = True     # masked 'l2' x update: ((x D) * M) D^T fused into one kernel where it covers k
 
 
 def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', likelihood='l2', mask=None,
@@ -162,9 +163,15 @@ def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None, precision
         side.wait_stream(cur)
         graph = torch.cuda.CUDAGraph()
         before = ops.LAUNCHES
-        with torch.cuda.graph(graph, stream=side):
-            solver.sweep(3)
-            solver.sweep(4)
+        # (capture_begin / capture_end directly: the torch.cuda.graph context manager also runs the garbage collector
+        # and empties the allocator cache, which costs more than the sweeps it is supposed to save)
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                solver.sweep(3)
+                solver.sweep(4)
+            finally:
+                graph.capture_end()
         per_replay = ops.LAUNCHES - before
         cur.wait_stream(side)
         since_poll = 2
@@ -240,6 +247,7 @@ class MuSolver(object):
         if mask is not None:
             self.ym = empty2d(n, f, False, dev)
             ops.mask_mul(y, mask, self.ym)                                # y * mask, once (grads.py:113,123)
+        self.b2b = bool(USE_B2B and mask is not None and not kl and ops.gemm_b2b_masked_supported(k))
         if mask is not None or kl:
             self.F = empty2d(n, f, False, dev)                            # the [n, f] intermediate
             self.NEGD = empty2d(k, f, False, dev)
@@ -310,8 +318,11 @@ class MuSolver(object):
             ops.make_rhs(D, False, False, out=Dt, skip=latch)
             if not self.kl:
                 # ---- masked l2 (grads.py:112-115, 122-125)
-                ops.gemm_nt(X, Dt, E(ops.EPI_STORE_MASK, F, mask=mask), skip=latch)
-                ops.gemm_nt(F, D, E(ops.EPI_STORE, NEG), skip=latch)
+                if self.b2b:
+                    ops.gemm_b2b_masked(X, Dt, E(ops.EPI_STORE, NEG, mask=mask), skip=latch)    # ((x D) * M) D^T fused
+                else:
+                    ops.gemm_nt(X, Dt, E(ops.EPI_STORE_MASK, F, mask=mask), skip=latch)
+                    ops.gemm_nt(F, D, E(ops.EPI_STORE, NEG), skip=latch)
                 ops.gemm_nt(ym, D, E(ops.EPI_MU_NUM, X, x=X, other=NEG), skip=latch)
                 ops.gemm_nt(X, Dt, E(ops.EPI_STORE_MASK, F, mask=mask), skip=latch)
                 ops.gemm_tn(X, ym, POS, workspace=ws, skip=latch)

@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 from ._device import empty2d, full2d
-from .dictionary_learning import _ShuffledRows
+from ._lib import rview
 
 MINIBATCH_METHODS = ['asg-mu', 'gsg-mu', 'asag-mu', 'gsag-mu', 'svrmu', 'svrmu-acc']
 
@@ -99,6 +99,29 @@ class MuParts(object):
                 ops.scale(self.ones_kf, NEGD, rowscale=self.xsum)
             else:
                 ops.gemm_tn(x, m, NEGD, workspace=ws)
+
+
+class _ShuffledRows(object):
+    """Device rows under the reference's cumulative shuffle (utils/data.py:124-156): two owned buffers are
+    used alternately as gather targets; the caller's array is only ever read."""
+
+    def __init__(self, array, cplx):
+        self.cur = array
+        self.cplx = cplx
+        self.spare = [None, None]
+        self.turn = 0
+
+    def shuffle(self, index_dev):
+        n, c = self.cur.shape
+        if self.spare[self.turn] is None:
+            self.spare[self.turn] = empty2d(n, c, self.cplx, self.cur.device)
+        dst = self.spare[self.turn]
+        ops.gather_rows(rview(self.cur), index_dev, rview(dst))
+        self.cur = dst
+        self.turn ^= 1
+
+    def rows(self, r, step):
+        return self.cur[r * step:(r + 1) * step]
 
 
 def solve_device(y, D0, x, tol, minibatch, maxiter, method, kl, mask, rng, forget_rate=0.5, alpha=1.0, beta=0.5):

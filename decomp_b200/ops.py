@@ -70,6 +70,22 @@ def gemm_nt(A, B, epi, skip=None):
     _count(1)
 
 
+def gemm_b2b_masked_supported(K1):
+    """True if the fused back-to-back masked GEMM covers this (real) code width."""
+    return bool(_lib.lib().decomp_gemm_b2b_masked_supported(int(K1)))
+
+
+def gemm_b2b_masked(W, R, epi, skip=None):
+    """epilogue(((W . R^T) * mask) . R): W [M, K1], R [F, K1]; epi.mask [M, F / cwidth]; see decomp_b200.h."""
+    M, K1 = W.shape
+    F = R.shape[0]
+    assert R.shape[1] == K1
+    rc = _lib.lib().decomp_gemm_b2b_masked_f64(_p(W), ld(W), _p(R), ld(R), M, K1, F, ctypes.byref(epi), _p(skip),
+                                               _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_b2b_masked_f64')
+    _count(1)
+
+
 def gemm_tn_workspace(M, N, K, device):
     nbytes = _lib.lib().decomp_gemm_tn_workspace_bytes(M, N, K)
     return torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=device)

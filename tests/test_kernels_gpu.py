@@ -589,3 +589,35 @@ def test_store_mask_fast_paths_are_exact():
     same_bits = out.view(torch.int64) == ref.view(torch.int64)
     assert bool((same_bits | nan).all())
     assert bool(((ref == 0) & torch.signbit(ref)).any())      # negative zeros were exercised
+
+
+@pytest.mark.parametrize('cplx', [False, True])
+@pytest.mark.parametrize('M,k,f', [(300, 32, 70), (1000, 64, 333), (257, 128, 1024), (129, 16, 40)])
+def test_gemm_b2b_masked(cplx, M, k, f):
+    """((W R^T) * mask) R in one kernel (lasso.py:259-271, grads.py:112-115) against numpy; ragged rows and channels.
+    Complex data goes through the real embedding: one operand serves (w A) and (. A^H)."""
+    import torch
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d, empty2d
+    from decomp_b200._lib import rview
+    cw = 2 if cplx else 1
+    if not ops.gemm_b2b_masked_supported(k * cw):
+        pytest.skip('width not covered by the fused kernel')
+    rng = np.random.RandomState(M + k + f)
+
+    def randn(*s):
+        return rng.randn(*s) + 1j * rng.randn(*s) if cplx else rng.randn(*s)
+
+    w, A = randn(M, k), randn(k, f)
+    mask = np.rint(rng.uniform(0.3, 1.0, size=(M, f)))
+    mask[::7] *= 0.5                                                  # not only 0 / 1 weights
+    dev = torch.device('cuda', 0)
+    Wd, Ad, Md = to_device2d(w, dev), to_device2d(A, dev), to_device2d(mask, dev)
+    R = ops.make_rhs(rview(Ad), cplx, False)                          # NT operand of w . A: [f*cw, k*cw]
+    out = empty2d(M, k, cplx, dev)
+    out.fill_(float('nan'))
+    ops.gemm_b2b_masked(rview(Wd), R, ops.epilogue(ops.EPI_STORE, rview(out), cwidth=cw, mask=Md))
+    torch.cuda.synchronize()
+    ref = (w.dot(A) * mask).dot(np.conj(A.T))
+    err = np.max(np.abs(out.cpu().numpy() - ref)) / np.max(np.abs(ref))
+    assert err <= 1e-13, err

@@ -128,6 +128,43 @@ def test_lasso_vs_oracle_multi_tile(method, mask_kind):
     assert abs(obj - obj_ref) <= RTOL * abs(obj_ref)
 
 
+@pytest.mark.parametrize('method', ['ista', 'fista', 'fista_pos'])
+@pytest.mark.parametrize('k', [32, 64, 128])
+def test_lasso_masked_fused_b2b_vs_oracle(method, k):
+    """Per-problem mask with a code width the fused back-to-back kernel covers (one launch per iteration)."""
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((1300,), k, 333, 7 + k, positive=method.endswith('_pos'))
+    it0, x_ref = orc.lasso(y, A, 0.05, tol=1e-7, method=method, maxiter=120, mask=mask)
+    it, x = lasso.solve(y, A, 0.05, tol=1e-7, method=method, maxiter=120, mask=mask)
+    assert it == it0
+    assert_close(x, x_ref, what='x')
+    obj, obj_ref = orc.lasso_objective(y, A, x, 0.05, mask), orc.lasso_objective(y, A, x_ref, 0.05, mask)
+    assert abs(obj - obj_ref) <= RTOL * abs(obj_ref)
+
+
+def test_lasso_masked_fused_b2b_complex_vs_oracle():
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((700,), 32, 130, 8, complex_=True)      # 2k = 64 real columns
+    it0, x_ref = orc.lasso(y, A, 0.05, tol=0.0, method='fista', maxiter=25, mask=mask)
+    it, x = lasso.solve(y, A, 0.05, tol=0.0, method='fista', maxiter=25, mask=mask)
+    assert it == it0
+    assert_close(x, x_ref, what='x')
+
+
+@pytest.mark.parametrize('k', [32, 128])
+def test_nmf_masked_fused_b2b_vs_oracle(k):
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(2001, 300, k, 13)
+    it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=16, mask=mask)
+    it, D, x = nmf.solve(y, D0.copy(), tol=0.0, maxiter=16, mask=mask)
+    assert it == it0 == 16
+    assert_close(D, D_ref, what='D')
+    assert_close(x, x_ref, what='x')
+
+
 def test_lasso_complex_vs_oracle_multi_tile():
     from decomp_b200 import lasso
     from oracle import decomp_oracle as orc

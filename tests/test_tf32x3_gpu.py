@@ -198,7 +198,8 @@ def test_nmf_tf32x3_convergence_and_unsupported():
         nmf.solve(y, D0.copy(), precision='bf16')
 
 
-@pytest.mark.parametrize('M,N,K,block', [(64, 300, 1000, 256), (256, 520, 9000, 4096), (32, 32, 100, 128)])
+@pytest.mark.parametrize('M,N,K,block', [(64, 300, 1000, 256), (256, 520, 9000, 4096), (32, 32, 100, 128),
+                                         (64, 64, 50, 128), (256, 96, 3001, 4096)])
 def test_tf32x3_splitk_k_blocked_layout(M, N, K, block):
     """x^T / y^T stored K-blocked ([K / block][rows][block], zero-filled tail): split-K reads block z for piece z;
     the blocked transpose and the blocked x-update output agree with the plain layouts."""

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_tf32x3_gpu.py tests/test_parity_gpu.py -m gpu -x -q -k "tf32 or nmf" > gpurun_out/r2g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2g_pytest.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2g_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2g_pytest.log
 tail -4 gpurun_out/r2g_pytest.log
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --legs nmf,tf32 > gpurun_out/r2g_bench_nmf.json 2> gpurun_out/r2g_bench_nmf.err; echo "rc=$?" >> gpurun_out/r2g_bench_nmf.err
 tail -3 gpurun_out/r2g_bench_nmf.err
