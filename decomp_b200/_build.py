@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdecomp_b200.so')
-SOURCES = ['gemm_api.cu', 'kernels_misc.cu', 'dl_kernels.cu', 'tf32x3.cu', 'staged_copy.cu']
+SOURCES = ['gemm_api.cu', 'kernels_misc.cu', 'dl_kernels.cu', 'tf32x3.cu', 'staged_copy.cu', 'nmf_small.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

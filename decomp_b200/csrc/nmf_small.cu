@@ -1,0 +1,316 @@
+// Whole NMF multiplicative-update runs of SMALL problems in one cooperative launch (BASELINE configs[0]: y 1000 x 200,
+// k = 20, 100 sweeps; the sizes of the reference's own tests).  At these sizes a sweep is a few microseconds of
+// arithmetic; launched kernel by kernel (12 launches per sweep) it costs ~100 us.  Here every CTA keeps its rows of
+// y, mask and x and the whole dictionary in shared memory for all sweeps, and a sweep is
+//     x update of the CTA's rows            (grads.py:77-84, 108-115)
+//     partial statistics of the CTA's rows  -> global, one slab per CTA
+//     grid barrier; fixed-order reduction of the slabs (deterministic); grid barrier
+//     D update, l2_strict, max |D - D_new|  (grads.py:86-93, 117-125; normalize.py:13-21; batch_mu.py:21-23),
+//     computed redundantly and identically by every CTA, so all of them take the same exit without exchanging it
+// Plain FP64 FMAs (the problems are far too small for the tensor pipe to matter).  k <= 32.
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace dcp {
+
+constexpr double kEpsS = 1.0e-15;
+constexpr int SMALL_THREADS = 256, SMALL_KMAX = 32;
+
+struct SmallNmfArgs {
+  const double* y;
+  long long ldy;
+  const double* mask;   // nullptr: unmasked
+  long long ldm;
+  double* x;            // [n, k] in / out
+  long long ldx;
+  const double* D_in;   // [k, f], rows already normalised (nmf.py:70)
+  long long ldd;
+  double* D_out;
+  long long ldo;
+  int n, f, k, sweeps, rows_per_cta;
+  double tol;
+  int* it_out;          // 0, or the sweep at which max |D - D_new| < tol
+  double* partials;     // [grid][slab] then [slab] reduced
+  unsigned* counter;    // grid barrier, zeroed by the host
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum_s(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const SmallNmfArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = a.n, f = a.f, k = a.k, R = a.rows_per_cta;
+  const int slab = MASKED ? 2 * k * f : k * f + k * k;   // per-CTA statistics: (T, NEGD) or (T, S)
+  double* D_s = sm;                     // [k][f]
+  double* Dn_s = D_s + k * f;           // [k][f]
+  double* G_s = Dn_s + k * f;           // [k][k]  D D^T (unmasked) / reduced S (unmasked)
+  double* y_s = G_s + k * k;            // [R][f]  y (masked: y * mask)
+  double* x_s = y_s + R * f;            // [R][k]
+  double* m_s = x_s + R * k;            // [R][f]  mask                     (masked only)
+  double* F_s = m_s + (MASKED ? R * f : 0);   // [R][f]  (x D) * mask         (masked only)
+  double* red = F_s + (MASKED ? R * f : 0);   // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * R;
+  const int rows = row0 < n ? (n - row0 < R ? n - row0 : R) : 0;
+  unsigned target = 0;
+
+  for (int e = tid; e < k * f; e += SMALL_THREADS) D_s[e] = a.D_in[(long long)(e / f) * a.ldd + e % f];
+  for (int e = tid; e < rows * f; e += SMALL_THREADS) {
+    const int r = e / f, j = e % f;
+    double v = a.y[(long long)(row0 + r) * a.ldy + j];
+    if (MASKED) {
+      const double m = a.mask[(long long)(row0 + r) * a.ldm + j];
+      m_s[e] = m;
+      v *= m;                                            // y * mask, once (grads.py:113,123)
+    }
+    y_s[e] = v;
+  }
+  for (int e = tid; e < rows * k; e += SMALL_THREADS) x_s[e] = a.x[(long long)(row0 + e / k) * a.ldx + e % k];
+  __syncthreads();
+
+  int converged_at = 0;
+  for (int it = 1; it <= a.sweeps; ++it) {
+    // ---------------------------------------------------------------- x update of this CTA's rows
+    if (!MASKED) {
+      for (int e = tid; e < k * k; e += SMALL_THREADS) {
+        const double* da = D_s + (e / k) * f;
+        const double* db = D_s + (e % k) * f;
+        double s = 0.0;
+        for (int j = 0; j < f; ++j) s += da[j] * db[j];
+        G_s[e] = s;
+      }
+      __syncthreads();
+    }
+    for (int r = warp; r < rows; r += SMALL_THREADS / 32) {
+      const double* yr = y_s + r * f;
+      double* xr = x_s + r * k;
+      if (MASKED) {
+        // F = (x D) * mask for the row (grads.py:112-115)
+        for (int j = lane; j < f; j += 32) {
+          double s = 0.0;
+          for (int b = 0; b < k; ++b) s += xr[b] * D_s[b * f + j];
+          F_s[r * f + j] = s * m_s[r * f + j];
+        }
+        __syncwarp();
+      }
+      double mine_pos = 0.0, mine_neg = 0.0;   // lane c ends up with the sums of atom c
+      for (int c = 0; c < k; ++c) {
+        const double* dc = D_s + c * f;
+        double p = 0.0, q = 0.0;
+        for (int j = lane; j < f; j += 32) {
+          p += yr[j] * dc[j];
+          if (MASKED) q += F_s[r * f + j] * dc[j];
+        }
+        p = warp_sum_s(p);
+        if (MASKED) q = warp_sum_s(q);
+        if (lane == c) {
+          mine_pos = p;
+          mine_neg = q;
+        }
+      }
+      if (!MASKED && lane < k) {
+        double q = 0.0;
+        for (int b = 0; b < k; ++b) q += xr[b] * G_s[b * k + lane];   // x (D D^T)
+        mine_neg = q;
+      }
+      __syncwarp();
+      if (lane < k) xr[lane] = xr[lane] * fmax(mine_pos, 0.0) / fmax(mine_neg, kEpsS);
+      __syncwarp();
+      if (MASKED) {
+        // F with the NEW x: the D update uses it (grads.py:122-125)
+        for (int j = lane; j < f; j += 32) {
+          double s = 0.0;
+          for (int b = 0; b < k; ++b) s += xr[b] * D_s[b * f + j];
+          F_s[r * f + j] = s * m_s[r * f + j];
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- statistics of this CTA's rows
+    double* mine = a.partials + (long long)blockIdx.x * slab;
+    for (int e = tid; e < k * f; e += SMALL_THREADS) {
+      const int c = e / f, j = e % f;
+      double t = 0.0, g = 0.0;
+      for (int r = 0; r < rows; ++r) {
+        t += x_s[r * k + c] * y_s[r * f + j];
+        if (MASKED) g += x_s[r * k + c] * F_s[r * f + j];
+      }
+      mine[e] = t;
+      if (MASKED) mine[k * f + e] = g;
+    }
+    if (!MASKED) {
+      for (int e = tid; e < k * k; e += SMALL_THREADS) {
+        double s = 0.0;
+        for (int r = 0; r < rows; ++r) s += x_s[r * k + e / k] * x_s[r * k + e % k];
+        mine[k * f + e] = s;
+      }
+    }
+    grid_barrier(a.counter, target);
+    // ---------------------------------------------------------------- fixed-order reduction over the CTAs
+    double* total = a.partials + (long long)gridDim.x * slab;
+    for (int e = blockIdx.x * SMALL_THREADS + tid; e < slab; e += gridDim.x * SMALL_THREADS) {
+      double s = 0.0;
+      for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(a.partials + (long long)c * slab + e);
+      total[e] = s;
+    }
+    grid_barrier(a.counter, target);
+    // ---------------------------------------------------------------- D update (every CTA, identically)
+    if (!MASKED) {
+      for (int e = tid; e < k * k; e += SMALL_THREADS) G_s[e] = __ldcg(total + k * f + e);   // S = x^T x
+      __syncthreads();
+    }
+    for (int e = tid; e < k * f; e += SMALL_THREADS) {
+      const int c = e / f, j = e % f;
+      double den;
+      if (MASKED) {
+        den = __ldcg(total + k * f + e);
+      } else {
+        den = 0.0;
+        for (int b = 0; b < k; ++b) den += G_s[c * k + b] * D_s[b * f + j];
+      }
+      Dn_s[e] = D_s[e] * fmax(__ldcg(total + e), 0.0) / fmax(den, kEpsS);
+    }
+    __syncthreads();
+    double md = 0.0;
+    for (int c = warp; c < k; c += SMALL_THREADS / 32) {
+      double s = 0.0;
+      for (int j = lane; j < f; j += 32) s += Dn_s[c * f + j] * Dn_s[c * f + j];
+      const double nrm = sqrt(warp_sum_s(s));           // l2_strict: no floor (normalize.py:13-21)
+      for (int j = lane; j < f; j += 32) {
+        const double v = Dn_s[c * f + j] / nrm;
+        const double d = fabs(D_s[c * f + j] - v);
+        md = (d != d) ? d : ((md != md) ? md : fmax(md, d));   // NaN wins like numpy's max
+        Dn_s[c * f + j] = v;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, md, o);
+      md = (other != other) ? other : ((md != md) ? md : fmax(md, other));
+    }
+    if (lane == 0) red[warp] = md;
+    __syncthreads();
+    for (int e = tid; e < k * f; e += SMALL_THREADS) D_s[e] = Dn_s[e];
+    double all = red[0];
+    for (int w = 1; w < SMALL_THREADS / 32; ++w) {
+      const double other = red[w];
+      all = (other != other) ? other : ((all != all) ? all : fmax(all, other));
+    }
+    __syncthreads();
+    if (a.tol > 0.0 && all < a.tol) {      // batch_mu.py:22-23: identical on every CTA
+      converged_at = it;
+      break;
+    }
+    // the partial slabs are rewritten next sweep: everybody must be past the reduction (second barrier above) --
+    // and the reduced slab `total` is only rewritten after the next first barrier, when all CTAs have read it
+  }
+  for (int e = tid; e < rows * k; e += SMALL_THREADS) a.x[(long long)(row0 + e / k) * a.ldx + e % k] = x_s[e];
+  if (blockIdx.x == 0) {
+    for (int e = tid; e < k * f; e += SMALL_THREADS) a.D_out[(long long)(e / f) * a.ldo + e % f] = D_s[e];
+    if (tid == 0) *a.it_out = converged_at;
+  }
+}
+
+static size_t small_smem_bytes(int f, int k, int R, bool masked) {
+  return sizeof(double) * ((size_t)2 * k * f + (size_t)k * k + (size_t)R * f * (masked ? 3 : 1) + (size_t)R * k + 32);
+}
+
+static void small_plan(int64_t n, int* grid, int* R) {
+  const int sms = num_sms();
+  long long r = (n + sms - 1) / sms;
+  if (r < 1) r = 1;
+  *R = (int)r;
+  *grid = (int)((n + r - 1) / r);
+}
+
+}  // namespace dcp
+
+using namespace dcp;
+
+extern "C" {
+
+int decomp_nmf_mu_small_supported(int64_t n, int64_t f, int64_t k, int32_t masked) {
+  if (n <= 0 || f <= 0 || k <= 0 || k > SMALL_KMAX || n > (1 << 20) || f > (1 << 16)) return 0;
+  int grid, R;
+  small_plan(n, &grid, &R);
+  return small_smem_bytes((int)f, (int)k, R, masked != 0) <= (size_t)200 * 1024;
+}
+
+size_t decomp_nmf_mu_small_workspace_bytes(int64_t n, int64_t f, int64_t k, int32_t masked) {
+  if (!decomp_nmf_mu_small_supported(n, f, k, masked)) return 0;
+  int grid, R;
+  small_plan(n, &grid, &R);
+  const size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  return sizeof(double) * slab * ((size_t)grid + 1) + 16;   // slabs + the reduced slab + the barrier counter
+}
+
+int decomp_nmf_mu_small_f64(const double* y, int64_t ldy, const double* mask, int64_t ldm, double* x, int64_t ldx,
+                            const double* D_in, int64_t ldd, double* D_out, int64_t ldo, int64_t n, int64_t f,
+                            int64_t k, int32_t sweeps, double tol, int32_t* it_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (!decomp_nmf_mu_small_supported(n, f, k, mask != nullptr) || y == nullptr || x == nullptr || D_in == nullptr ||
+      D_out == nullptr || it_out == nullptr || sweeps < 0) {
+    set_error("decomp_nmf_mu_small_f64: unsupported size or invalid argument");
+    return DECOMP_ERR_INVALID;
+  }
+  const size_t need = decomp_nmf_mu_small_workspace_bytes(n, f, k, mask != nullptr);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("decomp_nmf_mu_small_f64: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DECOMP_ERR_INVALID;
+  }
+  int grid, R;
+  small_plan(n, &grid, &R);
+  const bool masked = mask != nullptr;
+  const size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  SmallNmfArgs a;
+  a.y = y;
+  a.ldy = ldy;
+  a.mask = mask;
+  a.ldm = ldm;
+  a.x = x;
+  a.ldx = ldx;
+  a.D_in = D_in;
+  a.ldd = ldd;
+  a.D_out = D_out;
+  a.ldo = ldo;
+  a.n = (int)n;
+  a.f = (int)f;
+  a.k = (int)k;
+  a.sweeps = sweeps;
+  a.rows_per_cta = R;
+  a.tol = tol;
+  a.it_out = it_out;
+  a.partials = reinterpret_cast<double*>(workspace);
+  a.counter = reinterpret_cast<unsigned*>(a.partials + slab * ((size_t)grid + 1));
+  cudaStream_t st = as_stream(stream);
+  cudaError_t e = cudaMemsetAsync(a.counter, 0, 16, st);
+  if (e != cudaSuccess) return check_cuda(e, "nmf_small counter");
+  const size_t smem = small_smem_bytes((int)f, (int)k, R, masked);
+  void* kern = masked ? (void*)nmf_mu_small_kernel<true> : (void*)nmf_mu_small_kernel<false>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return check_cuda(e, "nmf_small smem");
+  void* args[] = {(void*)&a};
+  e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(SMALL_THREADS), args, smem, st);
+  return check_cuda(e, "nmf_small launch");
+}
+
+}  // extern "C"

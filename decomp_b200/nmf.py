@@ -135,6 +135,8 @@ def _solve_minibatch(y, D, x, tol, minibatch, maxiter, method, kl, mask, random_
     return it, to_host(Dd, y, out_dtype), to_host(xd, y, out_dtype)
 
 
+USE_SMALL = True
+SMALL_MAX_WORK = 5.0e7      # n k f up to which a whole run goes into one cooperative launch (decomp_nmf_mu_small_f64)
 GRAPH_MAX_WORK = 2.0e9      # n k f below which a sweep is launch-bound and is replayed from a CUDA graph
 GRAPH_MIN_SWEEPS = 12
 
@@ -147,9 +149,22 @@ def mu_device(y, D0, X, tol, maxiter, kl=False, mask=None, group=None, precision
     ping-pongs between two buffers) is captured into a CUDA graph once and replayed.  Nothing in a sweep touches
     the host -- convergence is a device latch whose value is the device-side sweep count under replay -- so the
     results and the returned iteration count are those of the sweep-by-sweep loop."""
-    solver = MuSolver(y, D0, X, tol, kl=kl, mask=mask, group=group, precision=precision)
     n, f = y.shape
     sweeps = maxiter - 1
+    k = D0.shape[0]
+    if (USE_SMALL and group is None and not kl and precision == 'fp64' and sweeps >= 1
+            and float(n) * f * k <= SMALL_MAX_WORK and ops.nmf_mu_small_supported(n, f, k, mask is not None)):
+        # the whole run in one cooperative launch: rows and dictionary stay in shared memory for all sweeps
+        dev = y.device
+        Dn = empty2d(k, f, False, dev)
+        ops.normalize_rows(D0, Dn, False, True)                           # nmf.py:70
+        D_out = empty2d(k, f, False, dev)
+        it_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = ops.nmf_mu_small(y, mask, X, Dn, D_out, sweeps, tol, it_dev)
+        fired = int(it_dev.item()) if tol > 0.0 else 0
+        del ws
+        return (fired if fired else maxiter), D_out, X
+    solver = MuSolver(y, D0, X, tol, kl=kl, mask=mask, group=group, precision=precision)
     stopped_at = 0
     it = 1
     if (group is None and not solver.tf32 and sweeps >= GRAPH_MIN_SWEEPS

@@ -356,6 +356,23 @@ def scale_scalar(A, scalar_dev, out):
     return out
 
 
+def nmf_mu_small_supported(n, f, k, masked):
+    return bool(_lib.lib().decomp_nmf_mu_small_supported(int(n), int(f), int(k), int(bool(masked))))
+
+
+def nmf_mu_small(y, mask, X, D_in, D_out, sweeps, tol, it_out):
+    """`sweeps` multiplicative updates of a small problem in ONE cooperative launch; see decomp_b200.h."""
+    n, f = y.shape
+    k = D_in.shape[0]
+    ws = workspace(_lib.lib().decomp_nmf_mu_small_workspace_bytes(n, f, k, int(mask is not None)), y.device)
+    rc = _lib.lib().decomp_nmf_mu_small_f64(_p(y), ld(y), _p(mask), ld(mask) if mask is not None else 0, _p(X), ld(X),
+                                            _p(D_in), ld(D_in), _p(D_out), ld(D_out), n, f, k, int(sweeps), float(tol),
+                                            _p(it_out), _p(ws), ws.numel() * 8, _lib.stream_ptr())
+    _lib.check(rc, 'decomp_nmf_mu_small_f64')
+    _count(1)
+    return ws
+
+
 def mu_update(x, num, den, out, skip=None):
     rows, cols = x.shape
     rc = _lib.lib().decomp_mu_update_f64(_p(x), ld(x), _p(num), ld(num), _p(den), ld(den), rows, cols, _p(out), ld(out),

@@ -101,6 +101,17 @@ int decomp_probe_dmma_tflops(double* tflops_out);
 int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N,
                        int64_t K, const decomp_epilogue_t* epi, const int32_t* skip_if, void* stream);
 
+/* Back-to-back GEMM of the masked updates without the [M, F] intermediate:
+ *   acc[m][n] = sum_j ((sum_k W[m][k] R[j][k]) * mask[m][j / cwidth]) * R[j][n]        W [M, K1], R [F, K1]
+ * followed by the epilogue `epi` (DECOMP_EPI_STORE or DECOMP_EPI_PROX; epi->mask is the [M, F / cwidth] mask).
+ *   masked ISTA / FISTA  ((w A) * M) A^H   lasso.py:259-271   W = w, R = decomp_make_rhs(A, conj_transpose = 0)
+ *   masked NMF           ((x D) * M) D^T   grads.py:112-115   W = x, R = D^T
+ * (for complex data the real embedding of A^H is the transpose of that of A, so one operand serves both products).
+ * K1 must be 32, 64 or 128 (decomp_gemm_b2b_masked_supported); other widths use two decomp_gemm_nt_f64 launches. */
+int decomp_gemm_b2b_masked_supported(int64_t K1);
+int decomp_gemm_b2b_masked_f64(const double* W, int64_t ldw, const double* R, int64_t ldr, int64_t M, int64_t K1,
+                               int64_t F, const decomp_epilogue_t* epi, const int32_t* skip_if, void* stream);
+
 /* acc[m][n] = sum_k A[k*lda + m] * B[k*ldb + n]   (A: [K,M], B: [K,N]; contraction over rows = samples),
  * split along K across CTAs with a deterministic two-stage reduction through `workspace`.
  *   combine = 0: out = acc             (x.T.dot(y), x.T.dot(f), grads.py:120-125)
@@ -288,6 +299,19 @@ int decomp_dl_masked_update_phase_f64(int32_t phase, const double* S_slab, int64
                                       const double* T, int64_t ldt, const double* D, int64_t ldd, int64_t k, int64_t f,
                                       int32_t is_complex, double* D_slab_out, double* stats, double* workspace,
                                       void* stream);
+
+/* ---- whole NMF-MU runs of small problems in one cooperative launch ------------------------ */
+/* batch_mu.solve (nmf_methods/batch_mu.py:8-26) for problems whose rows / dictionary fit in shared memory (k <= 32;
+ * BASELINE configs[0] and the sizes of the reference's own tests): `sweeps` = maxiter - 1 multiplicative updates of
+ * x [n,k] (in place) and D (D_in: rows already l2_strict-normalised, nmf.py:70; D_out: result), 'l2' likelihood,
+ * optional mask [n,f].  *it_out = 0, or the sweep at which max |D - D_new| < tol (tol <= 0: never).  Same arithmetic
+ * as the sweep-by-sweep kernels up to summation order.  workspace: decomp_nmf_mu_small_workspace_bytes(). */
+int decomp_nmf_mu_small_supported(int64_t n, int64_t f, int64_t k, int32_t masked);
+size_t decomp_nmf_mu_small_workspace_bytes(int64_t n, int64_t f, int64_t k, int32_t masked);
+int decomp_nmf_mu_small_f64(const double* y, int64_t ldy, const double* mask, int64_t ldm, double* x, int64_t ldx,
+                            const double* D_in, int64_t ldd, double* D_out, int64_t ldo, int64_t n, int64_t f,
+                            int64_t k, int32_t sweeps, double tol, int32_t* it_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* ---- host-side staging of pageable inputs -------------------------------------------------- */
 /* dst_device[0:bytes] = src_host[0:bytes] for an ordinary (pageable) host array, the kind of array the reference's

@@ -244,3 +244,36 @@ def test_nmf_streamed_from_host_matches_resident(masked):
         assert it == it0
         assert_close(D, D_ref, what='D')
         assert_close(x, x_ref, what='x')
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_nmf_small_launch_graph_and_eager_paths_agree(masked, monkeypatch):
+    """Small problems run whole solves in one cooperative launch; launch-bound ones replay a CUDA graph; the rest
+    enqueue sweep by sweep.  All three give the oracle's iteration count and factors."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(1000, 200, 20, 0, 'l2', reference_order=False)       # BASELINE configs[0]
+    m = mask if masked else None
+    for tol, maxiter in ((0.0, 101), (1.0e-4, 2000)):
+        it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=tol, maxiter=maxiter, mask=m)
+        for path in ('small', 'graph', 'eager'):
+            monkeypatch.setattr(nmf, 'USE_SMALL', path == 'small')
+            monkeypatch.setattr(nmf, 'GRAPH_MIN_SWEEPS', 12 if path != 'eager' else 10 ** 9)
+            it, D, x = nmf.solve(y, D0.copy(), tol=tol, maxiter=maxiter, mask=m)
+            assert it == it0, (path, tol, it, it0)
+            assert_close(D, D_ref, what='D ' + path)
+            assert_close(x, x_ref, what='x ' + path)
+
+
+def test_nmf_small_launch_odd_sizes():
+    """Rows that do not fill the last CTA, more CTAs than rows, a single atom."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    for n, f, k, seed in ((257, 67, 7, 3), (40, 33, 1, 5), (2000, 31, 32, 6)):
+        y, D0, mask = gc._nmf_data(n, f, k, seed)
+        for m in (None, mask):
+            it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=31, mask=m)
+            it, D, x = nmf.solve(y, D0.copy(), tol=0.0, maxiter=31, mask=m)
+            assert it == it0
+            assert_close(D, D_ref, what='D')
+            assert_close(x, x_ref, what='x')
