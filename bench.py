@@ -445,6 +445,18 @@ def run_ours(args):
                                           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                                           'ms_per_call': e2ep * 1e3, 'host_memory': 'page-locked',
                                           'calls_ms': [t * 1e3 for t in e2ep_times], 'note': note % 'page-locked'}
+            # what the host-to-device link gives this rank while every rank copies at once: the floor of the call above
+            ydev = torch.empty((B, f), dtype=torch.float64, device=device)
+            ydev.copy_(yh, non_blocking=True)
+            probe_ms, _, _ = timed_regions(lambda r: ydev.copy_(yh, non_blocking=True), 3)
+            t_probe = median(probe_ms) * 1e-3
+            for key in ('e2e', 'e2e_pinned'):
+                out['fista'][key]['h2d_copy_only'] = {
+                    'ms': t_probe * 1e3, 'gbs_per_gpu': yh.numel() * 8 / t_probe / 1e9,
+                    'gbs_all_gpus': world * yh.numel() * 8 / t_probe / 1e9,
+                    'note': 'bare cudaMemcpyAsync of y from page-locked memory, all ranks at once, max over ranks: '
+                            'the part of ms_per_call no kernel can remove'}
+            del ydev
             res.clear()
             del yh, Ah, yp, Ap
         else:

@@ -277,3 +277,24 @@ def test_nmf_small_launch_odd_sizes():
             assert it == it0
             assert_close(D, D_ref, what='D')
             assert_close(x, x_ref, what='x')
+
+
+def test_dictionary_learning_masked_complex_multi_chunk_statistics():
+    """BASELINE configs[3] in small: complex128, masked, and enough atoms that the Hermitian half of the [k, f, k]
+    statistic is accumulated in several packed GEMMs (4656 (a, b >= a) pairs: >= 3 chunks of the real
+    decomp_b200.dictionary_learning._pair_cols width), through dictionary_learning.solve itself."""
+    import torch
+    from decomp_b200 import dictionary_learning
+    from oracle import decomp_oracle as orc
+    n, f, k, mb = 1100, 256, 96, 512
+    y, D0, mask = gc._dl_data(n, f, k, 21, True)
+    pairs = k * (k + 1) // 2
+    cap = dictionary_learning._pair_cols(f, 2, torch.device('cuda', 0))
+    assert -(-pairs // cap) >= 3, (pairs, cap)
+    kw = dict(tol=0.0, minibatch=mb, maxiter=2, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5, mask=mask,
+              random_seed=2)
+    it0, D_ref, x_ref = orc.dictionary_learning(y * mask, D0.copy(), 0.05, **kw)
+    it, D, x = dictionary_learning.solve(y * mask, D0.copy(), 0.05, **kw)
+    assert it == it0
+    assert_close(D, D_ref, what='D')
+    assert_close(x, x_ref, what='x')
