@@ -743,6 +743,8 @@ def run_ours(args):
         line['clocks'] = clocks
         print(json.dumps(line))
     if world > 1:
+        from decomp_b200 import comm
+        comm.destroy_all()
         dist.destroy_process_group()
 
 

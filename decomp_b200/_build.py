@@ -8,7 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdecomp_b200.so')
-SOURCES = ['gemm_api.cu', 'kernels_misc.cu', 'dl_kernels.cu', 'tf32x3.cu', 'staged_copy.cu', 'nmf_small.cu']
+SOURCES = ['gemm_api.cu', 'kernels_misc.cu', 'dl_kernels.cu', 'tf32x3.cu', 'staged_copy.cu', 'nmf_small.cu', 'comm.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError('nvcc failed on ' + src)
-    cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lpthread']
+    cmd = [nvcc, '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lpthread', '-ldl']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

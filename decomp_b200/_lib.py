@@ -113,6 +113,13 @@ def _declare(lib):
     lib.decomp_nmf_mu_small_workspace_bytes.restype = ctypes.c_size_t
     lib.decomp_nmf_mu_small_f64.argtypes = [c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_dp, c_i64, c_i64, c_i64, c_i64,
                                             c_i32, ctypes.c_double, c_dp, c_dp, ctypes.c_size_t, c_dp]
+    lib.decomp_comm_unique_id.argtypes = [c_dp]
+    lib.decomp_comm_init.argtypes = [c_dp, c_i32, c_i32, ctypes.POINTER(ctypes.c_void_p)]
+    lib.decomp_comm_destroy.argtypes = [c_dp]
+    lib.decomp_comm_allreduce_sum_f64.argtypes = [c_dp, c_dp, c_i64, c_dp]
+    lib.decomp_comm_allreduce_min_i32.argtypes = [c_dp, c_dp, c_i64, c_dp]
+    lib.decomp_comm_reduce_scatter_sum_f64.argtypes = [c_dp, c_dp, c_dp, c_i64, c_dp]
+    lib.decomp_comm_allgather_f64.argtypes = [c_dp, c_dp, c_dp, c_i64, c_dp]
     lib.decomp_staged_upload.argtypes = [c_dp, c_dp, ctypes.c_size_t, c_dp, ctypes.c_size_t, c_i32, c_i32, c_dp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -131,6 +138,8 @@ EXPORTS = (
     'decomp_gemm_nt_tf32x3_splitk_workspace_bytes', 'decomp_gemm_nt_tf32x3_splitk_f64', 'decomp_nmf_xupdate_tf32x3',
     'decomp_split_transpose_tf32_f64',
     'decomp_lasso_resident_supported', 'decomp_lasso_resident_f64', 'decomp_staged_upload',
+    'decomp_comm_unique_id', 'decomp_comm_init', 'decomp_comm_destroy', 'decomp_comm_allreduce_sum_f64',
+    'decomp_comm_allreduce_min_i32', 'decomp_comm_reduce_scatter_sum_f64', 'decomp_comm_allgather_f64',
     'decomp_nmf_mu_small_supported', 'decomp_nmf_mu_small_workspace_bytes', 'decomp_nmf_mu_small_f64',
 )
 

@@ -59,7 +59,8 @@ template <bool MASKED>
 __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const SmallNmfArgs a) {
   extern __shared__ __align__(16) double sm[];
   const int n = a.n, f = a.f, k = a.k, R = a.rows_per_cta;
-  const int slab = MASKED ? 2 * k * f : k * f + k * k;   // per-CTA statistics: (T, NEGD) or (T, S)
+  const int slab_len = MASKED ? 2 * k * f : k * f + k * k;   // per-CTA statistics: (T, NEGD) or (T, S)
+  const int slab = (slab_len + 3) & ~3;                      // slab pitch: 32-byte aligned for the reduction's loads
   double* D_s = sm;                     // [k][f]
   double* Dn_s = D_s + k * f;           // [k][f]
   double* G_s = Dn_s + k * f;           // [k][k]  D D^T (unmasked) / reduced S (unmasked)
@@ -87,16 +88,18 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
   for (int e = tid; e < rows * k; e += SMALL_THREADS) x_s[e] = a.x[(long long)(row0 + e / k) * a.ldx + e % k];
   __syncthreads();
 
+  for (int e = slab_len + tid; e < slab; e += SMALL_THREADS) a.partials[(long long)blockIdx.x * slab + e] = 0.0;
   int converged_at = 0;
   for (int it = 1; it <= a.sweeps; ++it) {
     // ---------------------------------------------------------------- x update of this CTA's rows
     if (!MASKED) {
-      for (int e = tid; e < k * k; e += SMALL_THREADS) {
+      for (int e = warp; e < k * k; e += SMALL_THREADS / 32) {     // one warp per entry of D D^T
         const double* da = D_s + (e / k) * f;
         const double* db = D_s + (e % k) * f;
         double s = 0.0;
-        for (int j = 0; j < f; ++j) s += da[j] * db[j];
-        G_s[e] = s;
+        for (int j = lane; j < f; j += 32) s += da[j] * db[j];
+        s = warp_sum_s(s);
+        if (lane == 0) G_s[e] = s;
       }
       __syncthreads();
     }
@@ -166,11 +169,27 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
     }
     grid_barrier(a.counter, target);
     // ---------------------------------------------------------------- fixed-order reduction over the CTAs
+    // (one warp per entry: lane l adds the slabs l, l + 32, ... in order, then a fixed shuffle tree -- the same
+    // association every time, and the ~gridDim.x loads of an entry are in flight together instead of one by one)
     double* total = a.partials + (long long)gridDim.x * slab;
-    for (int e = blockIdx.x * SMALL_THREADS + tid; e < slab; e += gridDim.x * SMALL_THREADS) {
-      double s = 0.0;
-      for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(a.partials + (long long)c * slab + e);
-      total[e] = s;
+    for (int e4 = blockIdx.x * (SMALL_THREADS / 32) + warp; e4 < slab / 4; e4 += gridDim.x * (SMALL_THREADS / 32)) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (unsigned c = lane; c < gridDim.x; c += 32) {
+        const double2* src = reinterpret_cast<const double2*>(a.partials + (long long)c * slab) + 2 * e4;
+        const double2 lo = __ldcg(src), hi = __ldcg(src + 1);
+        s0 += lo.x;
+        s1 += lo.y;
+        s2 += hi.x;
+        s3 += hi.y;
+      }
+      s0 = warp_sum_s(s0);
+      s1 = warp_sum_s(s1);
+      s2 = warp_sum_s(s2);
+      s3 = warp_sum_s(s3);
+      if (lane == 0) {
+        reinterpret_cast<double2*>(total)[2 * e4] = make_double2(s0, s1);
+        reinterpret_cast<double2*>(total)[2 * e4 + 1] = make_double2(s2, s3);
+      }
     }
     grid_barrier(a.counter, target);
     // ---------------------------------------------------------------- D update (every CTA, identically)
@@ -259,7 +278,8 @@ size_t decomp_nmf_mu_small_workspace_bytes(int64_t n, int64_t f, int64_t k, int3
   if (!decomp_nmf_mu_small_supported(n, f, k, masked)) return 0;
   int grid, R;
   small_plan(n, &grid, &R);
-  const size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  slab = (slab + 3) & ~(size_t)3;
   return sizeof(double) * slab * ((size_t)grid + 1) + 16;   // slabs + the reduced slab + the barrier counter
 }
 
@@ -280,7 +300,8 @@ int decomp_nmf_mu_small_f64(const double* y, int64_t ldy, const double* mask, in
   int grid, R;
   small_plan(n, &grid, &R);
   const bool masked = mask != nullptr;
-  const size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  size_t slab = masked ? (size_t)2 * k * f : (size_t)k * f + (size_t)k * k;
+  slab = (slab + 3) & ~(size_t)3;
   SmallNmfArgs a;
   a.y = y;
   a.ldy = ldy;

@@ -22,7 +22,7 @@ and the final ``x`` is un-permuted the same way.
 import numpy as np
 import torch
 
-from . import ops
+from . import comm, ops
 from ._device import array_kind, empty2d, is_torch, np_dtype, require_cuda, to_device2d, to_host, zeros2d
 from ._lib import rview
 from .lasso import DEVICE_RULES, AVAILABLE_METHODS, lasso_device
@@ -268,7 +268,7 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                         ops.dl_mirror(S, k, f, cplx)
                         ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)            # :216-222
                     else:
-                        dist.reduce_scatter_tensor(S_red, S_part, group=group)                          # along f
+                        comm.reduce_scatter_sum(S_red, S_part, group)                                   # along f
                         S2, R2 = S.view(k * fs, k * cw), S_red.view(k * fs, k * cw)
                         ops.axpby(beta, S2, 1.0, R2, S2)
                         ops.dl_mirror(S, k, fs, cplx)
@@ -276,11 +276,11 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                         ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
                         # channel-local Jacobi update of this rank's slab, two [k] sums over all channels exchanged
                         ops.dl_masked_update_phase(1, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
-                        dist.all_reduce(stats, group=group)
+                        comm.all_reduce_sum(stats, group)
                         ops.dl_masked_update_phase(2, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
-                        dist.all_reduce(stats, group=group)
+                        comm.all_reduce_sum(stats, group)
                         ops.dl_masked_update_phase(3, S, j0, rview(T), rview(D), cplx, D_slab, stats, Dt_ws)
-                        dist.all_gather_into_tensor(D_all, D_slab, group=group)
+                        comm.all_gather(D_all, D_slab, group)
                         rview(Dn).copy_(D_all.permute(1, 0, 2).reshape(k, world * fs * cw)[:, :f * cw])
                 if checks:
                     ops.max_abs_diff(rview(D), rview(Dn), cplx, result, scratch)
@@ -295,9 +295,4 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
 
 def _allreduce(t, group):
     """Sum over the ranks, in place, also for row-padded (non-contiguous) buffers."""
-    if t.is_contiguous():
-        torch.distributed.all_reduce(t, group=group)
-    else:
-        flat = t.contiguous()
-        torch.distributed.all_reduce(flat, group=group)
-        t.copy_(flat)
+    return comm.all_reduce_sum(t, group)

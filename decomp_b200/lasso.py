@@ -28,7 +28,7 @@ import threading
 import numpy as np
 import torch
 
-from . import ops
+from . import comm, ops
 from ._device import (array_kind, empty2d, flatten_rows, is_torch, np_dtype, require_cuda, to_device1d,
                       to_device2d, to_host)
 from ._lib import rview
@@ -524,7 +524,7 @@ class LassoSolver(object):
         if check and self.group is not None:
             if self.B == 0:
                 self.latch.fill_(value)
-            torch.distributed.all_reduce(self.latch, op=torch.distributed.ReduceOp.MIN, group=self.group)
+            comm.all_reduce_min_i32(self.latch, self.group)
 
     def _launch_resident(self, i0, i1):
         """Iterations i0 <= i < i1 in one launch; the convergence test may only sit on the last one."""
@@ -598,8 +598,8 @@ def _global_mask_mean(mask, local_rows, group):
     dist = torch.distributed
     sums = ops.col_sums(mask, 1.0)
     rows = torch.tensor([float(local_rows)], dtype=torch.float64, device=mask.device)
-    dist.all_reduce(sums, group=group)
-    dist.all_reduce(rows, group=group)
+    comm.all_reduce_sum(sums, group)
+    comm.all_reduce_sum(rows, group)
     f = sums.numel()
     mean = torch.empty_like(sums)
     ops.scale(sums.view(1, f), mean.view(1, f), rowscale=rows, invert_row=True)

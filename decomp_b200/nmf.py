@@ -23,7 +23,7 @@ own order is kept.
 import numpy as np
 import torch
 
-from . import ops
+from . import comm, ops
 from ._device import array_kind, empty2d, full2d, is_torch, np_dtype, require_cuda, to_device2d, to_host
 from .utils import assertion
 
@@ -358,7 +358,7 @@ class MuSolver(object):
                 if mask is None:
                     ops.col_sums(X, 1.0, out=self.xsum)
                     if group is not None:
-                        torch.distributed.all_reduce(self.xsum, group=group)
+                        comm.all_reduce_sum(self.xsum, group)
                     ops.scale(self.ones_kf, NEGD, rowscale=self.xsum)
                 else:
                     ops.gemm_tn(X, mask, NEGD, workspace=ws, skip=latch)
@@ -498,9 +498,4 @@ def mu_streamed(y, D0, X, tol, maxiter, mask, block_rows):
 
 def _allreduce2d(t, group):
     """Sum a (possibly row-padded) 2-D statistic over the ranks, in place."""
-    if t.is_contiguous():
-        torch.distributed.all_reduce(t, group=group)
-    else:
-        flat = t.contiguous()
-        torch.distributed.all_reduce(flat, group=group)
-        t.copy_(flat)
+    return comm.all_reduce_sum(t, group)

@@ -322,6 +322,24 @@ int decomp_nmf_mu_small_f64(const double* y, int64_t ldy, const double* mask, in
 int decomp_staged_upload(void* dst_device, const void* src_host, size_t bytes, void* pinned_ring, size_t slot_bytes,
                          int32_t slots, int32_t threads, void* stream);
 
+/* ---- collectives of the sharded solves (thin NCCL wrappers, bound to the process's libnccl.so.2 at run time) ----
+ * One communicator per process (= per GPU).  decomp_comm_unique_id on one rank, the 128 bytes handed to every rank by
+ * the host, decomp_comm_init on all ranks.  The calls enqueue on `stream`.
+ *   all-reduce (sum, f64):    x^T y [k,f], x^T x [k,k] per NMF sweep / dictionary-learning minibatch (grads.py:117-125,
+ *                             dictionary_learning.py:147-152), the two [k] sums of the sharded masked update
+ *   all-reduce (min, i32):    the convergence latch of the batched Lasso (lasso.py:293/409: one max over ALL problems)
+ *   reduce-scatter / all-gather (f64): the masked [k,f,k] statistic along f and the new dictionary
+ *                             (dictionary_learning.py:206-222) */
+#define DECOMP_COMM_ID_BYTES 128
+int decomp_comm_unique_id(void* id_out);
+int decomp_comm_init(const void* id, int32_t nranks, int32_t rank, void** comm_out);
+int decomp_comm_destroy(void* comm);
+int decomp_comm_allreduce_sum_f64(void* comm, double* buf, int64_t count, void* stream);
+int decomp_comm_allreduce_min_i32(void* comm, int32_t* buf, int64_t count, void* stream);
+int decomp_comm_reduce_scatter_sum_f64(void* comm, const double* send, double* recv, int64_t recv_count,
+                                       void* stream);
+int decomp_comm_allgather_f64(void* comm, const double* send, double* recv, int64_t send_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

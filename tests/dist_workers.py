@@ -98,6 +98,8 @@ def gpu_sharded_dictionary_learning(rank, world, port, out):
                 it0, D_ref, x_ref = orc.dictionary_learning(yy, D0.copy(), 0.05, mask=mask if masked else None, **kw)
                 res['dl_%s_%s_mb%d' % ('c' if cplx else 'f', 'mask' if masked else 'nomask', mb)] = (
                     it, it0, rel(D, D_ref), rel(x, shard(x_ref, rank, world)))
+    from decomp_b200 import comm
+    comm.destroy_all()
     out[rank] = res
     dist.destroy_process_group()
 
@@ -130,6 +132,36 @@ def cpu_dl_row_sharding(rank, world, port, out):
 
 
 # --------------------------------------------------------------------------------------- GPU / nccl
+def gpu_comm_wrappers(rank, world, port, out):
+    """decomp_comm_* (the C ABI's NCCL wrappers) against the expected sums / slabs."""
+    _init(rank, world, port, 'nccl')
+    from decomp_b200 import comm
+    dev = torch.device('cuda', rank)
+    res = {}
+    g = dist.group.WORLD
+    t = torch.arange(12, dtype=torch.float64, device=dev).reshape(3, 4) * (rank + 1)
+    comm.all_reduce_sum(t, g)
+    res['sum'] = bool(torch.equal(t.cpu(), torch.arange(12, dtype=torch.float64).reshape(3, 4) * sum(range(1, world + 1))))
+    padded = (torch.ones((4, 6), dtype=torch.float64, device=dev) * (rank + 1))[:, :5]      # row-padded view
+    comm.all_reduce_sum(padded, g)
+    res['sum_padded'] = bool((padded.cpu() == float(sum(range(1, world + 1)))).all())
+    latch = torch.tensor([5 if rank == 0 else 0], dtype=torch.int32, device=dev)
+    comm.all_reduce_min_i32(latch, g)
+    res['min'] = int(latch.item()) == 0
+    inp = torch.stack([torch.full((2, 3), float(10 * d + rank), dtype=torch.float64, device=dev) for d in range(world)])
+    slab = torch.empty((2, 3), dtype=torch.float64, device=dev)
+    comm.reduce_scatter_sum(slab, inp, g)
+    res['reduce_scatter'] = bool((slab.cpu() == float(sum(10 * rank + r for r in range(world)))).all())
+    gathered = torch.empty((world, 2, 3), dtype=torch.float64, device=dev)
+    comm.all_gather(gathered, slab, g)
+    want = torch.stack([torch.full((2, 3), float(sum(10 * d + r for r in range(world))), dtype=torch.float64)
+                        for d in range(world)])
+    res['all_gather'] = bool(torch.equal(gathered.cpu(), want))
+    comm.destroy_all()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
 def gpu_sharded_solves(rank, world, port, out):
     """Sharded NMF (unmasked, masked) and sharded Lasso (tol > 0: global convergence decision) against the oracle."""
     _init(rank, world, port, 'nccl')
@@ -154,5 +186,7 @@ def gpu_sharded_solves(rank, world, port, out):
                                      mask=None if m is None else shard(m, rank, world), group=dist.group.WORLD)
         it0, x_ref = orc.lasso(yl, A, 0.05, tol=1e-6, method='fista', maxiter=1000, mask=m)
         res[name] = (it, it0, rel(x, shard(x_ref, rank, world)))
+    from decomp_b200 import comm
+    comm.destroy_all()
     out[rank] = res
     dist.destroy_process_group()

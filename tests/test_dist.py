@@ -32,6 +32,15 @@ def test_world_size_2_gloo_dictionary_learning_row_sharding():
 
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_world_size_2_comm_wrappers():
+    out = _spawn(dist_workers.gpu_comm_wrappers, 2)
+    assert set(out) == {0, 1}
+    for rank, res in out.items():
+        assert all(res.values()), (rank, res)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
 def test_world_size_2_nccl_sharded_solves():
     out = _spawn(dist_workers.gpu_sharded_solves, 2)
     assert set(out) == {0, 1}
