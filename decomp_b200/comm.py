@@ -53,17 +53,18 @@ def _contiguous(t):
 
 
 def all_reduce_sum(t, group):
-    """In-place sum over the ranks of a float64 tensor (row-padded 2-D views included)."""
+    """In-place sum over the ranks of a float64 / complex128 tensor (row-padded 2-D views included)."""
     if not t.is_cuda:
         flat = _contiguous(t)
         torch.distributed.all_reduce(flat, group=group)
         if flat is not t:
             t.copy_(flat)
         return t
-    assert t.dtype == torch.float64
+    assert t.dtype in (torch.float64, torch.complex128)
     flat = _contiguous(t)
+    count = flat.numel() * (2 if t.is_complex() else 1)          # complex128: interleaved doubles
     c = communicator(group)
-    _lib.check(_lib.lib().decomp_comm_allreduce_sum_f64(c.handle, ctypes.c_void_p(flat.data_ptr()), flat.numel(),
+    _lib.check(_lib.lib().decomp_comm_allreduce_sum_f64(c.handle, ctypes.c_void_p(flat.data_ptr()), count,
                                                         _lib.stream_ptr()), 'decomp_comm_allreduce_sum_f64')
     if flat is not t:
         t.copy_(flat)
