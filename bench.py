@@ -334,7 +334,8 @@ def run_ours(args):
     dmma_peak = ops.probe_dmma_tflops()
     K, W, R = max(1, args.steps), max(0, args.warmup), max(1, args.repeats)
     out = {}
-    clocks = None
+    clocks = None            # the primary leg's record
+    leg_clocks = {}          # every other timed leg, by name
     cpu_arm_mod = None
     if rank == 0 and world == 1 and 'cpu' in legs:
         from oracle import cpu_arm as cpu_arm_mod
@@ -389,7 +390,7 @@ def run_ours(args):
             solver.iterate(0, W + K)
             ms32_list, launches32, c32 = timed_regions(
                 lambda r: solver.iterate(W + K * (r + 1), W + K * (r + 2)), R32)
-            clocks = merge_clocks(clocks, c32)
+            leg_clocks['fista_tf32x3'] = c32
             ms32 = median(ms32_list)
             x32 = solver.finish().result
             ref = lasso.LassoSolver(y, A, alpha, None, 0.0, W + K * (R32 + 1), 'fista', False)
@@ -521,7 +522,6 @@ def run_ours(args):
                 solver.sweep(it)
             ms32_list, launches32, c3 = timed_regions(
                 lambda r: [solver.sweep(it) for it in range(Wn + 1 + r * Kn, Wn + 1 + (r + 1) * Kn)], Rn)
-            c2 = merge_clocks(c2, c3)
             t32 = median(ms32_list) * 1e-3 / Kn
             D32 = solver.Dbuf[(Wn + Rn * Kn) % 2]
             err = float(((D32 - D64).abs().max() / D64.abs().max()).item())
@@ -538,6 +538,7 @@ def run_ours(args):
                              'note': 'y is read once row-major (y D^T) and once transposed (x^T y), both as TF32 pairs; '
                                      'tensor side: %.3g TF32 flop per sweep = %.1f TFLOP/s' % (fl32, fl32 / t32 / 1e12),
                              'kernel': 'tf32x3_gemm_kernel<XUPD> (y D^T + ratio) and tf32x3_gemm_kernel<PARTIAL> (x^T y)'}}
+            res['tf32x3']['clocks'] = c3
             del D64, D32
         del solver, y, X, D0, D, mask
         torch.cuda.empty_cache()
@@ -549,7 +550,7 @@ def run_ours(args):
                                      '(BASELINE.json configs[2] shape, weak scaling)' % (args.rows, NMF['f'], NMF['k'])}
         res['scaling'] = 'weak'
         out['nmf'] = res
-        clocks = merge_clocks(clocks, c2)
+        leg_clocks['nmf'] = c2
     if 'nmf_strong' in legs:
         n_tot = args.strong_rows
         lo, hi = rank * n_tot // world, (rank + 1) * n_tot // world
@@ -558,7 +559,7 @@ def run_ours(args):
             res['same_run_as_secondary'] = True
         else:
             res, c2 = nmf_leg(hi - lo, 'strong', tf32='tf32' in legs)
-            clocks = merge_clocks(clocks, c2)
+            leg_clocks['nmf_strong'] = c2
         res['config'] = {'workload': 'NMF-MU l2, %d rows IN TOTAL x %d features, k=%d, float64, tol=0, sample axis '
                                      'sharded over %d GPU(s) with all-reduce of X^T Y [k,f] and X^T X [k,k] per sweep '
                                      '(BASELINE.json configs[2], strong scaling)' % (n_tot, NMF['f'], NMF['k'], world)}
@@ -597,7 +598,7 @@ def run_ours(args):
     if 'configs' in legs:
         extra = {}
         res, c2 = nmf_leg(args.c5_rows, 'weak', masked=True, shape=C5)
-        clocks = merge_clocks(clocks, c2)
+        leg_clocks['c5_masked_nmf'] = c2
         res['config'] = {'workload': 'masked NMF-MU l2, %d rows per GPU x %d, k=%d, 10 %% missing, float64 '
                                      '(BASELINE.json configs[4], per-GPU shard)' % (args.c5_rows, C5['f'], C5['k'])}
         extra['c5_masked_nmf_sweep'] = res
@@ -607,7 +608,7 @@ def run_ours(args):
         s5 = lasso.LassoSolver(y5, A5, 0.1, None, 0.0, 100000, 'fista', False, mask=m5)
         s5.iterate(0, 3)
         ms5, l5, c5 = timed_regions(lambda r: s5.iterate(3 + 5 * r, 8 + 5 * r), 3)
-        clocks = merge_clocks(clocks, c5)
+        leg_clocks['c5_masked_fista'] = c5
         t5 = median(ms5) * 1e-3 / 5
         fl5 = 4.0 * n5 * k5 * f5
         by5 = n5 * f5 * 8.0 + 5.0 * n5 * k5 * 8
@@ -740,7 +741,10 @@ def run_ours(args):
             line['extra_configs'] = out['extra_configs']
         if 'parity' in out:
             line['parity_multi_gpu'] = out['parity']
+        if clocks is None and leg_clocks:                      # no primary leg in this run
+            clocks = merge_clocks(None, list(leg_clocks.values())[0])
         line['clocks'] = clocks
+        line['clocks_other_legs'] = leg_clocks
         print(json.dumps(line))
     if world > 1:
         from decomp_b200 import comm

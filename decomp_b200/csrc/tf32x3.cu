@@ -128,6 +128,58 @@ struct Tf32Args {
   long long ldxt;
 };
 
+// one 32-column chunk of an accumulator row (already in registers) -> memory, by epilogue mode
+template <int MODE>
+__device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uint32_t (&v)[32], long long row, int n0,
+                                                    int c0, int z) {
+  if constexpr (MODE == TF_STORE || MODE == TF_PARTIAL) {
+    const long long prow = MODE == TF_PARTIAL ? (long long)z * a.M + row : row;
+    float* dst = a.P + prow * a.ldp + n0 + c0;
+    if (n0 + c0 + 32 <= a.N) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
+    }
+  } else {
+    // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here
+    double* xr = a.X + row * a.ldx + c0;
+    const float* ng = a.NEG + row * a.ldneg + c0;
+    float* xh = a.Xh + row * a.ldxh + c0;
+    float* xl = a.Xl + row * a.ldxh + c0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
+      const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
+      const float4 n4 = *reinterpret_cast<const float4*>(ng + j);
+      const double xin[4] = {x01.x, x01.y, x23.x, x23.y};
+      const float nin[4] = {n4.x, n4.y, n4.z, n4.w};
+      double r[4];
+      float h[4], l[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double pos = (double)__uint_as_float(v[j + t]);
+        r[t] = __ddiv_rn(__dmul_rn(xin[t], fmax(pos, 0.0)), fmax((double)nin[t], kEpsT));
+        split_tf32(r[t], h[t], l[t]);
+        // a warp writes 32 consecutive rows: 128 contiguous bytes in either layout
+        const long long ti = a.xt_block > 0
+                                 ? ((row / a.xt_block) * a.N + (c0 + j + t)) * a.xt_block + row % a.xt_block
+                                 : (long long)(c0 + j + t) * a.ldxt + row;
+        a.XTh[ti] = h[t];
+        a.XTl[ti] = l[t];
+      }
+      *reinterpret_cast<double2*>(xr + j) = make_double2(r[0], r[1]);
+      *reinterpret_cast<double2*>(xr + j + 2) = make_double2(r[2], r[3]);
+      *reinterpret_cast<float4*>(xh + j) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(xl + j) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -281,52 +333,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
         if (row >= a.M || n0 + c0 >= a.N) continue;
-        if constexpr (MODE == TF_STORE || MODE == TF_PARTIAL) {
-          const long long prow = MODE == TF_PARTIAL ? (long long)z * a.M + row : row;
-          float* dst = a.P + prow * a.ldp + n0 + c0;
-          if (n0 + c0 + 32 <= a.N) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
-          }
-        } else {
-          // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here
-          double* xr = a.X + row * a.ldx + c0;
-          const float* ng = a.NEG + row * a.ldneg + c0;
-          float* xh = a.Xh + row * a.ldxh + c0;
-          float* xl = a.Xl + row * a.ldxh + c0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
-            const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
-            const float4 n4 = *reinterpret_cast<const float4*>(ng + j);
-            const double xin[4] = {x01.x, x01.y, x23.x, x23.y};
-            const float nin[4] = {n4.x, n4.y, n4.z, n4.w};
-            double r[4];
-            float h[4], l[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const double pos = (double)__uint_as_float(v[j + t]);
-              r[t] = __ddiv_rn(__dmul_rn(xin[t], fmax(pos, 0.0)), fmax((double)nin[t], kEpsT));
-              split_tf32(r[t], h[t], l[t]);
-              // a warp writes 32 consecutive rows: 128 contiguous bytes in either layout
-              const long long ti = a.xt_block > 0
-                                       ? ((row / a.xt_block) * a.N + (c0 + j + t)) * a.xt_block + row % a.xt_block
-                                       : (long long)(c0 + j + t) * a.ldxt + row;
-              a.XTh[ti] = h[t];
-              a.XTl[ti] = l[t];
-            }
-            *reinterpret_cast<double2*>(xr + j) = make_double2(r[0], r[1]);
-            *reinterpret_cast<double2*>(xr + j + 2) = make_double2(r[2], r[3]);
-            *reinterpret_cast<float4*>(xh + j) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(xl + j) = make_float4(l[0], l[1], l[2], l[3]);
-          }
-        }
+        tf32_epilogue_chunk<MODE>(a, v, row, n0, c0, z);
       }
       tc_fence_before();
       __syncwarp();
@@ -342,6 +349,260 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair GEMM
+// The same GEMM with tcgen05.mma.cta_group::2: two CTAs of a cluster (the two SMs of a TPC) compute one 256 x N tile.
+// Each CTA stages ITS 128 rows of A and ITS half of B's rows; the pair's MMA (issued by the leader CTA only, M = 256)
+// reads A from each CTA's own shared memory and the two halves of B from both.  A stage is 64 KB instead of 96 KB
+// (three stages fit instead of two) and each SM ingests 64 KB per k-block instead of 96 KB -- the operand stream into
+// the SM, not the tensor pipe, is what bounds the single-CTA kernel.
+// Barrier protocol (as in the public sm_100 2-SM GEMMs): full[s] lives in the leader, count 2 (one arrival per CTA's
+// producer), both CTAs' TMA loads complete_tx on it; empty[s] and acc_full[b] exist in both CTAs and are signalled
+// by the leader's tcgen05.commit multicast; acc_empty[b] lives in the leader, count 8 (4 epilogue warps x 2 CTAs).
+constexpr int T2_STAGES = 3;
+constexpr int T2_HALF_N_BYTES = (TNMAX / 2) * TBK * 4;                   // 16 KB: this CTA's half of a B box
+constexpr int T2_STAGE_BYTES = 2 * TA_BYTES + 2 * T2_HALF_N_BYTES;        // 64 KB
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 16 * 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory pointer of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory, completion signalled on a barrier given as a shared::cluster address
+// (the leader's): the .cta_group::2 form allows the barrier to sit in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                 int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same offset in both CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                        const Tf32Args a, const int* __restrict__ skip_if) {
+  if (skip_if != nullptr && *skip_if != 0) return;     // uniform over the grid: both CTAs of a pair leave together
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + T2_STAGES;
+  uint64_t* acc_full = empty_bar + T2_STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int N = a.mma_n, NH = N / 2;             // this CTA stages NH rows of each B box
+  const int tiles_m2 = (a.M + 2 * TBM - 1) / (2 * TBM);
+  const int tiles_mn = tiles_m2 * a.tiles_n;
+  const int items = tiles_mn * a.splits;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * N)) cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);      // used in the leader: one arrival per CTA's producer
+      mbar_init(&empty_bar[s], 1);     // one multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);      // one multicast commit
+      mbar_init(&acc_empty[b], 8);     // used in the leader: 4 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAh);
+    tma_prefetch_desc(&tmAl);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmBl);
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                  // the peer's barriers are initialised before anything is signalled on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb, int& z) {
+    const int tm = item % tiles_m2;
+    const int tn = (item / tiles_m2) % a.tiles_n;
+    z = item / tiles_mn;
+    m0 = tm * 2 * TBM;
+    n0 = tn * N;
+    kb0 = z * a.kb_per_split;
+    nkb = a.kb_total - kb0 < a.kb_per_split ? a.kb_total - kb0 : a.kb_per_split;
+  };
+  const int first = (int)cluster_id_x(), stride = (int)num_clusters_x();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t pair_bytes = 2u * (2u * TA_BYTES + 2u * (uint32_t)NH * TBK * 4u);
+      for (int item = first; item < items; item += stride) {
+        int m0, n0, kb0, nkb, z;
+        decode(item, m0, n0, kb0, nkb, z);
+        const int am = m0 + (int)rank * TBM, bn = n0 + (int)rank * NH;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const uint32_t lead_full = mapa_u32(&full_bar[s], 0);
+          unsigned char* st = smem + s * T2_STAGE_BYTES;
+          if (a.blocked) {
+            const int k0 = kb * TBK;
+            tma_load_3d_pair(st, &tmAh, lead_full, k0, am, z);
+            tma_load_3d_pair(st + TA_BYTES, &tmAl, lead_full, k0, am, z);
+            tma_load_3d_pair(st + 2 * TA_BYTES, &tmBh, lead_full, k0, bn, z);
+            tma_load_3d_pair(st + 2 * TA_BYTES + T2_HALF_N_BYTES, &tmBl, lead_full, k0, bn, z);
+          } else {
+            const int k0 = (kb0 + kb) * TBK;
+            tma_load_2d_pair(st, &tmAh, lead_full, k0, am);
+            tma_load_2d_pair(st + TA_BYTES, &tmAl, lead_full, k0, am);
+            tma_load_2d_pair(st + 2 * TA_BYTES, &tmBh, lead_full, k0, bn);
+            tma_load_2d_pair(st + 2 * TA_BYTES + T2_HALF_N_BYTES, &tmBl, lead_full, k0, bn);
+          }
+          if (leader)
+            mbar_arrive_expect_tx(&full_bar[s], pair_bytes);
+          else
+            mbar_arrive_remote(lead_full);
+          if (++s == T2_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M = 256 >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * TBM) >> 4) << 24);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = first; item < items; item += stride) {
+      int m0, n0, kb0, nkb, z;
+      decode(item, m0, n0, kb0, nkb, z);
+      mbar_wait(&acc_empty[acc], acc_ph ^ 1u);   // both CTAs' epilogues have drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_hi = smem_u32(smem + s * T2_STAGE_BYTES);
+          const uint32_t a_lo = a_hi + TA_BYTES;
+          const uint32_t b_hi = a_hi + 2 * TA_BYTES;
+          const uint32_t b_lo = b_hi + T2_HALF_N_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) {
+            const uint32_t off = (uint32_t)k * 32u;
+            const uint64_t dah = umma_desc_k_sw128(a_hi + off), dal = umma_desc_k_sw128(a_lo + off);
+            const uint64_t dbh = umma_desc_k_sw128(b_hi + off), dbl = umma_desc_k_sw128(b_lo + off);
+            umma_tf32_pair(tmem_d, dal, dbh, idesc, (kb | k) != 0 ? 1u : 0u);   // small terms first
+            umma_tf32_pair(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32_pair(tmem_d, dah, dbh, idesc, 1u);
+          }
+          tc_commit_pair(&empty_bar[s]);                      // both CTAs may refill the stage
+          if (kb == nkb - 1) tc_commit_pair(&acc_full[acc]);  // both CTAs' epilogues may read their half
+        }
+        __syncwarp();
+        if (++s == T2_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+    const int e = warp - 4;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int item = first; item < items; item += stride) {
+      int m0, n0, kb0, nkb, z;
+      decode(item, m0, n0, kb0, nkb, z);
+      const long long row = (long long)m0 + (long long)rank * TBM + e * 32 + lane;
+      mbar_wait(&acc_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * N);
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        if (row >= a.M || n0 + c0 >= a.N) continue;
+        tf32_epilogue_chunk<MODE>(a, v, row, n0, c0, z);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_u32(&acc_empty[acc], 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_ph ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                  // nobody frees tensor memory or leaves while the peer still uses the pair
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
   }
 }
 
