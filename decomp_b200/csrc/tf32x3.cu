@@ -20,6 +20,7 @@
 // Per iteration: GEMM reads 2 x 4 B and writes 4 B per element, the pass reads 4 + 8 + 8 B and writes 8 + 4 + 4 B:
 // 48 B per element against 40 B for the fused FP64 launch, but nothing is bound by the FP64 tensor pipe any more.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -820,21 +821,47 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   // (a K-blocked operand keeps its block length whatever K is: the tensor map is built from kb_per_split)
   if (!a.blocked && a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
   a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  // CTA pairs (tcgen05.mma.cta_group::2) when there are at least two 128-row tiles: each CTA stages half of B
+  static const bool pair_enabled = [] {
+    const char* e = getenv("DECOMP_TF32_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool pair = pair_enabled && a.M > TBM && num_sms() >= 2;
+  const uint32_t b_box = pair ? (uint32_t)a.mma_n / 2 : (uint32_t)a.mma_n;
   CUtensorMap tah, tal, tbh, tbl;
   int rc;
   if (a.blocked) {
     const uint64_t block = (uint64_t)a.kb_per_split * TBK, blocks = (uint64_t)a.splits;
     rc = make_map_f32_blocked(&tah, A_hi, block, (uint64_t)a.M, blocks, TBM);
     if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tal, A_lo, block, (uint64_t)a.M, blocks, TBM);
-    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbh, B_hi, block, (uint64_t)a.N, blocks, (uint32_t)a.mma_n);
-    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbl, B_lo, block, (uint64_t)a.N, blocks, (uint32_t)a.mma_n);
+    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbh, B_hi, block, (uint64_t)a.N, blocks, b_box);
+    if (rc == DECOMP_OK) rc = make_map_f32_blocked(&tbl, B_lo, block, (uint64_t)a.N, blocks, b_box);
   } else {
     rc = make_map_f32(&tah, A_hi, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
     if (rc == DECOMP_OK) rc = make_map_f32(&tal, A_lo, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda, TBM);
-    if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
-    if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, (uint32_t)a.mma_n);
+    if (rc == DECOMP_OK) rc = make_map_f32(&tbh, B_hi, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, b_box);
+    if (rc == DECOMP_OK) rc = make_map_f32(&tbl, B_lo, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)ldb, b_box);
   }
   if (rc != DECOMP_OK) return rc;
+  if (pair) {
+    auto kern2 = tf32x3_gemm_pair_kernel<MODE>;
+    static bool configured2 = false;   // per instantiation
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 pair smem)");
+      configured2 = true;
+    }
+    const long long tiles_m2 = (a.M + 2 * TBM - 1) / (2 * TBM);
+    const long long items2 = tiles_m2 * a.tiles_n * a.splits;
+    if (items2 > 2147483647LL) {
+      set_error("tf32x3 GEMM: too many tiles");
+      return DECOMP_ERR_INVALID;
+    }
+    long long clusters = num_sms() / 2;
+    if (clusters > items2) clusters = items2;
+    kern2<<<(unsigned)(2 * clusters), 256, T2_SMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
+    return check_cuda(cudaGetLastError(), "tf32x3 pair gemm launch");
+  }
   auto kern = tf32x3_gemm_kernel<MODE>;
   static bool configured = false;   // per instantiation
   if (!configured) {
