@@ -116,18 +116,33 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
         __syncwarp();
       }
       double mine_pos = 0.0, mine_neg = 0.0;   // lane c ends up with the sums of atom c
-      for (int c = 0; c < k; ++c) {
-        const double* dc = D_s + c * f;
-        double p = 0.0, q = 0.0;
-        for (int j = lane; j < f; j += 32) {
-          p += yr[j] * dc[j];
-          if (MASKED) q += F_s[r * f + j] * dc[j];
+      // eight atoms at a time: one pass over the row feeds eight independent accumulator chains
+      for (int c0 = 0; c0 < k; c0 += 8) {
+        double p[8], q[8];
+        const double* dc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          p[u] = q[u] = 0.0;
+          dc[u] = D_s + (c0 + u < k ? c0 + u : k - 1) * f;
         }
-        p = warp_sum_s(p);
-        if (MASKED) q = warp_sum_s(q);
-        if (lane == c) {
-          mine_pos = p;
-          mine_neg = q;
+        for (int j = lane; j < f; j += 32) {
+          const double yv = yr[j];
+          const double fv = MASKED ? F_s[r * f + j] : 0.0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double d = dc[u][j];
+            p[u] += yv * d;
+            if (MASKED) q[u] += fv * d;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          p[u] = warp_sum_s(p[u]);
+          if (MASKED) q[u] = warp_sum_s(q[u]);
+          if (lane == c0 + u) {
+            mine_pos = p[u];
+            mine_neg = q[u];
+          }
         }
       }
       if (!MASKED && lane < k) {
@@ -197,16 +212,25 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
       for (int e = tid; e < k * k; e += SMALL_THREADS) G_s[e] = __ldcg(total + k * f + e);   // S = x^T x
       __syncthreads();
     }
-    for (int e = tid; e < k * f; e += SMALL_THREADS) {
-      const int c = e / f, j = e % f;
-      double den;
-      if (MASKED) {
-        den = __ldcg(total + k * f + e);
-      } else {
-        den = 0.0;
-        for (int b = 0; b < k; ++b) den += G_s[c * k + b] * D_s[b * f + j];
+    for (int e0 = tid; e0 < k * f; e0 += 4 * SMALL_THREADS) {      // four entries per thread in flight
+      double den[4], num[4];
+      int ee[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * SMALL_THREADS;
+        ee[u] = e < k * f ? e : k * f - 1;
+        num[u] = __ldcg(total + ee[u]);
+        den[u] = MASKED ? __ldcg(total + k * f + ee[u]) : 0.0;
       }
-      Dn_s[e] = D_s[e] * fmax(__ldcg(total + e), 0.0) / fmax(den, kEpsS);
+      if (!MASKED) {
+        for (int b = 0; b < k; ++b) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) den[u] += G_s[(ee[u] / f) * k + b] * D_s[b * f + ee[u] % f];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u * SMALL_THREADS < k * f) Dn_s[ee[u]] = D_s[ee[u]] * fmax(num[u], 0.0) / fmax(den[u], kEpsS);
     }
     __syncthreads();
     double md = 0.0;

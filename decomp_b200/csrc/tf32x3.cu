@@ -95,7 +95,6 @@ __global__ void split_tf32_kernel(const double* __restrict__ A, long long lda, l
 
 // ------------------------------------------------------------------------------------------------ GEMM
 constexpr int TBM = 128, TBK = 32, TSTAGES = 2, TNMAX = 256;
-constexpr int TF_PREFETCH = 6;                    // k-blocks the L2 prefetch runs ahead of the shared-memory ring
 constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int TB_BYTES = TNMAX * TBK * 4;        // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;   // 96 KB
@@ -111,7 +110,6 @@ struct Tf32Args {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
   int mma_n;              // N of one MMA = rows of one B box (multiple of 32, <= 256); tiles_n boxes cover N
-  int prefetch_b;         // row-major B is streamed from HBM too (large N): prefetch it like A (a small B lives in L2)
   int blocked;            // operands stored K-blocked, [K / kblock][rows][kblock] with kblock = 32 kb_per_split: split z
                           // reads block z (3-D tensor maps).  A sample-axis contraction over row-major x^T, y^T would
                           // touch one 128-byte piece per row 4 n bytes apart -- hundreds of pages per TMA box
@@ -248,30 +246,10 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = 2u * TA_BYTES + 2u * (uint32_t)N * TBK * 4u;
-      auto prefetch = [&](int m0, int n0, int kb0, int kb, int z) {
-        if (a.blocked) {
-          tma_prefetch_l2_3d(&tmAh, kb * TBK, m0, z);
-          tma_prefetch_l2_3d(&tmAl, kb * TBK, m0, z);
-          tma_prefetch_l2_3d(&tmBh, kb * TBK, n0, z);
-          tma_prefetch_l2_3d(&tmBl, kb * TBK, n0, z);
-        } else {
-          tma_prefetch_l2_2d(&tmAh, (kb0 + kb) * TBK, m0);
-          tma_prefetch_l2_2d(&tmAl, (kb0 + kb) * TBK, m0);
-          if (a.prefetch_b) {
-            tma_prefetch_l2_2d(&tmBh, (kb0 + kb) * TBK, n0);
-            tma_prefetch_l2_2d(&tmBl, (kb0 + kb) * TBK, n0);
-          }
-        }
-      };
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int m0, n0, kb0, nkb, z;
         decode(item, m0, n0, kb0, nkb, z);
-        // The ring holds two k-blocks; a k-block fetched from HBM arrives ~1.8 us after it is requested (ncu: no unit
-        // above 46 %, the kernel waits on latency), so the operands are pulled into L2 TF_PREFETCH k-blocks ahead of
-        // the ring: the ring's own loads then see L2 latency.
-        for (int kb = 0; kb < TF_PREFETCH && kb < nkb; ++kb) prefetch(m0, n0, kb0, kb, z);
         for (int kb = 0; kb < nkb; ++kb) {
-          if (kb + TF_PREFETCH < nkb) prefetch(m0, n0, kb0, kb + TF_PREFETCH, z);
           mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], bytes);
           unsigned char* st = smem + s * TSTAGE_BYTES;
@@ -517,28 +495,11 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
       int s = 0;
       uint32_t ph = 0;
       const uint32_t pair_bytes = 2u * (2u * TA_BYTES + 2u * (uint32_t)NH * TBK * 4u);
-      auto prefetch = [&](int am, int bn, int kb0, int kb, int z) {   // L2 prefetch ahead of the ring, see above
-        if (a.blocked) {
-          tma_prefetch_l2_3d(&tmAh, kb * TBK, am, z);
-          tma_prefetch_l2_3d(&tmAl, kb * TBK, am, z);
-          tma_prefetch_l2_3d(&tmBh, kb * TBK, bn, z);
-          tma_prefetch_l2_3d(&tmBl, kb * TBK, bn, z);
-        } else {
-          tma_prefetch_l2_2d(&tmAh, (kb0 + kb) * TBK, am);
-          tma_prefetch_l2_2d(&tmAl, (kb0 + kb) * TBK, am);
-          if (a.prefetch_b) {
-            tma_prefetch_l2_2d(&tmBh, (kb0 + kb) * TBK, bn);
-            tma_prefetch_l2_2d(&tmBl, (kb0 + kb) * TBK, bn);
-          }
-        }
-      };
       for (int item = first; item < items; item += stride) {
         int m0, n0, kb0, nkb, z;
         decode(item, m0, n0, kb0, nkb, z);
         const int am = m0 + (int)rank * TBM, bn = n0 + (int)rank * NH;
-        for (int kb = 0; kb < TF_PREFETCH && kb < nkb; ++kb) prefetch(am, bn, kb0, kb, z);
         for (int kb = 0; kb < nkb; ++kb) {
-          if (kb + TF_PREFETCH < nkb) prefetch(am, bn, kb0, kb + TF_PREFETCH, z);
           mbar_wait(&empty_bar[s], ph ^ 1u);
           const uint32_t lead_full = mapa_u32(&full_bar[s], 0);
           unsigned char* st = smem + s * T2_STAGE_BYTES;
@@ -860,7 +821,6 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   // (a K-blocked operand keeps its block length whatever K is: the tensor map is built from kb_per_split)
   if (!a.blocked && a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
   a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
-  a.prefetch_b = (double)a.N * (double)a.K * 8.0 > 32.0e6 ? 1 : 0;
   // CTA pairs (tcgen05.mma.cta_group::2) when there are at least two 128-row tiles: each CTA stages half of B
   static const bool pair_enabled = [] {
     const char* e = getenv("DECOMP_TF32_PAIR");
