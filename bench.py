@@ -135,6 +135,19 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def tf32_peak():
+    """Dense TF32 tensor rate (TFLOP/s) for a kernel timed inside a long step: half of the measured sustained bf16
+    rate (kind::tf32 runs at half the kind::f16 rate; MEASURED_PEAKS.json has no TF32 entry), else the nominal 1100."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        if p.get('bf16_tflops_sustained'):
+            return 0.5 * float(p['bf16_tflops_sustained']), ('half of MEASURED_PEAKS.json bf16_tflops_sustained (%.1f); '
+                                                             'no TF32 entry there' % float(p['bf16_tflops_sustained']))
+    return 1100.0, 'nominal dense TF32 (B200_PROFILING.md)'
+
+
 def load_traffic():
     """dram bytes per launch of the dominant kernels, from the committed ncu --set full captures (profiles/)."""
     path = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
@@ -330,6 +343,7 @@ def run_ours(args):
         return max_over_ranks(median(times)), times
 
     hbm_peak, hbm_src = load_peaks()
+    tf_peak, tf_src = tf32_peak()
     traffic = load_traffic()
     dmma_peak = ops.probe_dmma_tflops()
     K, W, R = max(1, args.steps), max(0, args.warmup), max(1, args.repeats)
@@ -532,12 +546,18 @@ def run_ours(args):
                 'launches': launches32, 'dtype': 'tf32x3 GEMMs (tcgen05, FP32 accumulate in TMEM, FP64 slab sums) + f64 updates',
                 'max_rel_diff_D_vs_fp64': err, 'sweeps_compared': Wn + Rn * Kn,
                 'speedup_vs_fp64': t_sweep / t32,
-                'roofline': {'bound': 'hbm', 'achieved': by32 / t32 / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                             'frac': by32 / t32 / 1e9 / hbm_peak, 'traffic': traffic.get('nmf_tf32x3_sweep_dram_bytes'),
-                             'algorithmic_bytes_per_sweep': by32,
-                             'note': 'y is read once row-major (y D^T) and once transposed (x^T y), both as TF32 pairs; '
-                                     'tensor side: %.3g TF32 flop per sweep = %.1f TFLOP/s' % (fl32, fl32 / t32 / 1e12),
-                             'kernel': 'tf32x3_gemm_kernel<XUPD> (y D^T + ratio) and tf32x3_gemm_kernel<PARTIAL> (x^T y)'}}
+                'roofline': {'bound': 'tensor', 'achieved': fl32 / t32 / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                             'frac': fl32 / t32 / 1e12 / tf_peak, 'traffic': traffic.get('nmf_tf32x3_sweep_dram_bytes'),
+                             'peak_source': tf_src,
+                             'algorithmic_flops_per_sweep': fl32,
+                             'note': 'three TF32 products per FP64-equivalent product (hi*hi + hi*lo + lo*hi): 3 x (4nkf + '
+                                     '4nk^2) flop; the tensor pipe under the power cap bounds the sweep, HBM does not',
+                             'kernel': 'tf32x3_gemm_pair_kernel<XUPD> (y D^T + ratio) and <PARTIAL> (x^T y), '
+                                       'tcgen05.mma.cta_group::2.kind::tf32',
+                             'hbm': {'algorithmic_bytes_per_sweep': by32, 'achieved_gbs': by32 / t32 / 1e9,
+                                     'peak_gbs': hbm_peak, 'frac': by32 / t32 / 1e9 / hbm_peak,
+                                     'note': 'y is read once row-major (y D^T) and once transposed (x^T y), both as '
+                                             'TF32 pairs'}}}
             res['tf32x3']['clocks'] = c3
             del D64, D32
         del solver, y, X, D0, D, mask
