@@ -63,12 +63,12 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
   const int slab = (slab_len + 3) & ~3;                      // slab pitch: 32-byte aligned for the reduction's loads
   double* D_s = sm;                     // [k][f]
   double* Dn_s = D_s + k * f;           // [k][f]
-  double* G_s = Dn_s + k * f;           // [k][k]  D D^T (unmasked) / reduced S (unmasked)
+  double* G_s = Dn_s + k * f;           // [k][k]  the reduced S = x^T x (unmasked)
   double* y_s = G_s + k * k;            // [R][f]  y (masked: y * mask)
   double* x_s = y_s + R * f;            // [R][k]
   double* m_s = x_s + R * k;            // [R][f]  mask                     (masked only)
-  double* F_s = m_s + (MASKED ? R * f : 0);   // [R][f]  (x D) * mask         (masked only)
-  double* red = F_s + (MASKED ? R * f : 0);   // [32]
+  double* F_s = m_s + (MASKED ? R * f : 0);   // [R][f]  x D (masked: (x D) * mask)
+  double* red = F_s + R * f;                  // [32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * R;
   const int rows = row0 < n ? (n - row0 < R ? n - row0 : R) : 0;
@@ -92,29 +92,17 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
   int converged_at = 0;
   for (int it = 1; it <= a.sweeps; ++it) {
     // ---------------------------------------------------------------- x update of this CTA's rows
-    if (!MASKED) {
-      for (int e = warp; e < k * k; e += SMALL_THREADS / 32) {     // one warp per entry of D D^T
-        const double* da = D_s + (e / k) * f;
-        const double* db = D_s + (e % k) * f;
-        double s = 0.0;
-        for (int j = lane; j < f; j += 32) s += da[j] * db[j];
-        s = warp_sum_s(s);
-        if (lane == 0) G_s[e] = s;
-      }
-      __syncthreads();
-    }
     for (int r = warp; r < rows; r += SMALL_THREADS / 32) {
       const double* yr = y_s + r * f;
       double* xr = x_s + r * k;
-      if (MASKED) {
-        // F = (x D) * mask for the row (grads.py:112-115)
-        for (int j = lane; j < f; j += 32) {
-          double s = 0.0;
-          for (int b = 0; b < k; ++b) s += xr[b] * D_s[b * f + j];
-          F_s[r * f + j] = s * m_s[r * f + j];
-        }
-        __syncwarp();
+      // F = x D for the row, times the mask if there is one (grads.py:110, 112-115): the denominator is F D^T in
+      // the reference's own association (no D D^T)
+      for (int j = lane; j < f; j += 32) {
+        double s = 0.0;
+        for (int b = 0; b < k; ++b) s += xr[b] * D_s[b * f + j];
+        F_s[r * f + j] = MASKED ? s * m_s[r * f + j] : s;
       }
+      __syncwarp();
       double mine_pos = 0.0, mine_neg = 0.0;   // lane c ends up with the sums of atom c
       // eight atoms at a time: one pass over the row feeds eight independent accumulator chains
       for (int c0 = 0; c0 < k; c0 += 8) {
@@ -127,28 +115,23 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
         }
         for (int j = lane; j < f; j += 32) {
           const double yv = yr[j];
-          const double fv = MASKED ? F_s[r * f + j] : 0.0;
+          const double fv = F_s[r * f + j];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const double d = dc[u][j];
             p[u] += yv * d;
-            if (MASKED) q[u] += fv * d;
+            q[u] += fv * d;
           }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           p[u] = warp_sum_s(p[u]);
-          if (MASKED) q[u] = warp_sum_s(q[u]);
+          q[u] = warp_sum_s(q[u]);
           if (lane == c0 + u) {
             mine_pos = p[u];
             mine_neg = q[u];
           }
         }
-      }
-      if (!MASKED && lane < k) {
-        double q = 0.0;
-        for (int b = 0; b < k; ++b) q += xr[b] * G_s[b * k + lane];   // x (D D^T)
-        mine_neg = q;
       }
       __syncwarp();
       if (lane < k) xr[lane] = xr[lane] * fmax(mine_pos, 0.0) / fmax(mine_neg, kEpsS);
@@ -274,7 +257,7 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
 }
 
 static size_t small_smem_bytes(int f, int k, int R, bool masked) {
-  return sizeof(double) * ((size_t)2 * k * f + (size_t)k * k + (size_t)R * f * (masked ? 3 : 1) + (size_t)R * k + 32);
+  return sizeof(double) * ((size_t)2 * k * f + (size_t)k * k + (size_t)R * f * (masked ? 3 : 2) + (size_t)R * k + 32);
 }
 
 static void small_plan(int64_t n, int* grid, int* R) {
