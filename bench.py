@@ -564,14 +564,28 @@ def run_ours(args):
         torch.cuda.empty_cache()
         return res, c2
 
-    if 'nmf' in legs:
+    def guarded(name, fn):
+        """Runs a secondary leg; an exception (raised on every rank alike: the legs are deterministic) is recorded
+        under the leg's key instead of costing the primary line."""
+        try:
+            fn()
+        except Exception as exc:                                    # noqa: BLE001
+            import traceback
+            out.setdefault('errors', {})[name] = '%s: %s' % (type(exc).__name__, str(exc)[:300])
+            sys.stderr.write('leg %s failed:\n%s\n' % (name, traceback.format_exc()))
+            torch.cuda.empty_cache()
+
+    def leg_nmf():
         res, c2 = nmf_leg(args.rows, 'weak', tf32='tf32' in legs)
         res['config'] = {'workload': 'NMF-MU l2, %d rows per GPU x %d features, k=%d, float64, tol=0 '
                                      '(BASELINE.json configs[2] shape, weak scaling)' % (args.rows, NMF['f'], NMF['k'])}
         res['scaling'] = 'weak'
         out['nmf'] = res
         leg_clocks['nmf'] = c2
-    if 'nmf_strong' in legs:
+
+    if 'nmf' in legs:
+        guarded('nmf', leg_nmf)
+    def leg_nmf_strong():
         n_tot = args.strong_rows
         lo, hi = rank * n_tot // world, (rank + 1) * n_tot // world
         if world == 1 and 'nmf' in out and args.rows == n_tot:
@@ -586,7 +600,10 @@ def run_ours(args):
         res['scaling'] = 'strong'
         res['sweeps_per_s'] = res['iters_per_s']
         out['nmf_strong'] = res
-    if 'nmf_e2e' in legs:
+
+    if 'nmf_strong' in legs:
+        guarded('nmf_strong', leg_nmf_strong)
+    def leg_nmf_e2e():
         n_e, f, k = args.e2e_nmf_rows, NMF['f'], NMF['k']
         y_d, D0_d, _ = nmf_data_device(torch, n_e, f, k, rank, device)
         y_np, D_np = y_d.cpu().numpy(), D0_d.cpu().numpy()
@@ -614,9 +631,12 @@ def run_ours(args):
         del y_np, D_np, D_e, x_e
         torch.cuda.empty_cache()
 
+    if 'nmf_e2e' in legs:
+        guarded('nmf_e2e', leg_nmf_e2e)
+
     # ---------------------------------------------------------------- BASELINE configs[3] and [4]
-    if 'configs' in legs:
-        extra = {}
+    def leg_configs():
+        extra = out.setdefault('extra_configs', {})        # filled in place: a failure keeps what was measured
         res, c2 = nmf_leg(args.c5_rows, 'weak', masked=True, shape=C5)
         leg_clocks['c5_masked_nmf'] = c2
         res['config'] = {'workload': 'masked NMF-MU l2, %d rows per GPU x %d, k=%d, 10 %% missing, float64 '
@@ -706,11 +726,16 @@ def run_ours(args):
             dt = time.perf_counter() - t0
             extra['c1_nmf_small']['cpu_baseline'] = {'value': 100.0 / dt, 'unit': 'sweeps/s', 'cores': cpu_cores,
                                                      'kind': cpu.kind, 'sample': 'the same call (%.3f s), %s' % (dt, cpu.where)}
-        out['extra_configs'] = extra
+
+    if 'configs' in legs:
+        guarded('configs', leg_configs)
 
     # ---------------------------------------------------------------- multi-GPU parity self-check (outside timing)
-    if 'parity' in legs:
+    def leg_parity():
         out['parity'] = parity_check(np, torch, dist, world, rank, group, device)
+
+    if 'parity' in legs:
+        guarded('parity', leg_parity)
 
     # ---------------------------------------------------------------- CPU baselines (rank 0, N = 1 only)
     cpu_f = cpu_n = None
@@ -761,6 +786,8 @@ def run_ours(args):
             line['extra_configs'] = out['extra_configs']
         if 'parity' in out:
             line['parity_multi_gpu'] = out['parity']
+        if 'errors' in out:
+            line['leg_errors'] = out['errors']
         if clocks is None and leg_clocks:                      # no primary leg in this run
             clocks = merge_clocks(None, list(leg_clocks.values())[0])
         line['clocks'] = clocks

@@ -147,24 +147,30 @@ __device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uin
         if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
     }
   } else {
-    // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here
+    // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here.
+    // All loads of the chunk are issued before its first store: x is updated in place, so the compiler may not move
+    // a load above an earlier store by itself, and a thread that alternates 16-byte loads and stores pays one DRAM
+    // round trip per four columns (the epilogue, not the MMAs, was then the critical path of this mode).
     double* xr = a.X + row * a.ldx + c0;
     const float* ng = a.NEG + row * a.ldneg + c0;
     float* xh = a.Xh + row * a.ldxh + c0;
     float* xl = a.Xl + row * a.ldxh + c0;
+    double2 xin[16];
+    float4 nin[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) xin[j] = *reinterpret_cast<const double2*>(xr + 2 * j);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) nin[j] = *reinterpret_cast<const float4*>(ng + 4 * j);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const double2 x01 = *reinterpret_cast<const double2*>(xr + j);
-      const double2 x23 = *reinterpret_cast<const double2*>(xr + j + 2);
-      const float4 n4 = *reinterpret_cast<const float4*>(ng + j);
-      const double xin[4] = {x01.x, x01.y, x23.x, x23.y};
-      const float nin[4] = {n4.x, n4.y, n4.z, n4.w};
+      const double xv[4] = {xin[j / 2].x, xin[j / 2].y, xin[j / 2 + 1].x, xin[j / 2 + 1].y};
+      const float nv[4] = {nin[j / 4].x, nin[j / 4].y, nin[j / 4].z, nin[j / 4].w};
       double r[4];
       float h[4], l[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const double pos = (double)__uint_as_float(v[j + t]);
-        r[t] = __ddiv_rn(__dmul_rn(xin[t], fmax(pos, 0.0)), fmax((double)nin[t], kEpsT));
+        r[t] = __ddiv_rn(__dmul_rn(xv[t], fmax(pos, 0.0)), fmax((double)nv[t], kEpsT));
         split_tf32(r[t], h[t], l[t]);
         // a warp writes 32 consecutive rows: 128 contiguous bytes in either layout
         const long long ti = a.xt_block > 0

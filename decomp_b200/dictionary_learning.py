@@ -58,7 +58,7 @@ def solve(y, D, alpha, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method=
 
     if minibatch is None:
         raise NotImplementedError('Only online methods are implemented. minibatch is required.')
-    if y.shape[0] < minibatch:
+    if group is None and y.shape[0] < minibatch:        # (sharded: checked against the total row count below)
         raise ValueError('Minibatch size should be smaller than the total size. Given {} < {}'.format(
             y.shape[0], minibatch))
     if method != 'block_cd':
