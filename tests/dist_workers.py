@@ -89,7 +89,7 @@ def gpu_sharded_dictionary_learning(rank, world, port, out):
     for cplx in (False, True):
         y, D0, mask = gc._dl_data(230, 33, 12, 9, cplx)
         for masked in (False, True):
-            for mb, tol in ((63, 0.0), (20, 1e-3)):
+            for mb, tol in ((63, 0.0), (20, 1e-3), (150, 0.0)):      # 150: more than the 115 rows a rank holds
                 yy = y * mask if masked else y
                 kw = dict(tol=tol, minibatch=mb, maxiter=3, lasso_method='fista', lasso_iter=10, lasso_tol=1.0e-5,
                           random_seed=4)
