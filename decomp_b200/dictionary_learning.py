@@ -180,11 +180,17 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
         Wt = empty2d(widest * cw, minibatch, False, dev)     # transposed pair products: contraction index contiguous
         Xt = empty2d(k * cw, minibatch, False, dev)          # transposed codes and mask of the minibatch
         Mt = empty2d(f, minibatch, False, dev)
-        Ptmp = empty2d(f, widest, cplx, dev)
         ws = ops.gemm_tn_workspace_for([(k * cw, f * cw, minibatch)], dev)
-        if sharded:
-            S_part = torch.zeros((world, k, fs, k * cw), dtype=torch.float64, device=dev)   # reduce-scatter input
-            S_red = torch.empty((k, fs, k * cw), dtype=torch.float64, device=dev)
+        if not sharded:
+            Ptmp = empty2d(f, widest, cplx, dev)
+        else:
+            # the packed pair statistics [f, pairs] of a chunk are reduce-scattered ALONG f as they are (only the
+            # Hermitian half crosses the links, and no dense [k, f, k] send buffer exists): contiguous send buffers
+            # of fs * world rows (rows beyond f stay zero), one per distinct chunk width
+            # (row pitch rounded up to an even number of doubles: the GEMM epilogue stores 16-byte pairs)
+            Psend = {wd: torch.zeros((fs * world, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev)
+                     for wd in set(c[0].numel() for c in chunks)}
+            Precv = {wd: torch.empty((fs, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev) for wd in Psend}
             stats = torch.zeros(k * 4, dtype=torch.float64, device=dev)
             D_slab = torch.zeros((k, fs * cw), dtype=torch.float64, device=dev)
             D_all = torch.empty((world, k, fs * cw), dtype=torch.float64, device=dev)
@@ -245,32 +251,35 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                 else:
                     # ---- S[a][j][b] = sum_i conj(x_ia) x_ib m_ij (:210-213) is Hermitian in (a, b): accumulate b >= a as
                     # NT GEMMs  mask^T [f, rows] . Wt [pairs, rows]^T, mirror the rest.  Sharded: every rank forms its
-                    # rows' contribution to ALL channels, laid out as one slab per destination rank
-                    S_dst = S if not sharded else S_part
+                    # rows' contribution to ALL channels of a chunk of pairs; the chunk is reduce-scattered along f and
+                    # each rank folds its channels into its slab of S
                     T_dst = T if not sharded else T_part
                     comb = stat_combine if not sharded else stat_combine - 1
                     if m:
                         ops.make_rhs(xr, False, False, out=Xt[:, :m])
                         ops.make_rhs(m_mb, False, False, out=Mt[:, :m])
-                        for colA, colB in chunks:
-                            wd = colA.numel()
-                            Wc, Pc = Wt[:wd * cw, :m], rview(Ptmp[:, :wd])
+                    for colA, colB in chunks:
+                        wd = colA.numel()
+                        Pc = rview(Ptmp[:, :wd]) if not sharded else Psend[wd][:f, :wd * cw]
+                        if m:
+                            Wc = Wt[:wd * cw, :m]
                             ops.dl_pair_products_t(Xt[:, :m], cplx, colA, colB, Wc)
                             ops.gemm_nt(Mt[:, :m], Wc, ops.epilogue(ops.EPI_STORE, Pc))
-                            ops.dl_scatter_stats(Pc, cplx, colA, colB, k, 0.0 if sharded else beta, S_dst,
-                                                 slab_channels=fs if sharded else 0)
+                        else:
+                            Pc.zero_()                    # (only a sharded run can leave a rank without rows)
+                        if sharded:
+                            comm.reduce_scatter_sum(Precv[wd], Psend[wd], group)                        # along f
+                            Pc = Precv[wd][:, :wd * cw]
+                        ops.dl_scatter_stats(Pc, cplx, colA, colB, k, beta, S)                          # S <- beta S + .
+                    if m:
                         ops.mask_mul(rview(y_mb), m_mb, rview(YM[:m]), cwidth=cw)
                         ops.gemm_tn(xr, rview(YM[:m]), rview(T_dst), combine=comb, beta=beta, workspace=ws)   # :214
                     elif sharded:
-                        S_part.zero_()
                         T_part.zero_()
                     if not sharded:
                         ops.dl_mirror(S, k, f, cplx)
                         ops.dl_masked_update(S, rview(T), rview(D), rview(Dn), cplx, Dt_ws)            # :216-222
                     else:
-                        comm.reduce_scatter_sum(S_red, S_part, group)                                   # along f
-                        S2, R2 = S.view(k * fs, k * cw), S_red.view(k * fs, k * cw)
-                        ops.axpby(beta, S2, 1.0, R2, S2)
                         ops.dl_mirror(S, k, fs, cplx)
                         _allreduce(T_part, group)
                         ops.axpby(beta, rview(T), 1.0, rview(T_part), rview(T))
