@@ -365,6 +365,16 @@ int decomp_lasso_resident_f64(const double* Q, int64_t ldq, int64_t M, int64_t N
   a.iters = iters;
   a.check = epi->check;
   a.zero = 0;
+  static const int knob_skew = [] {
+    const char* e = getenv("DECOMP_RESIDENT_SKEW");
+    return e != nullptr ? atoi(e) : 2;
+  }();
+  static const int knob_prefetch = [] {
+    const char* e = getenv("DECOMP_RESIDENT_PREFETCH");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  a.skew = knob_skew < 0 ? 0 : knob_skew;
+  a.prefetch = knob_prefetch;
   a.c = epi->other;
   a.ldc = epi->ldother;
   a.x = epi->out;

@@ -46,6 +46,7 @@ struct ResidentSmem {
 struct ResidentArgs {
   long long M;
   int N, iters, check, zero;
+  int skew, prefetch;  // tuning knobs (DECOMP_RESIDENT_SKEW: k-blocks group 1 trails group 0; DECOMP_RESIDENT_PREFETCH)
   const double* c;     // [M, N]  (y A^H) / L
   long long ldc;
   double* x;           // [M, N]  in: x_prev, out: x after `iters` iterations
@@ -141,7 +142,9 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   const int stages = S::RING_BYTES / stage_bytes < RES_MAX_STAGES ? S::RING_BYTES / stage_bytes : RES_MAX_STAGES;
   const int kb_bytes = BMG * 128;   // one k-block of a group's resident w tile
   // group 1 starts an iteration when group 0 is this many k-blocks into it (the ring lets group 0 lead by stages - 1)
-  const int skew_kb = KB - 1 < 2 ? KB - 1 : (stages - 1 < 2 ? stages - 1 : 2);
+  int skew_kb = a.skew;
+  if (skew_kb > KB - 1) skew_kb = KB - 1;
+  if (skew_kb > stages - 1) skew_kb = stages - 1;
   // every CTA owns one contiguous range of rows (a multiple of the DMMA row granularity 8) and walks it in blocks of
   // BM rows; the ragged last block only computes the 8-row groups it has, so the grid is loaded evenly to 8 rows
   const long long per_cta = (((a.M + gridDim.x - 1) / gridDim.x) + 7) & ~7LL;
@@ -184,7 +187,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           // reaches at about the same time, is not a burst of HBM reads
           next_tile_at += per_tile;
           ++tile;
-          if (tile < tiles) {
+          if (tile < tiles && a.prefetch) {
             const long long m1 = row_begin + (long long)tile * BM;
             for (int kb2 = 0; kb2 < KB; ++kb2) {
               tma_prefetch_l2_2d(&tmW, kb2 * BK, (int)m1);
