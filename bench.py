@@ -531,7 +531,7 @@ def run_ours(args):
             del solver
             torch.cuda.empty_cache()
             X.fill_(1.0)
-            solver = nmf.MuSolver(y, D0, X, 0.0, group=group, precision='tf32x3')
+            solver = nmf.MuSolver(y, D0, X, 0.0, mask=mask, group=group, precision='tf32x3')
             for it in range(1, Wn + 1):
                 solver.sweep(it)
             ms32_list, launches32, c3 = timed_regions(
@@ -558,6 +558,21 @@ def run_ours(args):
                                      'peak_gbs': hbm_peak, 'frac': by32 / t32 / 1e9 / hbm_peak,
                                      'note': 'y is read once row-major (y D^T) and once transposed (x^T y), both as '
                                              'TF32 pairs'}}}
+            if masked:
+                # masked model: six TF32-split GEMMs and the [n, f] intermediate as a TF32 pair through HBM -- bound by
+                # HBM, not by the tensor pipe (BASELINE.json configs[4]: "HBM-bound elementwise path")
+                fl32m = 3.0 * 12.0 * n_rows * k * f
+                by32m = 56.0 * n_rows * f + 10.0 * n_rows * k * 8
+                res['tf32x3']['roofline'] = {
+                    'bound': 'hbm', 'achieved': by32m / t32 / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': by32m / t32 / 1e9 / hbm_peak, 'traffic': traffic.get('nmf_masked_tf32x3_sweep_dram_bytes'),
+                    'algorithmic_bytes_per_sweep': by32m,
+                    'note': 'per row and feature: y*mask as a TF32 pair row-major and transposed (8 + 8 B), the FP32 '
+                            'mask twice (4 + 4 B), f = (x D)*mask written and read as a TF32 pair twice (2 x 16 B)',
+                    'kernel': 'tf32x3_gemm_pair_kernel<FMASK> ((x D)*mask -> TF32 pair), <STORE> (f D^T), <XUPD>, '
+                              '<PARTIAL> (x^T (y*m), x^T f)',
+                    'tensor': {'algorithmic_flops_per_sweep': fl32m, 'achieved_tflops': fl32m / t32 / 1e12,
+                               'peak_tflops': tf_peak, 'frac': fl32m / t32 / 1e12 / tf_peak, 'peak_source': tf_src}}
             res['tf32x3']['clocks'] = c3
             del D64, D32
         del solver, y, X, D0, D, mask
@@ -637,7 +652,7 @@ def run_ours(args):
     # ---------------------------------------------------------------- BASELINE configs[3] and [4]
     def leg_configs():
         extra = out.setdefault('extra_configs', {})        # filled in place: a failure keeps what was measured
-        res, c2 = nmf_leg(args.c5_rows, 'weak', masked=True, shape=C5)
+        res, c2 = nmf_leg(args.c5_rows, 'weak', masked=True, shape=C5, tf32='tf32' in legs)
         leg_clocks['c5_masked_nmf'] = c2
         res['config'] = {'workload': 'masked NMF-MU l2, %d rows per GPU x %d, k=%d, 10 %% missing, float64 '
                                      '(BASELINE.json configs[4], per-GPU shard)' % (args.c5_rows, C5['f'], C5['k'])}

@@ -93,6 +93,16 @@ __global__ void split_tf32_kernel(const double* __restrict__ A, long long lda, l
   }
 }
 
+__global__ void to_f32_kernel(const double* __restrict__ A, long long lda, long long rows, long long cols,
+                              float* __restrict__ out, long long ldo) {
+  const long long total = rows * cols;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / cols, c = idx % cols;
+    out[r * ldo + c] = __double2float_rn(A[r * lda + c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM
 constexpr int TBM = 128, TBK = 32, TSTAGES = 2, TNMAX = 256;
 constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KB
@@ -105,6 +115,8 @@ constexpr int TF_STORE = 0;     // P[row][n0 + c] = acc                         
 constexpr int TF_PARTIAL = 1;   // P[(z * M + row)][n0 + c] = acc of K-split z        (FP32 slabs, reduced in FP64 later)
 constexpr int TF_XUPD = 2;      // NMF x update: x <- x * max(acc, 0) / max(neg, eps)  (grads.py:84) in FP64, written as
                                 // FP64 x, its TF32 pair row-major and its TF32 pair transposed
+constexpr int TF_FMASK = 3;     // masked model: F = acc * mask (grads.py:112,122; lasso.py:262) written as a TF32 pair,
+                                // row-major (A operand of F D^T) and / or K-blocked transposed (B operand of x^T F)
 
 struct Tf32Args {
   int M, N, K;
@@ -119,12 +131,12 @@ struct Tf32Args {
   // XUPD
   double* X;              // [M, N] in / out
   long long ldx;
-  const float* NEG;       // [M, N] x (D D^T)
+  const float* NEG;       // XUPD: [M, N] x (D D^T);  FMASK: the [M, N] mask (FP32) or null
   long long ldneg;
-  float* Xh;              // [M, N] TF32 pair of the new x, row-major (A operand of the next x G)
+  float* Xh;              // [M, N] TF32 pair of the new x (FMASK: of F, or null), row-major
   float* Xl;
   long long ldxh;
-  float* XTh;             // [N, M] TF32 pair of the new x, transposed (A operand of x^T y, K-major)
+  float* XTh;             // [N, M] TF32 pair of the new x (FMASK: of F, or null), transposed (K-major for x^T y)
   float* XTl;
   long long ldxt;
 };
@@ -145,6 +157,68 @@ __device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uin
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
+    }
+  } else if constexpr (MODE == TF_FMASK) {
+    // F = acc * mask in FP32 (one rounding, 2^-24: below the 3 x TF32 products' own 2^-21), split exactly into hi + lo
+    const int col0 = n0 + c0;
+    const int ncols = a.N - col0 < 32 ? a.N - col0 : 32;
+    float p[32];
+    if (a.NEG != nullptr) {
+      const float* mk = a.NEG + row * a.ldneg + col0;
+      if (ncols == 32) {
+        float4 m4[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m4[j] = __ldcs(reinterpret_cast<const float4*>(mk) + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p[4 * j] = __uint_as_float(v[4 * j]) * m4[j].x;
+          p[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * m4[j].y;
+          p[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * m4[j].z;
+          p[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * m4[j].w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) p[j] = j < ncols ? __uint_as_float(v[j]) * mk[j] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) p[j] = __uint_as_float(v[j]);
+    }
+    float h[32], l[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      h[j] = to_tf32(p[j]);
+      l[j] = to_tf32(p[j] - h[j]);
+    }
+    if (a.Xh != nullptr) {
+      float* fh = a.Xh + row * a.ldxh + col0;
+      float* fl = a.Xl + row * a.ldxh + col0;
+      if (ncols == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          reinterpret_cast<float4*>(fh)[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+          reinterpret_cast<float4*>(fl)[j] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) {
+            fh[j] = h[j];
+            fl[j] = l[j];
+          }
+      }
+    }
+    if (a.XTh != nullptr) {
+      // a warp writes 32 consecutive rows of one column: 128 contiguous bytes
+      const long long base = a.xt_block > 0 ? (row / a.xt_block) * (long long)a.N * a.xt_block + row % a.xt_block : row;
+      const long long cstride = a.xt_block > 0 ? a.xt_block : a.ldxt;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) {
+          const long long ti = base + (long long)(col0 + j) * cstride;
+          a.XTh[ti] = h[j];
+          a.XTl[ti] = l[j];
+        }
     }
   } else {
     // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here.
@@ -991,6 +1065,49 @@ int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy,
   a.ldxt = ldxt;
   a.xt_block = xt_block > 0 ? xt_block : 0;
   return launch_tf32<TF_XUPD>(Y_hi, Y_lo, ldy, D_hi, D_lo, ldd, a, 0, skip_if, stream);
+}
+
+int decomp_gemm_nt_mask_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
+                               int64_t ldb, int64_t M, int64_t N, int64_t K, const float* mask, int64_t ldmask,
+                               float* F_hi, float* F_lo, int64_t ldf, float* FT_hi, float* FT_lo, int64_t ldft,
+                               int64_t ft_block, const int32_t* skip_if, void* stream) {
+  if (M <= 0 || N <= 0) return DECOMP_OK;
+  const bool rowmajor = F_hi != nullptr, transposed = FT_hi != nullptr;
+  if (K <= 0 || (!rowmajor && !transposed) || (rowmajor && (F_lo == nullptr || (ldf & 3))) ||
+      (transposed && FT_lo == nullptr) || (mask != nullptr && (ldmask & 3)) || M > 2147483647LL || N > 2147483647LL ||
+      K > 2147483647LL) {
+    set_error("decomp_gemm_nt_mask_tf32x3: needs K > 0, an output, ldf and ldmask multiples of 4");
+    return DECOMP_ERR_INVALID;
+  }
+  if (transposed && ft_block > 0 && (ft_block % 128) != 0) {
+    set_error("decomp_gemm_nt_mask_tf32x3: the block length of the transposed output must be a multiple of 128");
+    return DECOMP_ERR_INVALID;
+  }
+  Tf32Args a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = (int)N;
+  a.K = (int)K;
+  a.NEG = mask;
+  a.ldneg = ldmask;
+  a.Xh = F_hi;
+  a.Xl = F_lo;
+  a.ldxh = ldf;
+  a.XTh = FT_hi;
+  a.XTl = FT_lo;
+  a.ldxt = ldft;
+  a.xt_block = ft_block > 0 ? ft_block : 0;
+  return launch_tf32<TF_FMASK>(A_hi, A_lo, lda, B_hi, B_lo, ldb, a, 0, skip_if, stream);
+}
+
+int decomp_to_f32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* out, int64_t ldo, void* stream) {
+  if (rows <= 0 || cols <= 0) return DECOMP_OK;
+  long long b = (rows * cols + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  to_f32_kernel<<<(unsigned)b, 256, 0, as_stream(stream)>>>(A, lda, rows, cols, out, ldo);
+  DCP_CHECK_LAUNCH("to_f32");
+  return DECOMP_OK;
 }
 
 int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* hiT, float* loT,

@@ -43,10 +43,11 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
     (the role of the reference's ``AsyncMinibatchData``, utils/data.py:212-313); ``x`` and ``D`` live on the device.
 
     ``precision`` (not in the reference): 'fp64' (default; matches the numpy path to ~1e-13) or 'tf32x3' -- full-batch
-    unmasked 'l2' MU with the three large contractions (y D^T, x (D D^T), x^T y / x^T x) on the tcgen05 tensor cores,
-    operands split into two TF32 pieces, FP32 accumulation in tensor memory (sample-axis sums in slabs of 4096 rows
-    added up in FP64); the ratios, the D update and the normalisation stay FP64.  Agrees with the FP64 path to ~1e-5
-    relative on D and x (tests/test_tf32x3_gpu.py states the tolerance).  Needs k a multiple of 32 up to 256.
+    'l2' MU, with or without ``mask``, with the large contractions (y D^T, x (D D^T), x^T y / x^T x; masked:
+    (x D) * mask, f D^T, x^T (y * mask), x^T f) on the tcgen05 tensor cores, operands split into two TF32 pieces, FP32
+    accumulation in tensor memory (sample-axis sums in slabs of 4096 rows added up in FP64); the ratios, the D update
+    and the normalisation stay FP64.  Agrees with the FP64 path to ~1e-5 relative on D and x
+    (tests/test_tf32x3_gpu.py states the tolerance).  Needs k a multiple of 32 up to 256.
 
     ``group``: optional ``torch.distributed`` process group. Each rank passes its own contiguous block of
     rows of ``y`` / ``x`` / ``mask`` and the same ``D``; per sweep only the [k, f] and [k, k] statistics
@@ -80,9 +81,9 @@ def solve(y, D, x=None, tol=1.0e-3, minibatch=None, maxiter=1000, method='mu', l
         raise NotImplementedError('Likelihood {} is not implemented for nmf'.format(likelihood))
     if precision not in ('fp64', 'tf32x3'):
         raise ValueError("precision must be 'fp64' or 'tf32x3', given " + str(precision))
-    if precision == 'tf32x3' and (kl or mask is not None or minibatch is not None or host_block_rows is not None
+    if precision == 'tf32x3' and (kl or minibatch is not None or host_block_rows is not None
                                   or D.shape[0] % 32 != 0 or D.shape[0] > 256):
-        raise NotImplementedError("precision='tf32x3' covers the full-batch unmasked 'l2' update with k a multiple of "
+        raise NotImplementedError("precision='tf32x3' covers the full-batch 'l2' update with k a multiple of "
                                   "32 up to 256; use precision='fp64'")
     if host_block_rows is not None:
         if minibatch is not None or method != 'mu' or kl or group is not None or is_torch(y) or kwargs:
@@ -222,8 +223,8 @@ class MuSolver(object):
         dev = y.device
         self.y, self.X, self.mask, self.kl, self.tol, self.group = y, X, mask, kl, tol, group
         self.tf32 = precision == 'tf32x3'
-        if self.tf32 and (kl or mask is not None or D0.shape[0] % 32 != 0 or D0.shape[0] > 256):
-            raise NotImplementedError("precision='tf32x3': unmasked 'l2' update, k a multiple of 32 up to 256")
+        if self.tf32 and (kl or D0.shape[0] % 32 != 0 or D0.shape[0] > 256):
+            raise NotImplementedError("precision='tf32x3': 'l2' update, k a multiple of 32 up to 256")
         self.n, self.f = n, f = y.shape
         self.k = k = D0.shape[0]
         self.Dbuf = [empty2d(k, f, False, dev), empty2d(k, f, False, dev)]
@@ -240,8 +241,21 @@ class MuSolver(object):
             # x^T and y^T are stored K-blocked ([n / 4096][rows][4096]) so that a slab of the sample-axis contraction
             # is a compact piece of memory instead of one 128-byte line per row, 4 n bytes apart.
             blk = ops.TF32_K_PER_SPLIT
-            self.Yh, self.Yl = ops.split_tf32(y)
-            self.YTh, self.YTl = ops.split_transpose_tf32(y, block=blk)
+            ysrc = y
+            if mask is not None:
+                # masked model (grads.py:112-115, 122-125): y * mask replaces y in both numerators, once; the mask
+                # itself is read by the F = (x D) * mask epilogue as FP32
+                ysrc = empty2d(n, f, False, dev)
+                ops.mask_mul(y, mask, ysrc)
+                self.M32 = ops.to_f32(mask)
+                self.Fh, self.Fl = ops.empty_f32(n, f, dev), ops.empty_f32(n, f, dev)
+                self.FTh = ops.empty_f32_blocked(n, f, blk, dev, zero_tail=True)
+                self.FTl = ops.empty_f32_blocked(n, f, blk, dev, zero_tail=True)
+                self.DTh, self.DTl = ops.empty_f32(f, k, dev), ops.empty_f32(f, k, dev)
+                self.NEGD = empty2d(k, f, False, dev)
+            self.Yh, self.Yl = ops.split_tf32(ysrc)
+            self.YTh, self.YTl = ops.split_transpose_tf32(ysrc, block=blk)
+            del ysrc
             self.Xh, self.Xl = ops.split_tf32(X)
             self.XTh = ops.empty_f32_blocked(n, k, blk, dev, zero_tail=True)
             self.XTl = ops.empty_f32_blocked(n, k, blk, dev, zero_tail=True)
@@ -259,11 +273,15 @@ class MuSolver(object):
         self.counted = False    # True: the latch value is the device-side sweep count (graph replay)
         self.maxdiff = torch.zeros(2, dtype=torch.float64, device=dev)
         self.ym = y
-        if mask is not None:
+        if mask is not None and not self.tf32:
             self.ym = empty2d(n, f, False, dev)
             ops.mask_mul(y, mask, self.ym)                                # y * mask, once (grads.py:113,123)
-        self.b2b = bool(USE_B2B and mask is not None and not kl and ops.gemm_b2b_masked_supported(k))
-        if mask is not None or kl:
+        self.b2b = bool(USE_B2B and mask is not None and not kl and not self.tf32 and ops.gemm_b2b_masked_supported(k))
+        if self.tf32:
+            if mask is None:
+                self.G = empty2d(k, k, False, dev)
+                self.S = empty2d(k, k, False, dev)
+        elif mask is not None or kl:
             self.F = empty2d(n, f, False, dev)                            # the [n, f] intermediate
             self.NEGD = empty2d(k, f, False, dev)
         else:
@@ -293,7 +311,25 @@ class MuSolver(object):
         D, Dn = self.Dbuf[(it - 1) % 2], self.Dbuf[it % 2]
         Dt, POS, Draw = self.Dt, self.POS, self.Draw
         NEG = None if self.tf32 else self.NEG
-        if self.tf32:
+        if self.tf32 and mask is not None:
+            # ---- masked l2 (grads.py:112-115, 122-125) on the tcgen05 tensor cores; the [n, f] intermediate
+            # f = (x D) * mask travels as a TF32 pair: row-major for f D^T, K-blocked transposed for x^T f
+            ops.split_tf32(D, self.Dh, self.Dl)
+            ops.split_transpose_tf32(D, self.DTh, self.DTl)
+            ops.gemm_nt_mask_tf32x3(self.Xh, self.Xl, self.DTh, self.DTl, self.M32, F=(self.Fh, self.Fl), skip=latch)
+            ops.gemm_nt_tf32x3(self.Fh, self.Fl, self.Dh, self.Dl, self.NEG32, skip=latch)
+            ops.nmf_xupdate_tf32x3(self.Yh, self.Yl, self.Dh, self.Dl, X, self.NEG32, self.Xh, self.Xl, self.XTh,
+                                   self.XTl, skip=latch)
+            ops.gemm_nt_mask_tf32x3(self.Xh, self.Xl, self.DTh, self.DTl, self.M32, FT=(self.FTh, self.FTl), skip=latch)
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.YTh, self.YTl, POS, self.ws32, skip=latch, K=self.n)
+            ops.gemm_nt_tf32x3_splitk(self.XTh, self.XTl, self.FTh, self.FTl, self.NEGD, self.ws32, skip=latch, K=self.n)
+            if group is not None:
+                t0 = self._comm_mark()
+                _allreduce2d(POS, group)
+                _allreduce2d(self.NEGD, group)
+                self._comm_mark(t0)
+            ops.mu_update(D, POS, self.NEGD, Draw, skip=latch)
+        elif self.tf32:
             G, S = self.G, self.S
             # ---- x update (grads.py:108-111, f.dot(d.T) re-associated) on the tcgen05 tensor cores
             ops.split_tf32(D, self.Dh, self.Dl)

@@ -485,6 +485,35 @@ def nmf_xupdate_tf32x3(Y_hi, Y_lo, D_hi, D_lo, X, NEG, X_hi, X_lo, XT_hi, XT_lo,
     _count(1)
 
 
+def to_f32(A, out=None):
+    """float32 copy of the float64 matrix A (the mask of the TF32-split masked path)."""
+    rows, cols = A.shape
+    if out is None:
+        out = empty_f32(rows, cols, A.device)
+    rc = _lib.lib().decomp_to_f32_f64(_p(A), ld(A), rows, cols, _p(out), ld(out), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_to_f32_f64')
+    _count(1)
+    return out
+
+
+def gemm_nt_mask_tf32x3(A_hi, A_lo, B_hi, B_lo, mask32, F=None, FT=None, skip=None):
+    """F = (A . B^T) * mask32 on tcgen05 (TF32 split), written as the TF32 pair ``F`` = (hi, lo) row-major [M, N]
+    and / or ``FT`` = (hi, lo) transposed: [N, M], or K-blocked [ceil(M / block), N, block]."""
+    M, K = A_hi.shape
+    N = B_hi.shape[0]
+    Fh, Fl = F if F is not None else (None, None)
+    FTh, FTl = FT if FT is not None else (None, None)
+    blocked = FTh is not None and FTh.dim() == 3
+    ft_block = FTh.shape[2] if blocked else 0
+    ldft = 0 if (FTh is None or blocked) else ld(FTh)
+    rc = _lib.lib().decomp_gemm_nt_mask_tf32x3(_p(A_hi), _p(A_lo), ld(A_hi), _p(B_hi), _p(B_lo), ld(B_hi), M, N, K,
+                                               _p(mask32), ld(mask32) if mask32 is not None else 0, _p(Fh), _p(Fl),
+                                               ld(Fh) if Fh is not None else 0, _p(FTh), _p(FTl), ldft, ft_block,
+                                               _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_gemm_nt_mask_tf32x3')
+    _count(1)
+
+
 RESIDENT_MAX_ITERS = 32
 
 

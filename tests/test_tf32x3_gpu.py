@@ -190,7 +190,7 @@ def test_nmf_tf32x3_convergence_and_unsupported():
     assert 1 < it32 < 400 and abs(it32 - it64) <= 3
     assert np.max(np.abs(D32 - D64)) / np.max(np.abs(D64)) <= 1.0e-3
     with pytest.raises(NotImplementedError):
-        nmf.solve(y, D0.copy(), mask=mask, precision='tf32x3')
+        nmf.solve(y, D0.copy(), mask=mask, likelihood='kl', precision='tf32x3')
     y2, D2, _ = gc._nmf_data(100, 20, 3, 0)
     with pytest.raises(NotImplementedError):
         nmf.solve(y2, D2.copy(), precision='tf32x3')                     # k = 3
@@ -252,3 +252,75 @@ def test_nmf_xupdate_tf32x3_blocked_transpose():
     assert torch.equal(Th1.permute(1, 0, 2).reshape(k, nblk * block)[:, :n], Th0)
     assert torch.equal(Tl1.permute(1, 0, 2).reshape(k, nblk * block)[:, :n], Tl0)
     assert float(Th1.permute(1, 0, 2).reshape(k, nblk * block)[:, n:].abs().sum().item()) == 0.0
+
+
+@pytest.mark.parametrize('M,N,K,block', [(300, 200, 32, 128), (1000, 1024, 128, 4096), (5000, 530, 64, 4096),
+                                         (128, 96, 256, 0), (257, 36, 40, 0)])
+def test_gemm_nt_mask_tf32x3_kernel(M, N, K, block):
+    """F = (A B^T) * mask as a TF32 pair, row-major and transposed (plain / K-blocked), ragged edges included."""
+    from decomp_b200 import ops
+    from decomp_b200._device import to_device2d
+    rng = np.random.RandomState(M + N + K)
+    A, B = rng.randn(M, K), rng.randn(N, K)
+    mask = (rng.rand(M, N) > 0.3).astype(np.float64) * (1.0 + 0.25 * rng.rand(M, N))
+    Ah, Al = ops.split_tf32(to_device2d(A))
+    Bh, Bl = ops.split_tf32(to_device2d(B))
+    m32 = ops.to_f32(to_device2d(mask))
+    assert np.array_equal(m32.cpu().numpy(), mask.astype(np.float32))
+    Fh, Fl = ops.empty_f32(M, N, 'cuda'), ops.empty_f32(M, N, 'cuda')
+    if block:
+        FTh = ops.empty_f32_blocked(M, N, block, 'cuda', zero_tail=True)
+        FTl = ops.empty_f32_blocked(M, N, block, 'cuda', zero_tail=True)
+    else:
+        FTh, FTl = ops.empty_f32(N, M, 'cuda'), ops.empty_f32(N, M, 'cuda')
+    ops.gemm_nt_mask_tf32x3(Ah, Al, Bh, Bl, m32, F=(Fh, Fl), FT=(FTh, FTl))
+    torch.cuda.synchronize()
+    ref = A.dot(B.T) * mask
+    scale = np.abs(A).dot(np.abs(B.T)).max() * mask.max()
+    got = Fh.double().cpu().numpy() + Fl.double().cpu().numpy()
+    err = np.max(np.abs(got - ref)) / scale
+    print('masked product tf32x3 %dx%dx%d: rel err %.3g' % (M, N, K, err))
+    assert err <= GEMM_RTOL
+    assert int((Fh.view(torch.int32) & 0x1fff).abs().max().item()) == 0      # TF32-valued pieces
+    assert int((Fl.view(torch.int32) & 0x1fff).abs().max().item()) == 0
+    if block:
+        nblk = (M + block - 1) // block
+        th = FTh.permute(0, 2, 1).reshape(nblk * block, N)
+        tl = FTl.permute(0, 2, 1).reshape(nblk * block, N)
+        assert torch.equal(th[:M], Fh) and torch.equal(tl[:M], Fl)
+        assert float(th[M:].abs().max().item()) == 0.0 if nblk * block > M else True
+    else:
+        assert torch.equal(FTh, Fh.t()) and torch.equal(FTl, Fl.t())
+    # one output only, no mask
+    F2h, F2l = ops.empty_f32(M, N, 'cuda'), ops.empty_f32(M, N, 'cuda')
+    ops.gemm_nt_mask_tf32x3(Ah, Al, Bh, Bl, None, F=(F2h, F2l))
+    torch.cuda.synchronize()
+    got2 = F2h.double().cpu().numpy() + F2l.double().cpu().numpy()
+    assert np.max(np.abs(got2 - A.dot(B.T))) / scale <= GEMM_RTOL
+
+
+@pytest.mark.parametrize('n,f,k,sweeps', [(3001, 517, 64, 20), (9000, 260, 128, 10), (700, 1030, 32, 15)])
+def test_nmf_masked_tf32x3_vs_fp64(n, f, k, sweeps):
+    """Masked 'l2' solves: TF32-split path against the FP64 path (which matches the reference to 1e-10)."""
+    from decomp_b200 import nmf
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(n, f, k, 13)
+    it64, D64, x64 = nmf.solve(y, D0.copy(), tol=0.0, maxiter=sweeps + 1, mask=mask)
+    it32, D32, x32 = nmf.solve(y, D0.copy(), tol=0.0, maxiter=sweeps + 1, mask=mask, precision='tf32x3')
+    assert it64 == it32 == sweeps + 1
+    eD = np.max(np.abs(D32 - D64)) / np.max(np.abs(D64))
+    ex = np.max(np.abs(x32 - x64)) / np.max(np.abs(x64))
+    o64, o32 = orc.nmf_objective(y, x64, D64, mask), orc.nmf_objective(y, x32, D32, mask)
+    print('masked nmf tf32x3 n=%d f=%d k=%d sweeps=%d: err_D %.3g err_x %.3g objective %.3g'
+          % (n, f, k, sweeps, eD, ex, abs(o32 - o64) / abs(o64)))
+    assert eD <= NMF_RTOL and ex <= NMF_RTOL
+    assert abs(o32 - o64) <= NMF_OBJ_RTOL * abs(o64)
+
+
+def test_nmf_masked_tf32x3_convergence():
+    from decomp_b200 import nmf
+    y, D0, mask = gc._nmf_data(1501, 130, 32, 5)
+    it64, D64, _ = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=400, mask=mask)
+    it32, D32, _ = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=400, mask=mask, precision='tf32x3')
+    assert 1 < it32 < 400 and abs(it32 - it64) <= 3
+    assert np.max(np.abs(D32 - D64)) / np.max(np.abs(D64)) <= 1.0e-3
