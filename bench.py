@@ -677,6 +677,31 @@ def run_ours(args):
                                  'peak_gbs': hbm_peak}},
             'config': {'workload': 'masked FISTA iteration ((w A)*M) A^H, %d problems per GPU, A (%d,%d), float64 '
                                    '(the Lasso-C step of BASELINE.json configs[4])' % (n5, k5, f5)}}
+        if 'tf32' in legs:
+            x64 = s5.X.clone()
+            it_done = 3 + 5 * 3
+            del s5
+            torch.cuda.empty_cache()
+            s5 = lasso.LassoSolver(y5, A5, 0.1, None, 0.0, 100000, 'fista', False, mask=m5, precision='tf32x3')
+            s5.iterate(0, 3)
+            ms5t, l5t, c5t = timed_regions(lambda r: s5.iterate(3 + 5 * r, 8 + 5 * r), 3)
+            t5t = median(ms5t) * 1e-3 / 5
+            err5 = float(((s5.X - x64).abs().max() / x64.abs().max()).item())
+            by5t = n5 * f5 * (4.0 + 8.0 + 8.0) + 8.0 * n5 * k5 * 8
+            extra['c5_masked_fista_iter']['tf32x3'] = {
+                'value': n5 * world / t5t, 'unit': 'problem-iters/s', 'ms_per_step': t5t * 1e3,
+                'launches_per_iteration': l5t / 5.0, 'speedup_vs_fp64': t5 / t5t,
+                'max_rel_diff_x_vs_fp64': err5, 'iterations_compared': it_done,
+                'dtype': 'tf32x3 GEMMs (tcgen05, FP32 accumulate in TMEM) + f64 threshold / momentum pass',
+                'roofline': {'bound': 'hbm', 'achieved': by5t / t5t / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                             'frac': by5t / t5t / 1e9 / hbm_peak, 'traffic': None,
+                             'algorithmic_bytes_per_iteration': by5t,
+                             'note': 'per problem and feature: the FP32 mask (4 B) and t = (w A)*mask written and read as '
+                                     'a TF32 pair (8 + 8 B); per problem and atom: w pair, c, x_prev in, x, w pair out',
+                             'tensor': {'achieved_tflops': 3.0 * fl5 / t5t / 1e12, 'peak_tflops': tf_peak,
+                                        'frac': 3.0 * fl5 / t5t / 1e12 / tf_peak}},
+                'clocks': c5t}
+            del x64
         del s5, y5, A5, m5
         torch.cuda.empty_cache()
         # dictionary-learning minibatch step (configs[3]); the ranks share each minibatch when world > 1

@@ -87,12 +87,13 @@ def _declare(lib):
                                                      c_dp, c_i64, c_dp, ctypes.c_size_t, c_dp, c_dp]
     lib.decomp_nmf_xupdate_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp,
                                               c_i64, c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp, c_dp]
-    lib.decomp_gemm_nt_mask_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp,
-                                               c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp, c_dp]
+    lib.decomp_gemm_nt_mask_tf32x3.argtypes = [c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_i64, c_i64, c_dp, c_i64, c_i32,
+                                               c_dp, c_dp, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp, c_dp]
     lib.decomp_to_f32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_i64, c_dp]
     lib.decomp_split_transpose_tf32_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, c_dp, c_dp, c_i64, c_i64, c_dp]
     lib.decomp_proxq_apply_f64.argtypes = [c_dp, c_i64, ctypes.POINTER(Epilogue), c_dp, c_dp, c_i64, c_i64, c_i64, c_dp,
                                            c_dp]
+    lib.decomp_prox_apply_f64.argtypes = lib.decomp_proxq_apply_f64.argtypes
     lib.decomp_lasso_resident_supported.argtypes = [c_i64]
     lib.decomp_lasso_resident_f64.argtypes = [c_dp, c_i64, c_i64, c_i64, ctypes.POINTER(Epilogue), c_i32,
                                               ctypes.POINTER(ctypes.c_double), c_dp, c_dp]
@@ -139,7 +140,7 @@ EXPORTS = (
     'decomp_dl_sweep_workspace_bytes', 'decomp_dl_sweep_f64', 'decomp_dl_atom_weighted_f64', 'decomp_dl_pair_products_t_f64', 'decomp_dl_scatter_stats_f64', 'decomp_dl_mirror_f64', 'decomp_dl_masked_update_f64', 'decomp_dl_masked_update_phase_f64',
     'decomp_split_tf32_f64', 'decomp_gemm_nt_tf32x3', 'decomp_proxq_apply_f64',
     'decomp_gemm_nt_tf32x3_splitk_workspace_bytes', 'decomp_gemm_nt_tf32x3_splitk_f64', 'decomp_nmf_xupdate_tf32x3',
-    'decomp_split_transpose_tf32_f64', 'decomp_gemm_nt_mask_tf32x3', 'decomp_to_f32_f64',
+    'decomp_split_transpose_tf32_f64', 'decomp_gemm_nt_mask_tf32x3', 'decomp_to_f32_f64', 'decomp_prox_apply_f64',
     'decomp_lasso_resident_supported', 'decomp_lasso_resident_f64', 'decomp_staged_upload',
     'decomp_comm_unique_id', 'decomp_comm_init', 'decomp_comm_destroy', 'decomp_comm_allreduce_sum_f64',
     'decomp_comm_allreduce_min_i32', 'decomp_comm_reduce_scatter_sum_f64', 'decomp_comm_allgather_f64',

@@ -12,8 +12,9 @@
 //            one of two TMEM accumulators (2 x N columns) and commits to the ring's `empty` barrier / the
 //            accumulator's `full` barrier
 //   warp 2   allocates / frees the tensor memory
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> FP32 row-major P (each thread owns one
-//            output row, 128 contiguous bytes per chunk), then release the accumulator
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> FP32 row-major P (each thread owns one
+//            output row, 128 contiguous bytes per chunk; two warps per TMEM lane quarter take alternate chunks), then
+//            release the accumulator
 // Kernel 2, proxq_apply_kernel: the FP64 part of the iteration as one coalesced streaming pass
 //   z = c + P;  x_new = shrink(z, thr);  w_next = x_new + momentum (x_new - x_prev) -> written directly as the
 //   TF32 pair (w_hi, w_lo) the next GEMM reads; convergence test + last-CTA latch as in the FP64 kernels.
@@ -109,6 +110,14 @@ constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KB
 constexpr int TB_BYTES = TNMAX * TBK * 4;        // 32 KB
 constexpr int TSTAGE_BYTES = 2 * TA_BYTES + 2 * TB_BYTES;   // 96 KB
 constexpr int TSMEM_BYTES = TSTAGES * TSTAGE_BYTES + 16 * 8;
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue -- two warps per TMEM lane quarter
+// (warp % 4), taking alternate 32-column chunks of the accumulator
+// (the NMF x update keeps four: its epilogue holds a chunk of x and of the denominator in registers besides the
+// accumulator and needs the 255-register budget of a 256-thread CTA)
+__host__ __device__ constexpr int tf_epi_warps(int mode) { return mode == 2 ? 4 : 8; }
+__host__ __device__ constexpr int tf_threads(int mode) { return (4 + tf_epi_warps(mode)) * 32; }
+// FMASK: one padded 32 x 32 staging tile per epilogue warp behind the barriers
+__host__ __device__ constexpr int tf_tile_bytes(int mode) { return mode == 3 ? tf_epi_warps(mode) * 32 * 33 * 4 : 0; }
 
 // what the epilogue warps do with a finished 128 x mma_n accumulator tile
 constexpr int TF_STORE = 0;     // P[row][n0 + c] = acc                              (FP32)
@@ -122,6 +131,8 @@ struct Tf32Args {
   int M, N, K;
   int tiles_m, tiles_n, splits, kb_per_split, kb_total;
   int mma_n;              // N of one MMA = rows of one B box (multiple of 32, <= 256); tiles_n boxes cover N
+  int n_fast;             // tile order: the n tiles of one m tile run side by side (B small enough to stay in L2: A is
+                          // then read from HBM once instead of once per n tile)
   int blocked;            // operands stored K-blocked, [K / kblock][rows][kblock] with kblock = 32 kb_per_split: split z
                           // reads block z (3-D tensor maps).  A sample-axis contraction over row-major x^T, y^T would
                           // touch one 128-byte piece per row 4 n bytes apart -- hundreds of pages per TMA box
@@ -131,8 +142,9 @@ struct Tf32Args {
   // XUPD
   double* X;              // [M, N] in / out
   long long ldx;
-  const float* NEG;       // XUPD: [M, N] x (D D^T);  FMASK: the [M, N] mask (FP32) or null
+  const float* NEG;       // XUPD: [M, N] x (D D^T);  FMASK: the [M, N / cw] mask (FP32) or null
   long long ldneg;
+  int cw;                 // FMASK: 1 real, 2 complex (interleaved re / im columns share one mask entry)
   float* Xh;              // [M, N] TF32 pair of the new x (FMASK: of F, or null), row-major
   float* Xl;
   long long ldxh;
@@ -157,68 +169,6 @@ __device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uin
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (n0 + c0 + j < a.N) dst[j] = __uint_as_float(v[j]);
-    }
-  } else if constexpr (MODE == TF_FMASK) {
-    // F = acc * mask in FP32 (one rounding, 2^-24: below the 3 x TF32 products' own 2^-21), split exactly into hi + lo
-    const int col0 = n0 + c0;
-    const int ncols = a.N - col0 < 32 ? a.N - col0 : 32;
-    float p[32];
-    if (a.NEG != nullptr) {
-      const float* mk = a.NEG + row * a.ldneg + col0;
-      if (ncols == 32) {
-        float4 m4[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) m4[j] = __ldcs(reinterpret_cast<const float4*>(mk) + j);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          p[4 * j] = __uint_as_float(v[4 * j]) * m4[j].x;
-          p[4 * j + 1] = __uint_as_float(v[4 * j + 1]) * m4[j].y;
-          p[4 * j + 2] = __uint_as_float(v[4 * j + 2]) * m4[j].z;
-          p[4 * j + 3] = __uint_as_float(v[4 * j + 3]) * m4[j].w;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) p[j] = j < ncols ? __uint_as_float(v[j]) * mk[j] : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) p[j] = __uint_as_float(v[j]);
-    }
-    float h[32], l[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      h[j] = to_tf32(p[j]);
-      l[j] = to_tf32(p[j] - h[j]);
-    }
-    if (a.Xh != nullptr) {
-      float* fh = a.Xh + row * a.ldxh + col0;
-      float* fl = a.Xl + row * a.ldxh + col0;
-      if (ncols == 32) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          reinterpret_cast<float4*>(fh)[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-          reinterpret_cast<float4*>(fl)[j] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) {
-            fh[j] = h[j];
-            fl[j] = l[j];
-          }
-      }
-    }
-    if (a.XTh != nullptr) {
-      // a warp writes 32 consecutive rows of one column: 128 contiguous bytes
-      const long long base = a.xt_block > 0 ? (row / a.xt_block) * (long long)a.N * a.xt_block + row % a.xt_block : row;
-      const long long cstride = a.xt_block > 0 ? a.xt_block : a.ldxt;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols) {
-          const long long ti = base + (long long)(col0 + j) * cstride;
-          a.XTh[ti] = h[j];
-          a.XTl[ti] = l[j];
-        }
     }
   } else {
     // x <- x * max(pos, 0) / max(neg, eps), left to right like the reference (grads.py:84); N % 32 == 0 here.
@@ -261,8 +211,110 @@ __device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uin
   }
 }
 
+// ---- TF_FMASK epilogue: F = acc * mask in FP32 (one rounding, 2^-24: below the 3 x TF32 products' own 2^-21), split
+// exactly into hi + lo.  With K = k (a few k-blocks per tile) this mode is all epilogue: 12 bytes of HBM traffic per
+// accumulator element.  tcgen05.ld hands every thread one ROW of the tile, and a warp that stores 16-byte pieces of 32
+// different rows (4 KB apart) writes half sectors into 32 lines per instruction -- measured 2.5 TB/s.  So a 32 x 32
+// chunk is turned through a padded shared-memory tile: lane = column for the mask loads and the row-major stores
+// (128 contiguous bytes per instruction), lane = row again for the transposed stores.  The mask values of a chunk are
+// fetched one chunk ahead of the accumulator they multiply.
+constexpr int TF_TILE_LD = 33;
+constexpr int TF_TILE_BYTES = 32 * TF_TILE_LD * 4;          // per epilogue warp
+
+// mask[r0 + i][col] for i = 0..31 of this lane's column (1 where there is no mask, 0 beyond the edges)
+__device__ __forceinline__ void fmask_load(const Tf32Args& a, long long r0, int col, float (&m)[32]) {
+  const bool live = col < a.N;
+  if (a.NEG == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m[i] = 1.f;
+    return;
+  }
+  const float* mk = a.NEG + r0 * a.ldneg + (a.cw == 2 ? col >> 1 : col);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) m[i] = (live && r0 + i < a.M) ? __ldcs(mk + i * a.ldneg) : 0.f;
+}
+
+// v: this thread's row of the chunk (lane = row); m: the mask of this lane's column (lane = column)
+__device__ __forceinline__ void fmask_chunk(const Tf32Args& a, const uint32_t (&v)[32], const float (&m)[32],
+                                            long long r0, int col0, float* tile, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tile[lane * TF_TILE_LD + j] = __uint_as_float(v[j]);
+  __syncwarp();
+  const int col = col0 + lane;
+  const bool live = col < a.N;
+  float p[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) p[i] = tile[i * TF_TILE_LD + lane] * m[i];
+  if (a.Xh != nullptr) {
+    float* fh = a.Xh + r0 * a.ldxh + col;
+    float* fl = a.Xl + r0 * a.ldxh + col;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (live && r0 + i < a.M) {
+        const float h = to_tf32(p[i]);
+        fh[i * a.ldxh] = h;
+        fl[i * a.ldxh] = to_tf32(p[i] - h);
+      }
+  }
+  if (a.XTh != nullptr) {
+    // back to lane = row: a warp writes 32 consecutive rows of one column, 128 contiguous bytes
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tile[i * TF_TILE_LD + lane] = p[i];
+    __syncwarp();
+    const long long row = r0 + lane;
+    const long long tbase = a.xt_block > 0 ? (row / a.xt_block) * (long long)a.N * a.xt_block + row % a.xt_block : row;
+    const long long tstride = a.xt_block > 0 ? a.xt_block : a.ldxt;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (row < a.M && col0 + j < a.N) {
+        const float q = tile[lane * TF_TILE_LD + j];
+        const float h = to_tf32(q);
+        const long long ti = tbase + (long long)(col0 + j) * tstride;
+        a.XTh[ti] = h;
+        a.XTl[ti] = to_tf32(q - h);
+      }
+  }
+  __syncwarp();      // the tile is rewritten by the next chunk
+}
+
+// the epilogue warps' pass over one finished accumulator: 32-column chunks c0 = first, first + step, ...
+// row: this thread's row (lane = row), r0 = row - lane; tile: this warp's staging tile (FMASK only)
 template <int MODE>
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void tf32_epilogue_tile(const Tf32Args& a, uint32_t taddr, long long row, int n0, int N,
+                                                   int z, int first, int step, uint64_t* acc_full, uint32_t acc_ph,
+                                                   float* tile, int lane) {
+  if constexpr (MODE == TF_FMASK) {
+    const long long r0 = row - lane;
+    float mcur[32];
+    fmask_load(a, r0, n0 + first + lane, mcur);          // in flight while the MMAs of this tile are still running
+    mbar_wait(acc_full, acc_ph);
+    tc_fence_after();
+    for (int c0 = first; c0 < N; c0 += step) {
+      float mnext[32];
+      if (c0 + step < N) fmask_load(a, r0, n0 + c0 + step + lane, mnext);
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)c0, v);
+      if (r0 < a.M && n0 + c0 < a.N) fmask_chunk(a, v, mcur, r0, n0 + c0, tile, lane);   // warp-uniform condition
+      if (c0 + step < N) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mcur[j] = mnext[j];
+      }
+    }
+  } else {
+    mbar_wait(acc_full, acc_ph);
+    tc_fence_after();
+    for (int c0 = first; c0 < N; c0 += step) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)c0, v);
+      if (row >= a.M || n0 + c0 >= a.N) continue;
+      tf32_epilogue_chunk<MODE>(a, v, row, n0, c0, z);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(tf_threads(MODE), 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const Tf32Args a, const int* __restrict__ skip_if) {
@@ -289,7 +341,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], 4);   // one arrival per epilogue warp
+      mbar_init(&acc_empty[b], tf_epi_warps(MODE));   // one arrival per epilogue warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmAh);
@@ -311,8 +363,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   // item -> (m tile, n tile, K split): consecutive items share the split and the B tile, so that CTAs running side by
   // side hit the same operand lines in L2
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb, int& z) {
-    const int tm = item % a.tiles_m;
-    const int tn = (item / a.tiles_m) % a.tiles_n;
+    const int tm = a.n_fast ? (item / a.tiles_n) % a.tiles_m : item % a.tiles_m;
+    const int tn = a.n_fast ? item % a.tiles_n : (item / a.tiles_m) % a.tiles_n;
     z = item / tiles_mn;
     m0 = tm * TBM;
     n0 = tn * N;
@@ -400,22 +452,18 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> memory
-    const int e = warp - 4;                 // TMEM lane quarter this warp may access
+    const int e = (warp - 4) & 3;           // TMEM lane quarter this warp may access (warp % 4)
+    const int half = (warp - 4) >> 2;       // which of the alternate chunks
+    float* tile = reinterpret_cast<float*>(smem + TSTAGES * TSTAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 33);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int m0, n0, kb0, nkb, z;
       decode(item, m0, n0, kb0, nkb, z);
       const long long row = (long long)m0 + e * 32 + lane;
-      mbar_wait(&acc_full[acc], acc_ph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * N);
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (row >= a.M || n0 + c0 >= a.N) continue;
-        tf32_epilogue_chunk<MODE>(a, v, row, n0, c0, z);
-      }
+      tf32_epilogue_tile<MODE>(a, taddr, row, n0, N, z, half * 32, tf_epi_warps(MODE) * 8, &acc_full[acc], acc_ph,
+                               tile, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -441,7 +489,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 // the SM, not the tensor pipe, is what bounds the single-CTA kernel.
 // Barrier protocol (as in the public sm_100 2-SM GEMMs): full[s] lives in the leader, count 2 (one arrival per CTA's
 // producer), both CTAs' TMA loads complete_tx on it; empty[s] and acc_full[b] exist in both CTAs and are signalled
-// by the leader's tcgen05.commit multicast; acc_empty[b] lives in the leader, count 8 (4 epilogue warps x 2 CTAs).
+// by the leader's tcgen05.commit multicast; acc_empty[b] lives in the leader, count 16 (8 epilogue warps x 2 CTAs).
 constexpr int T2_STAGES = 3;
 constexpr int T2_HALF_N_BYTES = (TNMAX / 2) * TBK * 4;                   // 16 KB: this CTA's half of a B box
 constexpr int T2_STAGE_BYTES = 2 * TA_BYTES + 2 * T2_HALF_N_BYTES;        // 64 KB
@@ -510,7 +558,7 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tf_threads(MODE), 1)
 tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                         const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                         const Tf32Args a, const int* __restrict__ skip_if) {
@@ -539,7 +587,7 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);      // one multicast commit
-      mbar_init(&acc_empty[b], 8);     // used in the leader: 4 epilogue warps of each CTA
+      mbar_init(&acc_empty[b], 2 * tf_epi_warps(MODE));     // used in the leader: the epilogue warps of both CTAs
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmAh);
@@ -559,8 +607,8 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   auto decode = [&](int item, int& m0, int& n0, int& kb0, int& nkb, int& z) {
-    const int tm = item % tiles_m2;
-    const int tn = (item / tiles_m2) % a.tiles_n;
+    const int tm = a.n_fast ? (item / a.tiles_n) % tiles_m2 : item % tiles_m2;
+    const int tn = a.n_fast ? item % a.tiles_n : (item / tiles_m2) % a.tiles_n;
     z = item / tiles_mn;
     m0 = tm * 2 * TBM;
     n0 = tn * N;
@@ -654,22 +702,17 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
-    const int e = warp - 4;
+    const int e = (warp - 4) & 3, half = (warp - 4) >> 2;
+    float* tile = reinterpret_cast<float*>(smem + T2_STAGES * T2_STAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 33);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int item = first; item < items; item += stride) {
       int m0, n0, kb0, nkb, z;
       decode(item, m0, n0, kb0, nkb, z);
       const long long row = (long long)m0 + (long long)rank * TBM + e * 32 + lane;
-      mbar_wait(&acc_full[acc], acc_ph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(acc * N);
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (row >= a.M || n0 + c0 >= a.N) continue;
-        tf32_epilogue_chunk<MODE>(a, v, row, n0, c0, z);
-      }
+      tf32_epilogue_tile<MODE>(a, taddr, row, n0, N, z, half * 32, tf_epi_warps(MODE) * 8, &acc_full[acc], acc_ph,
+                               tile, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(mapa_u32(&acc_empty[acc], 0));
@@ -745,7 +788,10 @@ __device__ __forceinline__ double with_sign_of_t(double mag, double s) {
 }
 
 // one thread = one column pair; grid-stride over rows * N/2 pairs, row-contiguous
-template <int SHRINK>
+// PROX == false: z = other + P (the gradient step folded into Q and other, unmasked iteration)
+// PROX == true:  z = w + step (other - P) with w = w_hi + w_lo, P = ((w A) * M) A^H, threshold step * alpha_col * rowvec
+//                (masked iteration, lasso.py:259-271; the EPI_PROX epilogue of the FP64 GEMMs)
+template <int SHRINK, bool PROX>
 __global__ void __launch_bounds__(256)
 proxq_apply_kernel(const float* __restrict__ P, long long ldp, const decomp_epilogue_t ep, float* __restrict__ w_hi,
                    float* __restrict__ w_lo, long long ldw, long long M, long long N,
@@ -760,7 +806,17 @@ proxq_apply_kernel(const float* __restrict__ P, long long ldp, const decomp_epil
     const float2 p = *reinterpret_cast<const float2*>(P + row * ldp + col);
     const double2 c = *reinterpret_cast<const double2*>(ep.other + row * ep.ldother + col);
     const double2 xp = *reinterpret_cast<const double2*>(ep.prev + row * ep.ldprev + col);
-    const double z0 = c.x + (double)p.x, z1 = c.y + (double)p.y;
+    double z0, z1;
+    if constexpr (PROX) {
+      const float2 wh = *reinterpret_cast<const float2*>(w_hi + row * ldw + col);
+      const float2 wl = *reinterpret_cast<const float2*>(w_lo + row * ldw + col);
+      const double stepv = __ldg(ep.step);
+      z0 = ((double)wh.x + (double)wl.x) + stepv * (c.x - (double)p.x);
+      z1 = ((double)wh.y + (double)wl.y) + stepv * (c.y - (double)p.y);
+    } else {
+      z0 = c.x + (double)p.x;
+      z1 = c.y + (double)p.y;
+    }
     double t0, t1, tol0 = 0.0, tol1 = 0.0;
     if (SHRINK == DECOMP_SHRINK_COMPLEX) {
       t0 = t1 = __ldg(ep.colvec + (col >> 1));
@@ -771,6 +827,17 @@ proxq_apply_kernel(const float* __restrict__ P, long long ldp, const decomp_epil
       if (ep.check) {
         tol0 = __ldg(ep.colvec2 + col);
         tol1 = __ldg(ep.colvec2 + col + 1);
+      }
+    }
+    if constexpr (PROX) {
+      const double stepv = __ldg(ep.step);
+      if (ep.rowvec != nullptr) {
+        const double rowfac = __ldg(ep.rowvec + row);
+        t0 = stepv * (t0 * rowfac);
+        t1 = stepv * (t1 * rowfac);
+      } else if (!(ep.flags & DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD)) {
+        t0 = stepv * t0;
+        t1 = stepv * t1;
       }
     }
     double x0, x1;
@@ -901,6 +968,7 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   // (a K-blocked operand keeps its block length whatever K is: the tensor map is built from kb_per_split)
   if (!a.blocked && a.kb_per_split > a.kb_total) a.kb_per_split = a.kb_total;
   a.splits = (a.kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  a.n_fast = a.tiles_n > 1 && (long long)a.N * a.K * 8 <= (16ll << 20) ? 1 : 0;
   // CTA pairs (tcgen05.mma.cta_group::2) when there are at least two 128-row tiles: each CTA stages half of B
   static const bool pair_enabled = [] {
     const char* e = getenv("DECOMP_TF32_PAIR");
@@ -927,7 +995,7 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
     auto kern2 = tf32x3_gemm_pair_kernel<MODE>;
     static bool configured2 = false;   // per instantiation
     if (!configured2) {
-      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES + tf_tile_bytes(MODE));
       if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 pair smem)");
       configured2 = true;
     }
@@ -939,13 +1007,13 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
     }
     long long clusters = num_sms() / 2;
     if (clusters > items2) clusters = items2;
-    kern2<<<(unsigned)(2 * clusters), 256, T2_SMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
+    kern2<<<(unsigned)(2 * clusters), tf_threads(MODE), T2_SMEM_BYTES + tf_tile_bytes(MODE), as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
     return check_cuda(cudaGetLastError(), "tf32x3 pair gemm launch");
   }
   auto kern = tf32x3_gemm_kernel<MODE>;
   static bool configured = false;   // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES + tf_tile_bytes(MODE));
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tf32x3 smem)");
     configured = true;
   }
@@ -956,8 +1024,42 @@ static int launch_tf32(const float* A_hi, const float* A_lo, int64_t lda, const 
   }
   long long ctas = num_sms();
   if (ctas > items) ctas = items;
-  kern<<<(unsigned)ctas, 256, TSMEM_BYTES, as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
+  kern<<<(unsigned)ctas, tf_threads(MODE), TSMEM_BYTES + tf_tile_bytes(MODE), as_stream(stream)>>>(tah, tal, tbh, tbl, a, skip_if);
   return check_cuda(cudaGetLastError(), "tf32x3 gemm launch");
+}
+
+template <bool PROX>
+static int launch_prox_apply(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
+                             int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream) {
+  if (M <= 0 || N <= 0) return DECOMP_OK;
+  if (epi == nullptr || (N & 1) || epi->other == nullptr || epi->prev == nullptr || epi->out == nullptr ||
+      epi->colvec == nullptr || (ldp & 1) || (ldw & 1) || (PROX && epi->step == nullptr) ||
+      (epi->check && (epi->latch == nullptr || epi->scratch == nullptr))) {
+    set_error("decomp_prox%s_apply_f64: invalid argument", PROX ? "" : "q");
+    return DECOMP_ERR_INVALID;
+  }
+  long long b = (M * (N / 2) + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (b > cap) b = cap;
+  cudaStream_t st = as_stream(stream);
+  switch (epi->shrink) {
+    case DECOMP_SHRINK_REAL:
+      proxq_apply_kernel<DECOMP_SHRINK_REAL, PROX><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N,
+                                                                                  skip_if);
+      break;
+    case DECOMP_SHRINK_COMPLEX:
+      proxq_apply_kernel<DECOMP_SHRINK_COMPLEX, PROX><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N,
+                                                                                     skip_if);
+      break;
+    case DECOMP_SHRINK_POSITIVE:
+      proxq_apply_kernel<DECOMP_SHRINK_POSITIVE, PROX><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N,
+                                                                                      skip_if);
+      break;
+    default:
+      set_error("decomp_prox_apply: unknown shrink kind %d", epi->shrink);
+      return DECOMP_ERR_INVALID;
+  }
+  return check_cuda(cudaGetLastError(), "prox_apply launch");
 }
 
 extern "C" {
@@ -1069,9 +1171,13 @@ int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy,
 
 int decomp_gemm_nt_mask_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
                                int64_t ldb, int64_t M, int64_t N, int64_t K, const float* mask, int64_t ldmask,
-                               float* F_hi, float* F_lo, int64_t ldf, float* FT_hi, float* FT_lo, int64_t ldft,
-                               int64_t ft_block, const int32_t* skip_if, void* stream) {
+                               int32_t cwidth, float* F_hi, float* F_lo, int64_t ldf, float* FT_hi, float* FT_lo,
+                               int64_t ldft, int64_t ft_block, const int32_t* skip_if, void* stream) {
   if (M <= 0 || N <= 0) return DECOMP_OK;
+  if ((cwidth != 1 && cwidth != 2) || (cwidth == 2 && (N & 1))) {
+    set_error("decomp_gemm_nt_mask_tf32x3: cwidth must be 1 or 2 (and N even when 2)");
+    return DECOMP_ERR_INVALID;
+  }
   const bool rowmajor = F_hi != nullptr, transposed = FT_hi != nullptr;
   if (K <= 0 || (!rowmajor && !transposed) || (rowmajor && (F_lo == nullptr || (ldf & 3))) ||
       (transposed && FT_lo == nullptr) || (mask != nullptr && (ldmask & 3)) || M > 2147483647LL || N > 2147483647LL ||
@@ -1090,6 +1196,7 @@ int decomp_gemm_nt_mask_tf32x3(const float* A_hi, const float* A_lo, int64_t lda
   a.K = (int)K;
   a.NEG = mask;
   a.ldneg = ldmask;
+  a.cw = cwidth;
   a.Xh = F_hi;
   a.Xl = F_lo;
   a.ldxh = ldf;
@@ -1125,31 +1232,12 @@ int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, 
 
 int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
                            int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream) {
-  if (M <= 0 || N <= 0) return DECOMP_OK;
-  if (epi == nullptr || (N & 1) || epi->other == nullptr || epi->prev == nullptr || epi->out == nullptr ||
-      epi->colvec == nullptr || (ldp & 1) || (ldw & 1) || (epi->check && (epi->latch == nullptr || epi->scratch == nullptr))) {
-    set_error("decomp_proxq_apply_f64: invalid argument");
-    return DECOMP_ERR_INVALID;
-  }
-  long long b = (M * (N / 2) + 255) / 256;
-  const long long cap = (long long)num_sms() * 8;
-  if (b > cap) b = cap;
-  cudaStream_t st = as_stream(stream);
-  switch (epi->shrink) {
-    case DECOMP_SHRINK_REAL:
-      proxq_apply_kernel<DECOMP_SHRINK_REAL><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
-      break;
-    case DECOMP_SHRINK_COMPLEX:
-      proxq_apply_kernel<DECOMP_SHRINK_COMPLEX><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
-      break;
-    case DECOMP_SHRINK_POSITIVE:
-      proxq_apply_kernel<DECOMP_SHRINK_POSITIVE><<<(unsigned)b, 256, 0, st>>>(P, ldp, *epi, w_hi, w_lo, ldw, M, N, skip_if);
-      break;
-    default:
-      set_error("decomp_proxq_apply_f64: unknown shrink kind %d", epi->shrink);
-      return DECOMP_ERR_INVALID;
-  }
-  return check_cuda(cudaGetLastError(), "proxq_apply launch");
+  return launch_prox_apply<false>(P, ldp, epi, w_hi, w_lo, ldw, M, N, skip_if, stream);
+}
+
+int decomp_prox_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
+                          int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream) {
+  return launch_prox_apply<true>(P, ldp, epi, w_hi, w_lo, ldw, M, N, skip_if, stream);
 }
 
 }  // extern "C"

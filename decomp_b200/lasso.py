@@ -53,8 +53,10 @@ def solve(y, A, alpha, x=None, tol=1.0e-3, method='ista', maxiter=1000, mask=Non
     hot path and raise ``NotImplementedError``.
 
     ``precision`` (not in the reference): 'fp64' (default; matches the numpy path to ~1e-13) or 'tf32x3' -- the
-    unmasked iteration's GEMM on the tcgen05 tensor cores with operands split into two TF32 pieces and FP32
-    accumulation (the update itself stays FP64); agrees with the FP64 path to ~1e-5 relative on x.
+    iteration's GEMMs on the tcgen05 tensor cores with operands split into two TF32 pieces and FP32 accumulation
+    (the update itself stays FP64); agrees with the FP64 path to ~1e-5 relative on x.  Without a per-problem mask:
+    w (I - G/L), k (2k for complex data) a multiple of 32 up to 256; with one: (w A) * mask and its product with A^H,
+    the [B, f] intermediate travelling as a TF32 pair, any even real width.
     """
     array_kind(y, A, x, mask)
     # x = None means zeros(y.shape[:-1] + (k,), y.dtype) (lasso.py:73-74); they are created on the device
@@ -429,8 +431,8 @@ class LassoSolver(object):
             ops.gemm_nt(rview(T), AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
             self.A_rhs = ops.make_rhs(Anr, cplx, False)            # NT operand of  w . A
             # widths the fused back-to-back kernel covers: both masked GEMMs of an iteration in one launch
-            self.b2b = bool(USE_B2B and ops.gemm_b2b_masked_supported(k * cw))
-            if self.b2b:
+            self.b2b = bool(USE_B2B and not self.tf32 and ops.gemm_b2b_masked_supported(k * cw))
+            if self.b2b or self.tf32:
                 self.T = None                                      # only the set-up needed the [B, f] temporary
         else:
             ops.gemm_nt(yr, AH, ops.epilogue(ops.EPI_STORE, rview(yAh)))
@@ -449,9 +451,21 @@ class LassoSolver(object):
                 self.tol_pad = torch.ones(nv, dtype=torch.float64, device=dev)
                 self.tol_pad[:k].copy_(self.tol_vec)
             ops.scale_scalar(rview(yAh), self.step, rview(yAh))    # yAh <- yAh / L
-        if self.tf32:
+        if self.tf32 and full_mask:
+            # masked iteration on the tcgen05 tensor cores (lasso.py:259-271): t = (w A) * mask as a TF32 pair through
+            # HBM, then t A^H, then the FP64 threshold / momentum pass
             n_real = k * cw
-            if full_mask or n_real % 32 != 0 or n_real > 256:
+            if n_real % 2 != 0:
+                raise NotImplementedError("precision='tf32x3' with a mask needs an even k for real data; use "
+                                          "precision='fp64'")
+            self.M32 = ops.to_f32(mask)
+            self.Ar_hi, self.Ar_lo = ops.split_tf32(self.A_rhs)    # [f cw, k cw]: NT operand of w . A
+            self.AH_hi, self.AH_lo = ops.split_tf32(AH)            # [k cw, f cw]: NT operand of t . A^H
+            self.T_hi, self.T_lo = ops.empty_f32(B, f * cw, dev), ops.empty_f32(B, f * cw, dev)
+            self.P = ops.empty_f32(B, n_real, dev)
+        elif self.tf32:
+            n_real = k * cw
+            if n_real % 32 != 0 or n_real > 256:
                 raise NotImplementedError("precision='tf32x3' covers the unmasked iteration with k (2k for complex "
                                           "data) a multiple of 32 up to 256; use precision='fp64'")
             self.Q_hi, self.Q_lo = ops.split_tf32(self.Q_rhs)
@@ -484,6 +498,17 @@ class LassoSolver(object):
     def _launch(self, i, out_x):
         W, cw, latch = self.W, self.cw, self.latch
         check = self.checks and i % 10 == 0
+        if self.tf32 and self.full_mask:
+            epi = ops.epilogue(ops.EPI_PROX, out_x, cwidth=cw, other=rview(self.yAh), prev=rview(self.X),
+                               colvec=self.alpha_vec, colvec2=self.tol_vec, rowvec=self.rowvec, step=self.step,
+                               momentum=self.mom[i], shrink=self.shrink, check=check, latch=latch,
+                               scratch=self.scratch, latch_value=i + 1)
+            ops.gemm_nt_mask_tf32x3(self.W_hi, self.W_lo, self.Ar_hi, self.Ar_lo, self.M32, F=(self.T_hi, self.T_lo),
+                                    cwidth=cw, skip=latch)
+            ops.gemm_nt_tf32x3(self.T_hi, self.T_lo, self.AH_hi, self.AH_lo, self.P, skip=latch)
+            ops.prox_apply(self.P, epi, self.W_hi, self.W_lo, skip=latch)
+            self._exchange_latch(check, i + 1)
+            return
         if self.tf32:
             epi = ops.epilogue(ops.EPI_PROXQ, out_x, cwidth=cw, other=rview(self.yAh), prev=rview(self.X),
                                colvec=self.thr, colvec2=self.tol_vec, flags=ops.EPI_FLAG_COLVEC_IS_THRESHOLD,

@@ -496,7 +496,7 @@ def to_f32(A, out=None):
     return out
 
 
-def gemm_nt_mask_tf32x3(A_hi, A_lo, B_hi, B_lo, mask32, F=None, FT=None, skip=None):
+def gemm_nt_mask_tf32x3(A_hi, A_lo, B_hi, B_lo, mask32, F=None, FT=None, cwidth=1, skip=None):
     """F = (A . B^T) * mask32 on tcgen05 (TF32 split), written as the TF32 pair ``F`` = (hi, lo) row-major [M, N]
     and / or ``FT`` = (hi, lo) transposed: [N, M], or K-blocked [ceil(M / block), N, block]."""
     M, K = A_hi.shape
@@ -507,7 +507,7 @@ def gemm_nt_mask_tf32x3(A_hi, A_lo, B_hi, B_lo, mask32, F=None, FT=None, skip=No
     ft_block = FTh.shape[2] if blocked else 0
     ldft = 0 if (FTh is None or blocked) else ld(FTh)
     rc = _lib.lib().decomp_gemm_nt_mask_tf32x3(_p(A_hi), _p(A_lo), ld(A_hi), _p(B_hi), _p(B_lo), ld(B_hi), M, N, K,
-                                               _p(mask32), ld(mask32) if mask32 is not None else 0, _p(Fh), _p(Fl),
+                                               _p(mask32), ld(mask32) if mask32 is not None else 0, cwidth, _p(Fh), _p(Fl),
                                                ld(Fh) if Fh is not None else 0, _p(FTh), _p(FTl), ldft, ft_block,
                                                _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_gemm_nt_mask_tf32x3')
@@ -530,6 +530,15 @@ def lasso_resident(Q_rhs, M, epi, momentum, skip=None):
     rc = _lib.lib().decomp_lasso_resident_f64(_p(Q_rhs), ld(Q_rhs), M, N, ctypes.byref(epi), len(momentum), mom,
                                               _p(skip), _lib.stream_ptr())
     _lib.check(rc, 'decomp_lasso_resident_f64')
+    _count(1)
+
+
+def prox_apply(P, epi, w_hi, w_lo, skip=None):
+    """The masked iteration's FP64 pass: z = w + step (other - P), threshold / momentum / convergence as proxq_apply."""
+    M, N = P.shape
+    rc = _lib.lib().decomp_prox_apply_f64(_p(P), ld(P), ctypes.byref(epi), _p(w_hi), _p(w_lo), ld(w_hi), M, N,
+                                          _p(skip), _lib.stream_ptr())
+    _lib.check(rc, 'decomp_prox_apply_f64')
     _count(1)
 
 

@@ -230,15 +230,15 @@ int decomp_nmf_xupdate_tf32x3(const float* Y_hi, const float* Y_lo, int64_t ldy,
                               int64_t ldneg, float* X_hi, float* X_lo, int64_t ldxh, float* XT_hi, float* XT_lo,
                               int64_t ldxt, int64_t xt_block, const int32_t* skip_if, void* stream);
 /* The masked model's [rows, f] intermediate on the tcgen05 tensor cores (grads.py:112,114,122,124: f = x.dot(d) * mask;
- * lasso.py:262 the same with w, A):  F = (A . B^T) * mask, A_* [M,K], B_* [N,K] TF32 pairs, mask [M,N] FP32 (null: no
- * mask), the product rounded once to FP32 and written as a TF32 pair -- row-major (F_hi, F_lo [M][ldf]: A operand of
+ * lasso.py:262 the same with w, A):  F = (A . B^T) * mask, A_* [M,K], B_* [N,K] TF32 pairs, mask [M, N / cwidth] FP32 (null: no
+ * mask; cwidth 2: interleaved complex columns share one entry), the product rounded once to FP32 and written as a TF32 pair -- row-major (F_hi, F_lo [M][ldf]: A operand of
  * F D^T) when F_hi != NULL, and / or transposed (FT_hi, FT_lo: [N][ldft] when ft_block == 0, else K-blocked
  * [ceil(M / ft_block)][N][ft_block], ft_block % 128 == 0, tail zero-filled by the caller once: B operand of x^T F)
  * when FT_hi != NULL.  Any M, N, K. */
 int decomp_gemm_nt_mask_tf32x3(const float* A_hi, const float* A_lo, int64_t lda, const float* B_hi, const float* B_lo,
                                int64_t ldb, int64_t M, int64_t N, int64_t K, const float* mask, int64_t ldmask,
-                               float* F_hi, float* F_lo, int64_t ldf, float* FT_hi, float* FT_lo, int64_t ldft,
-                               int64_t ft_block, const int32_t* skip_if, void* stream);
+                               int32_t cwidth, float* F_hi, float* F_lo, int64_t ldf, float* FT_hi, float* FT_lo,
+                               int64_t ldft, int64_t ft_block, const int32_t* skip_if, void* stream);
 /* out (FP32) = A (FP64), round to nearest: the mask of the TF32-split masked path, once per solve */
 int decomp_to_f32_f64(const double* A, int64_t lda, int64_t rows, int64_t cols, float* out, int64_t ldo, void* stream);
 /* TF32 pair of A^T from A [rows, cols] FP64 (y^T, once per solve): hiT/loT [cols][ldt] FP32 when block == 0, else
@@ -250,6 +250,11 @@ int decomp_split_transpose_tf32_f64(const double* A, int64_t lda, int64_t rows, 
  * w_next is written as the TF32 pair (w_hi, w_lo) the next decomp_gemm_nt_tf32x3 reads. */
 int decomp_proxq_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
                            int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream);
+/* The same pass for the masked iteration (lasso.py:259-271; the DECOMP_EPI_PROX epilogue of the FP64 GEMMs):
+ * z = w + step (other - P) with w = w_hi + w_lo and P = ((w A) * mask) A^H, threshold step * colvec * rowvec
+ * (rowvec NULL: step * colvec, or colvec itself with DECOMP_EPI_FLAG_COLVEC_IS_THRESHOLD); epi->step is required. */
+int decomp_prox_apply_f64(const float* P, int64_t ldp, const decomp_epilogue_t* epi, float* w_hi, float* w_lo,
+                          int64_t ldw, int64_t M, int64_t N, const int32_t* skip_if, void* stream);
 
 /* `iters` (1..DECOMP_LASSO_RESIDENT_MAX_ITERS) unmasked ISTA / FISTA iterations in ONE launch with the iterate
  * resident on chip (lasso.py:244-271, 405-414 with the gradient step folded into Q as for DECOMP_EPI_PROXQ):

@@ -65,9 +65,9 @@ def test_lasso_tf32x3_unsupported_shapes():
     A, y, mask, _ = gc._lasso_data((50,), 5, 10, 0)
     with pytest.raises(NotImplementedError):
         lasso.solve(y, A, 0.05, precision='tf32x3')                    # k = 5 is not a multiple of 32
-    A, y, mask, _ = gc._lasso_data((50,), 32, 40, 0)
+    A, y, mask, _ = gc._lasso_data((50,), 5, 10, 0)
     with pytest.raises(NotImplementedError):
-        lasso.solve(y, A, 0.05, mask=mask, precision='tf32x3')          # masked iteration is FP64 only
+        lasso.solve(y, A, 0.05, mask=mask, precision='tf32x3')          # masked iteration: even real width
     with pytest.raises(ValueError):
         lasso.solve(y, A, 0.05, precision='fp16')
 
@@ -190,7 +190,7 @@ def test_nmf_tf32x3_convergence_and_unsupported():
     assert 1 < it32 < 400 and abs(it32 - it64) <= 3
     assert np.max(np.abs(D32 - D64)) / np.max(np.abs(D64)) <= 1.0e-3
     with pytest.raises(NotImplementedError):
-        nmf.solve(y, D0.copy(), mask=mask, likelihood='kl', precision='tf32x3')
+        nmf.solve(np.abs(y), D0.copy(), mask=mask, likelihood='kl', precision='tf32x3')
     y2, D2, _ = gc._nmf_data(100, 20, 3, 0)
     with pytest.raises(NotImplementedError):
         nmf.solve(y2, D2.copy(), precision='tf32x3')                     # k = 3
@@ -324,3 +324,31 @@ def test_nmf_masked_tf32x3_convergence():
     it32, D32, _ = nmf.solve(y, D0.copy(), tol=1e-4, maxiter=400, mask=mask, precision='tf32x3')
     assert 1 < it32 < 400 and abs(it32 - it64) <= 3
     assert np.max(np.abs(D32 - D64)) / np.max(np.abs(D64)) <= 1.0e-3
+
+
+@pytest.mark.parametrize('method,complex_,k,f', [('fista', False, 64, 100), ('ista', False, 30, 257),
+                                                 ('fista_pos', False, 128, 300), ('fista', True, 16, 40),
+                                                 ('ista', True, 33, 130)])
+def test_lasso_masked_tf32x3_vs_fp64(method, complex_, k, f):
+    """Masked iteration ((w A) * M) A^H with both GEMMs on tcgen05 against the FP64 path."""
+    from decomp_b200 import lasso
+    from oracle import decomp_oracle as orc
+    A, y, mask, _ = gc._lasso_data((2500,), k, f, 9, complex_=complex_, positive=method.endswith('_pos'))
+    it64, x64 = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=60, mask=mask)
+    it32, x32 = lasso.solve(y, A, 0.05, tol=0.0, method=method, maxiter=60, mask=mask, precision='tf32x3')
+    assert it64 == it32 == 59
+    err = np.max(np.abs(x32 - x64)) / np.max(np.abs(x64))
+    o64, o32 = orc.lasso_objective(y, A, x64, 0.05, mask), orc.lasso_objective(y, A, x32, 0.05, mask)
+    print('masked lasso tf32x3 %s complex=%s k=%d f=%d: x rel err %.3g objective %.3g'
+          % (method, complex_, k, f, err, abs(o32 - o64) / abs(o64)))
+    assert err <= X_RTOL, 'x rel err %g' % err
+    assert abs(o32 - o64) <= OBJ_RTOL * abs(o64)
+
+
+def test_lasso_masked_tf32x3_convergence():
+    from decomp_b200 import lasso
+    A, y, mask, _ = gc._lasso_data((700,), 32, 60, 4)
+    it64, x64 = lasso.solve(y, A, 0.05, tol=1e-5, method='fista', maxiter=500, mask=mask)
+    it32, x32 = lasso.solve(y, A, 0.05, tol=1e-5, method='fista', maxiter=500, mask=mask, precision='tf32x3')
+    assert 0 < it32 < 499 and abs(it32 - it64) <= 10
+    assert np.max(np.abs(x32 - x64)) / np.max(np.abs(x64)) <= 1.0e-3
