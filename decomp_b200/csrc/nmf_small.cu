@@ -10,6 +10,8 @@
 // Plain FP64 FMAs (the problems are far too small for the tensor pipe to matter).  k <= 32.
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace dcp {
@@ -263,6 +265,12 @@ static size_t small_smem_bytes(int f, int k, int R, bool masked) {
 static void small_plan(int64_t n, int* grid, int* R) {
   const int sms = num_sms();
   long long r = (n + sms - 1) / sms;
+  // DECOMP_SMALL_ROWS: lower bound on the rows per CTA (fewer CTAs: cheaper grid barriers and slab sums, longer row pass)
+  static const long long min_rows = [] {
+    const char* e = getenv("DECOMP_SMALL_ROWS");
+    return e != nullptr ? atoll(e) : 0ll;
+  }();
+  if (r < min_rows) r = min_rows;
   if (r < 1) r = 1;
   *R = (int)r;
   *grid = (int)((n + r - 1) / r);

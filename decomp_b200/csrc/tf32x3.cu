@@ -117,7 +117,7 @@ constexpr int TSMEM_BYTES = TSTAGES * TSTAGE_BYTES + 16 * 8;
 __host__ __device__ constexpr int tf_epi_warps(int mode) { return mode == 2 ? 4 : 8; }
 __host__ __device__ constexpr int tf_threads(int mode) { return (4 + tf_epi_warps(mode)) * 32; }
 // FMASK: one padded 32 x 32 staging tile per epilogue warp behind the barriers
-__host__ __device__ constexpr int tf_tile_bytes(int mode) { return mode == 3 ? tf_epi_warps(mode) * 32 * 33 * 4 : 0; }
+__host__ __device__ constexpr int tf_tile_bytes(int mode) { return mode == 3 ? tf_epi_warps(mode) * 32 * 32 * 4 : 0; }
 
 // what the epilogue warps do with a finished 128 x mma_n accumulator tile
 constexpr int TF_STORE = 0;     // P[row][n0 + c] = acc                              (FP32)
@@ -218,33 +218,116 @@ __device__ __forceinline__ void tf32_epilogue_chunk(const Tf32Args& a, const uin
 // chunk is turned through a padded shared-memory tile: lane = column for the mask loads and the row-major stores
 // (128 contiguous bytes per instruction), lane = row again for the transposed stores.  The mask values of a chunk are
 // fetched one chunk ahead of the accumulator they multiply.
-constexpr int TF_TILE_LD = 33;
-constexpr int TF_TILE_BYTES = 32 * TF_TILE_LD * 4;          // per epilogue warp
-
-// mask[r0 + i][col] for i = 0..31 of this lane's column (1 where there is no mask, 0 beyond the edges)
-__device__ __forceinline__ void fmask_load(const Tf32Args& a, long long r0, int col, float (&m)[32]) {
-  const bool live = col < a.N;
-  if (a.NEG == nullptr) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) m[i] = 1.f;
-    return;
-  }
-  const float* mk = a.NEG + r0 * a.ldneg + (a.cw == 2 ? col >> 1 : col);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) m[i] = (live && r0 + i < a.M) ? __ldcs(mk + i * a.ldneg) : 0.f;
+// The interior of the matrix (whole 32 x 32 chunks) takes a path of 16-byte accesses with the lanes laid out as 8
+// column quads x 4 rows -- the first version with 4-byte accesses and per-element predicates executed ~1600 warp
+// instructions per chunk and was issue-bound (ncu: 42 % issue active with two busy warps per scheduler).
+constexpr int TF_TILE_BYTES = 32 * 32 * 4;                  // per epilogue warp
+// staging tile: 32 rows of 8 16-byte column quads, quad q of row r stored at position q ^ (r & 7) -- a quarter warp
+// that writes one quad of 8 consecutive rows, or reads the 8 quads of one row, touches all 32 banks once
+__device__ __forceinline__ int tidx(int row, int col) {
+  return row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3));
 }
 
-// v: this thread's row of the chunk (lane = row); m: the mask of this lane's column (lane = column)
-__device__ __forceinline__ void fmask_chunk(const Tf32Args& a, const uint32_t (&v)[32], const float (&m)[32],
-                                            long long r0, int col0, float* tile, int lane) {
+__device__ __forceinline__ bool fmask_interior(const Tf32Args& a, long long r0, int col0) {
+  return r0 + 32 <= a.M && col0 + 32 <= a.N;
+}
+
+// interior chunk: this lane's mask values for rows r0 + (lane >> 3) + 4 t, t = 0..7, columns col0 + 4 (lane & 7) .. + 3
+__device__ __forceinline__ void fmask_prefetch(const Tf32Args& a, long long r0, int col0, int lane, float4 (&m)[8]) {
+  if (a.NEG == nullptr || !fmask_interior(a, r0, col0)) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) tile[lane * TF_TILE_LD + j] = __uint_as_float(v[j]);
-  __syncwarp();
+    for (int t = 0; t < 8; ++t) m[t] = make_float4(1.f, 1.f, 1.f, 1.f);
+    return;
+  }
+  const int cq = (lane & 7) * 4;
+  const long long rr = r0 + (lane >> 3);
+  if (a.cw == 2) {
+    const float* mk = a.NEG + rr * a.ldneg + ((col0 + cq) >> 1);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float2 q = __ldcs(reinterpret_cast<const float2*>(mk + 4 * t * a.ldneg));
+      m[t] = make_float4(q.x, q.x, q.y, q.y);
+    }
+  } else {
+    const float* mk = a.NEG + rr * a.ldneg + col0 + cq;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) m[t] = __ldcs(reinterpret_cast<const float4*>(mk + 4 * t * a.ldneg));
+  }
+}
+
+__device__ __forceinline__ void split4(const float4 p, float4& h, float4& l) {
+  h = make_float4(to_tf32(p.x), to_tf32(p.y), to_tf32(p.z), to_tf32(p.w));
+  l = make_float4(to_tf32(p.x - h.x), to_tf32(p.y - h.y), to_tf32(p.z - h.z), to_tf32(p.w - h.w));
+}
+
+// v: this thread's row of the chunk (lane = row); m: fmask_prefetch's values
+__device__ __forceinline__ void fmask_chunk_interior(const Tf32Args& a, const uint32_t (&v)[32], const float4 (&m)[8],
+                                                     long long r0, int col0, float* tile, int lane) {
+  const int cq = (lane & 7) * 4, rq = lane >> 3;
+  if (a.Xh != nullptr) {
+    // accumulator rows -> tile -> (4 rows x 8 column quads) per instruction: 128 contiguous bytes per row
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(tile + tidx(lane, 4 * j)) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                      __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    float* fh = a.Xh + (r0 + rq) * a.ldxh + col0 + cq;
+    float* fl = a.Xl + (r0 + rq) * a.ldxh + col0 + cq;
+    const long long step4 = 4 * a.ldxh;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float4 acc = *reinterpret_cast<const float4*>(tile + tidx(rq + 4 * t, cq));
+      float4 h, l;
+      split4(make_float4(acc.x * m[t].x, acc.y * m[t].y, acc.z * m[t].z, acc.w * m[t].w), h, l);
+      *reinterpret_cast<float4*>(fh) = h;
+      *reinterpret_cast<float4*>(fl) = l;
+      fh += step4;
+      fl += step4;
+    }
+    __syncwarp();
+  }
+  if (a.XTh != nullptr) {
+    // mask -> tile -> this thread's row; a warp then writes 32 consecutive rows of one column: 128 contiguous bytes
+#pragma unroll
+    for (int t = 0; t < 8; ++t) *reinterpret_cast<float4*>(tile + tidx(rq + 4 * t, cq)) = m[t];
+    __syncwarp();
+    const long long row = r0 + lane;
+    const long long tstride = a.xt_block > 0 ? a.xt_block : a.ldxt;
+    const long long tbase = (a.xt_block > 0 ? (row / a.xt_block) * (long long)a.N * a.xt_block + row % a.xt_block : row) +
+                            (long long)col0 * tstride;
+    float* th = a.XTh + tbase;
+    float* tl = a.XTl + tbase;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 mm = *reinterpret_cast<const float4*>(tile + tidx(lane, 4 * j));
+      float4 h, l;
+      split4(make_float4(__uint_as_float(v[4 * j]) * mm.x, __uint_as_float(v[4 * j + 1]) * mm.y,
+                         __uint_as_float(v[4 * j + 2]) * mm.z, __uint_as_float(v[4 * j + 3]) * mm.w), h, l);
+      th[0] = h.x; tl[0] = l.x;
+      th[tstride] = h.y; tl[tstride] = l.y;
+      th[2 * tstride] = h.z; tl[2 * tstride] = l.z;
+      th[3 * tstride] = h.w; tl[3 * tstride] = l.w;
+      th += 4 * tstride;
+      tl += 4 * tstride;
+    }
+    __syncwarp();
+  }
+}
+
+// edge chunk (ragged rows / columns), accumulator rows already in the tile: per-element predicates, 4-byte accesses,
+// its own mask loads
+// (not inlined, and the accumulator chunk comes through the tile: its register needs stay out of the interior path)
+__device__ __noinline__ void fmask_chunk_edge(const Tf32Args& a, long long r0, int col0, float* tile, int lane) {
   const int col = col0 + lane;
   const bool live = col < a.N;
+  const float* mk = a.NEG != nullptr ? a.NEG + r0 * a.ldneg + (a.cw == 2 ? col >> 1 : col) : nullptr;
   float p[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) p[i] = tile[i * TF_TILE_LD + lane] * m[i];
+  for (int i = 0; i < 32; ++i) {
+    const float m = mk == nullptr ? 1.f : ((live && r0 + i < a.M) ? mk[i * a.ldneg] : 0.f);
+    p[i] = tile[tidx(i, lane)] * m;
+  }
   if (a.Xh != nullptr) {
     float* fh = a.Xh + r0 * a.ldxh + col;
     float* fl = a.Xl + r0 * a.ldxh + col;
@@ -257,10 +340,9 @@ __device__ __forceinline__ void fmask_chunk(const Tf32Args& a, const uint32_t (&
       }
   }
   if (a.XTh != nullptr) {
-    // back to lane = row: a warp writes 32 consecutive rows of one column, 128 contiguous bytes
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tile[i * TF_TILE_LD + lane] = p[i];
+    for (int i = 0; i < 32; ++i) tile[tidx(i, lane)] = p[i];
     __syncwarp();
     const long long row = r0 + lane;
     const long long tbase = a.xt_block > 0 ? (row / a.xt_block) * (long long)a.N * a.xt_block + row % a.xt_block : row;
@@ -268,7 +350,7 @@ __device__ __forceinline__ void fmask_chunk(const Tf32Args& a, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (row < a.M && col0 + j < a.N) {
-        const float q = tile[lane * TF_TILE_LD + j];
+        const float q = tile[tidx(lane, j)];
         const float h = to_tf32(q);
         const long long ti = tbase + (long long)(col0 + j) * tstride;
         a.XTh[ti] = h;
@@ -286,19 +368,31 @@ __device__ __forceinline__ void tf32_epilogue_tile(const Tf32Args& a, uint32_t t
                                                    float* tile, int lane) {
   if constexpr (MODE == TF_FMASK) {
     const long long r0 = row - lane;
-    float mcur[32];
-    fmask_load(a, r0, n0 + first + lane, mcur);          // in flight while the MMAs of this tile are still running
+    float4 mcur[8];
+    fmask_prefetch(a, r0, n0 + first, lane, mcur);       // in flight while the MMAs of this tile are still running
     mbar_wait(acc_full, acc_ph);
     tc_fence_after();
     for (int c0 = first; c0 < N; c0 += step) {
-      float mnext[32];
-      if (c0 + step < N) fmask_load(a, r0, n0 + c0 + step + lane, mnext);
+      float4 mnext[8];
+      if (c0 + step < N) fmask_prefetch(a, r0, n0 + c0 + step, lane, mnext);
       uint32_t v[32];
       tmem_ld32(taddr + (uint32_t)c0, v);
-      if (r0 < a.M && n0 + c0 < a.N) fmask_chunk(a, v, mcur, r0, n0 + c0, tile, lane);   // warp-uniform condition
+      if (r0 < a.M && n0 + c0 < a.N) {                   // warp-uniform conditions
+        if (fmask_interior(a, r0, n0 + c0)) {
+          fmask_chunk_interior(a, v, mcur, r0, n0 + c0, tile, lane);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(tile + tidx(lane, 4 * j)) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
+          fmask_chunk_edge(a, r0, n0 + c0, tile, lane);
+        }
+      }
       if (c0 + step < N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mcur[j] = mnext[j];
+        for (int t = 0; t < 8; ++t) mcur[t] = mnext[t];
       }
     }
   } else {
@@ -454,7 +548,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     // ------------------------------------------------------------------ epilogue: TMEM -> registers -> memory
     const int e = (warp - 4) & 3;           // TMEM lane quarter this warp may access (warp % 4)
     const int half = (warp - 4) >> 2;       // which of the alternate chunks
-    float* tile = reinterpret_cast<float*>(smem + TSTAGES * TSTAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 33);
+    float* tile = reinterpret_cast<float*>(smem + TSTAGES * TSTAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 32);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -703,7 +797,7 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
     const int e = (warp - 4) & 3, half = (warp - 4) >> 2;
-    float* tile = reinterpret_cast<float*>(smem + T2_STAGES * T2_STAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 33);
+    float* tile = reinterpret_cast<float*>(smem + T2_STAGES * T2_STAGE_BYTES + 16 * 8) + (warp - 4) * (32 * 32);
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int item = first; item < items; item += stride) {
@@ -1183,6 +1277,10 @@ int decomp_gemm_nt_mask_tf32x3(const float* A_hi, const float* A_lo, int64_t lda
       (transposed && FT_lo == nullptr) || (mask != nullptr && (ldmask & 3)) || M > 2147483647LL || N > 2147483647LL ||
       K > 2147483647LL) {
     set_error("decomp_gemm_nt_mask_tf32x3: needs K > 0, an output, ldf and ldmask multiples of 4");
+    return DECOMP_ERR_INVALID;
+  }
+  if (mask != nullptr && (reinterpret_cast<uintptr_t>(mask) & 15u) != 0) {
+    set_error("decomp_gemm_nt_mask_tf32x3: the mask must be 16-byte aligned");
     return DECOMP_ERR_INVALID;
   }
   if (transposed && ft_block > 0 && (ft_block % 128) != 0) {
