@@ -57,6 +57,34 @@ __device__ __forceinline__ double warp_sum_s(double v) {
   return v;
 }
 
+// Sums of 16 values per lane over the warp in 16 shuffles instead of 80: every level of the xor butterfly also halves
+// the number of values a lane carries (the lane keeps the half its bit selects and receives the partner's partial sums
+// of that half).  Same pairs added at the same levels as warp_sum_s, so the sums are bitwise those.  On return lane l
+// holds the total of value (l >> 1) & 15.
+__device__ __forceinline__ double warp_sum16(double (&v)[16], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  double w8[8], w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double recv = __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 8], 16);
+    w8[i] = (b4 ? v[i + 8] : v[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double recv = __shfl_xor_sync(0xffffffffu, b3 ? w8[i] : w8[i + 4], 8);
+    w4[i] = (b3 ? w8[i + 4] : w8[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double recv = __shfl_xor_sync(0xffffffffu, b2 ? w4[i] : w4[i + 2], 4);
+    w2[i] = (b2 ? w4[i + 2] : w4[i]) + recv;
+  }
+  const double recv = __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+  double r = (b1 ? w2[1] : w2[0]) + recv;
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
 template <bool MASKED>
 __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const SmallNmfArgs a) {
   extern __shared__ __align__(16) double sm[];
@@ -125,14 +153,19 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
             q[u] += fv * d;
           }
         }
+        double pq[16];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          p[u] = warp_sum_s(p[u]);
-          q[u] = warp_sum_s(q[u]);
-          if (lane == c0 + u) {
-            mine_pos = p[u];
-            mine_neg = q[u];
-          }
+          pq[u] = p[u];
+          pq[8 + u] = q[u];
+        }
+        const double tot = warp_sum16(pq, lane);         // lane l: total of value (l >> 1) & 15
+        const int u = lane - c0;                         // lane c0 + u takes the sums of atom c0 + u
+        const double gp = __shfl_sync(0xffffffffu, tot, (2 * u) & 31);
+        const double gq = __shfl_sync(0xffffffffu, tot, (2 * u + 16) & 31);
+        if (u >= 0 && u < 8) {
+          mine_pos = gp;
+          mine_neg = gq;
         }
       }
       __syncwarp();
@@ -197,6 +230,33 @@ __global__ void __launch_bounds__(SMALL_THREADS, 1) nmf_mu_small_kernel(const Sm
       for (int e = tid; e < k * k; e += SMALL_THREADS) G_s[e] = __ldcg(total + k * f + e);   // S = x^T x
       __syncthreads();
     }
+    if (!MASKED && (k & 1) == 0) {
+      // den[c][j] = sum_b S[c][b] D[b][j]: a thread owns column j and all k denominators; per b one load of D[b][j] and
+      // S[b][c..c+1] (= S[c..c+1][b]: x^T x is bitwise symmetric) as broadcast 16-byte reads -- a third of the
+      // shared-memory loads of the entry-per-thread form below, same summation order
+      for (int j = tid; j < f; j += SMALL_THREADS) {
+        double den[SMALL_KMAX], num[SMALL_KMAX];
+#pragma unroll
+        for (int c = 0; c < SMALL_KMAX; ++c) {
+          den[c] = 0.0;
+          num[c] = c < k ? __ldcg(total + c * f + j) : 0.0;
+        }
+        for (int b = 0; b < k; ++b) {
+          const double d = D_s[b * f + j];
+          const double2* g = reinterpret_cast<const double2*>(G_s + b * k);
+#pragma unroll
+          for (int c = 0; c < SMALL_KMAX; c += 2)
+            if (c < k) {
+              const double2 g2 = g[c >> 1];
+              den[c] += g2.x * d;
+              den[c + 1] += g2.y * d;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < SMALL_KMAX; ++c)
+          if (c < k) Dn_s[c * f + j] = D_s[c * f + j] * fmax(num[c], 0.0) / fmax(den[c], kEpsS);
+      }
+    } else
     for (int e0 = tid; e0 < k * f; e0 += 4 * SMALL_THREADS) {      // four entries per thread in flight
       double den[4], num[4];
       int ee[4];
