@@ -749,7 +749,7 @@ def run_ours(args):
                                    'rows sharded over %d GPU(s), statistics reduce-scattered along f' % (n4, f4, steps4, mb, k4, world)}}
         del y4, D04, m4, Dt, D4, x4
         torch.cuda.empty_cache()
-        # configs[0]: NMF-MU 1000 x 200, k = 20, 100 sweeps through nmf.solve with host arrays (launch-bound: CUDA graph)
+        # configs[0]: NMF-MU 1000 x 200, k = 20, 100 sweeps through nmf.solve with host arrays (one cooperative launch)
         sys.path.insert(0, os.path.join(ROOT, 'tests'))
         import golden_cases as gc
         y1, D1, _ = gc._nmf_data(1000, 200, 20, 0, 'l2', reference_order=False)
@@ -758,8 +758,8 @@ def run_ours(args):
         extra['c1_nmf_small'] = {
             'value': 100.0 / t1, 'unit': 'sweeps/s', 'ms_per_call': t1 * 1e3, 'calls_ms': [t * 1e3 for t in times1],
             'config': {'workload': 'NMF-MU l2, y 1000x200 float64, k=20, 100 sweeps, one nmf.solve call with numpy '
-                                   'arrays in and out (BASELINE.json configs[0]); launch-bound, sweeps replayed from '
-                                   'a CUDA graph'}}
+                                   'arrays in and out (BASELINE.json configs[0]); all sweeps in one cooperative launch '
+                                   '(decomp_nmf_mu_small_f64)'}}
         if cpu_arm_mod is not None:
             t0 = time.perf_counter()
             cpu.nmf(y1, D1.copy(), tol=0.0, maxiter=101)
