@@ -481,6 +481,12 @@ def run_ours(args):
     # ---------------------------------------------------------------- NMF-MU (secondary): weak and strong scaling
     def nmf_leg(n_rows, label, masked=False, shape=NMF, tf32=False):
         f, k = shape['f'], shape['k']
+
+        def sweep_traffic(key):
+            # DRAM bytes of one sweep from the committed ncu pass at `sweep_rows` rows, scaled to this leg's rows
+            v = traffic.get(key)
+            return v * n_rows / float(traffic.get('sweep_rows', n_rows)) if v is not None else None
+
         Kn, Wn, Rn = max(2, args.nmf_steps), 2, 3
         y, D0, mask = nmf_data_device(torch, n_rows, f, k, rank, device, masked=masked)
         X = torch.ones((n_rows, k), dtype=torch.float64, device=device)
@@ -516,7 +522,8 @@ def run_ours(args):
             'allreduce_bytes_per_sweep': (2 * k * f if masked else k * f + k * k) * 8 if world > 1 else 0,
             'roofline': {'bound': 'tensor', 'achieved': flops_sweep / t_sweep / 1e12, 'peak': dmma_peak,
                          'unit': 'TFLOP/s', 'frac': flops_sweep / t_sweep / 1e12 / dmma_peak,
-                         'traffic': traffic.get('nmf_sweep_dram_bytes' if not masked else 'nmf_masked_sweep_dram_bytes'),
+                         'traffic': sweep_traffic('nmf_sweep_dram_bytes' if not masked else 'nmf_masked_sweep_dram_bytes'),
+                         'traffic_source': traffic.get('sweep_source'),
                          'kernel': 'whole sweep (per GPU): gemm_f64_kernel<NT, MU_NUM> (Y D^T) + gemm_f64_kernel<TN> '
                                    '(X^T Y) dominate with 2nkf flop each' if not masked else
                                    'whole masked sweep (per GPU): six 2nkf GEMMs, [n,f] intermediate fused where the '
@@ -547,7 +554,7 @@ def run_ours(args):
                 'max_rel_diff_D_vs_fp64': err, 'sweeps_compared': Wn + Rn * Kn,
                 'speedup_vs_fp64': t_sweep / t32,
                 'roofline': {'bound': 'tensor', 'achieved': fl32 / t32 / 1e12, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                             'frac': fl32 / t32 / 1e12 / tf_peak, 'traffic': traffic.get('nmf_tf32x3_sweep_dram_bytes'),
+                             'frac': fl32 / t32 / 1e12 / tf_peak, 'traffic': sweep_traffic('nmf_tf32x3_sweep_dram_bytes'),
                              'peak_source': tf_src,
                              'algorithmic_flops_per_sweep': fl32,
                              'note': 'three TF32 products per FP64-equivalent product (hi*hi + hi*lo + lo*hi): 3 x (4nkf + '
@@ -565,7 +572,7 @@ def run_ours(args):
                 by32m = 56.0 * n_rows * f + 10.0 * n_rows * k * 8
                 res['tf32x3']['roofline'] = {
                     'bound': 'hbm', 'achieved': by32m / t32 / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': by32m / t32 / 1e9 / hbm_peak, 'traffic': traffic.get('nmf_masked_tf32x3_sweep_dram_bytes'),
+                    'frac': by32m / t32 / 1e9 / hbm_peak, 'traffic': sweep_traffic('nmf_masked_tf32x3_sweep_dram_bytes'),
                     'algorithmic_bytes_per_sweep': by32m,
                     'note': 'per row and feature: y*mask as a TF32 pair row-major and transposed (8 + 8 B), the FP32 '
                             'mask twice (4 + 4 B), f = (x D)*mask written and read as a TF32 pair twice (2 x 16 B)',
