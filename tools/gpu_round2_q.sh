@@ -1,13 +1,24 @@
 #!/bin/bash
+# final 8-GPU pass: the driver's scaling command at N=8 for both arms, then N=2 for ours
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2q_pytest.log
-tail -3 gpurun_out/r2q_pytest.log
-timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --legs nmf,tf32 > gpurun_out/r2q_bench_nmf.json 2> gpurun_out/r2q_bench_nmf.err; echo "rc=$?" >> gpurun_out/r2q_bench_nmf.err
+nvidia-smi -L | wc -l > gpurun_out/r2q_gpus.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --impl reference --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2q_bench8_ref.json 2> gpurun_out/r2q_bench8_ref.err
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r2q_bench8.json 2> gpurun_out/r2q_bench8.err; echo "rc=$?" >> gpurun_out/r2q_bench8.err
+tail -3 gpurun_out/r2q_bench8.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2q_bench2.json 2> gpurun_out/r2q_bench2.err; echo "rc=$?" >> gpurun_out/r2q_bench2.err
 python - <<'PY'
 import json
-try:
-    b=json.load(open('gpurun_out/r2q_bench_nmf.json')); t=b['tf32x3']
-    print('tf32 ms', t['ms_per_step'], 'frac', t['roofline']['frac'], 'err', t['max_rel_diff_D_vs_fp64'], 'fp64', b['ms_per_step'])
-except Exception as e:
-    print('failed', e)
+for n in ('r2q_bench8','r2q_bench2'):
+    try:
+        b=json.loads(open('gpurun_out/%s.json'%n).read().strip().splitlines()[-1])
+        print(n, 'fista %.4g frac %.3f'%(b['value'], b['roofline']['frac']), 'e2e ms', b['e2e']['ms_per_call'], 'pinned', b['e2e_pinned']['ms_per_call'], 'h2d', b['e2e']['h2d_copy_only']['ms'], b['e2e']['h2d_copy_only']['gbs_all_gpus'])
+        s=b['secondary_strong']; print('  strong ms', s['ms_per_step'], 'allreduce', s['allreduce_ms_per_sweep'], 'tf32', s.get('tf32x3',{}).get('ms_per_step'))
+        if 'secondary' in b: print('  weak ms', b['secondary']['ms_per_step'], b['secondary'].get('tf32x3',{}).get('ms_per_step'))
+        print('  parity', b['parity_multi_gpu']['pass'], b['parity_multi_gpu']['worst_error_over_ranks'])
+        for k,v in b.get('extra_configs',{}).items():
+            print('  ', k, 'ms', v.get('ms_per_step', v.get('ms_per_call')), 'frac', v.get('roofline',{}).get('frac'), 'tf32', v.get('tf32x3',{}).get('ms_per_step'))
+        print('  errors', b.get('errors'))
+    except Exception as e:
+        print(n, 'failed', e)
 PY
+tail -c 300 gpurun_out/r2q_bench8_ref.json
