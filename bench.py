@@ -424,6 +424,32 @@ def run_ours(args):
                              'algorithmic_bytes_per_iteration': bytes32, 'peak_source': hbm_src},
             }
         # ---- end to end through the public API: ordinary numpy arrays first, page-locked ones beside
+        # ---- the other reading of "A 256x1024" (SURVEY.md 8, C2 caveat): 1024 atoms over 256 channels (compressed
+        # sensing, over-complete).  The iterate is 1024 doubles wide: one gemm_f64_proxq_kernel launch per iteration
+        if 'configs' in legs:
+            k2, f2 = FISTA['f'], FISTA['k']
+            y2, A2 = fista_data_device(torch, B, k2, f2, rank, device)
+            s2 = lasso.LassoSolver(y2, A2, alpha, None, 0.0, 100000, 'fista', False)
+            s2.iterate(0, 3)
+            ms2, l2_, c2_ = timed_regions(lambda r: s2.iterate(3 + 5 * r, 8 + 5 * r), 3)
+            leg_clocks['fista_1024x256'] = c2_
+            t2 = median(ms2) * 1e-3 / 5
+            fl2, by2 = 2.0 * B * k2 * k2, 5.0 * B * k2 * 8
+            out['fista_overcomplete'] = {
+                'value': B * world / t2, 'unit': 'problem-iters/s', 'iters_per_s': 1.0 / t2, 'ms_per_step': t2 * 1e3,
+                'launches_per_iteration': l2_ / 5.0,
+                'finite': bool(torch.isfinite(s2.X).all().item()),
+                'roofline': {'bound': 'tensor', 'achieved': fl2 / t2 / 1e12, 'peak': dmma_peak, 'unit': 'TFLOP/s',
+                             'frac': fl2 / t2 / 1e12 / dmma_peak, 'traffic': None,
+                             'kernel': 'gemm_f64_proxq_kernel (one FISTA iteration per launch, K = N = 1024)',
+                             'algorithmic_flops_per_iteration': fl2,
+                             'hbm': {'algorithmic_bytes_per_iteration': by2, 'achieved_gbs': by2 / t2 / 1e9,
+                                     'peak_gbs': hbm_peak}},
+                'config': {'workload': 'batched FISTA Lasso, %d problems per GPU, A (%d,%d): the compressed-sensing '
+                                       'reading of BASELINE.json configs[1] (SURVEY.md 8 C2 caveat), float64, tol=0'
+                                       % (B, k2, f2)}}
+            del s2, y2, A2
+            torch.cuda.empty_cache()
         if 'e2e' in legs:
             y_np, A_np = y.cpu().numpy(), A.cpu().numpy()              # pageable host arrays
             del y
@@ -813,6 +839,8 @@ def run_ours(args):
             for key in ('e2e', 'e2e_pinned', 'tf32x3'):
                 if key in prim:
                     line[key] = prim[key]
+            if 'fista_overcomplete' in out:
+                line['fista_overcomplete'] = out['fista_overcomplete']
             if cpu_f is not None:
                 line['cpu_baseline'] = cpu_f
         else:
