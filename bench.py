@@ -800,8 +800,63 @@ def run_ours(args):
             extra['c1_nmf_small']['cpu_baseline'] = {'value': 100.0 / dt, 'unit': 'sweeps/s', 'cores': cpu_cores,
                                                      'kind': cpu.kind, 'sample': 'the same call (%.3f s), %s' % (dt, cpu.where)}
 
+    def leg_configs_cpu():
+        """SURVEY.md 8(d) CPU plan for configs[3] and configs[4]: the reference at a stated reduced n, in rows per
+        second (its [n, f] / [mb, f, k] temporaries do not fit or finish at full size)."""
+        extra = out.setdefault('extra_configs', {})
+        rng = np.random.RandomState(5)
+        # ---- configs[4]: masked NMF sweep and masked FISTA iteration at 131072 / 32768 rows x 1024, k = 128
+        f5, k5 = C5['f'], C5['k']
+        n5 = 131072
+        Dt = np.maximum(rng.randn(k5, f5), 0.0)
+        y5 = np.maximum(rng.randn(n5, k5), 0.0).dot(Dt) + 0.1 * rng.randn(n5, f5)
+        D05 = np.maximum(Dt + 0.3 * rng.randn(k5, f5), 0.1)
+        m5 = (rng.rand(n5, f5) > 0.1).astype(np.float64)
+        t0 = time.perf_counter()
+        cpu.nmf(y5, D05.copy(), tol=0.0, maxiter=3, mask=m5)
+        dt = time.perf_counter() - t0
+        if 'c5_masked_nmf_sweep' in extra:
+            extra['c5_masked_nmf_sweep']['cpu_baseline'] = {
+                'value': n5 * 2 / dt, 'unit': 'row-iters/s', 'cores': cpu_cores, 'kind': cpu.kind,
+                'sample': 'n = %d rows x %d, k=%d, 10 %% mask, 2 sweeps of nmf.solve (%.1f s), %s'
+                          % (n5, f5, k5, dt, cpu.where)}
+        b5 = 32768
+        t0 = time.perf_counter()
+        cpu.lasso(y5[:b5], D05, 0.1, tol=0.0, method='fista', maxiter=10, mask=m5[:b5])
+        dt = time.perf_counter() - t0
+        if 'c5_masked_fista_iter' in extra:
+            extra['c5_masked_fista_iter']['cpu_baseline'] = {
+                'value': b5 * 10 / dt, 'unit': 'problem-iters/s', 'cores': cpu_cores, 'kind': cpu.kind,
+                'sample': '%d problems, A (%d,%d), 10 %% mask, 10 FISTA iterations in one lasso.solve call (%.1f s, '
+                          'set-up included), %s' % (b5, k5, f5, dt, cpu.where)}
+        del y5, m5
+        # ---- configs[3]: ONE minibatch step of 128 rows (the reference materialises [mb, f, k] complex, 2.1 GB here, and
+        # makes several single-threaded passes over the 8.6 GB statistics per step: ~40 s on 16 cores)
+        f4, k4, mb4 = C4['f'], C4['k'], 128
+
+        def crandn(*shape):
+            return rng.randn(*shape) + 1j * rng.randn(*shape)
+
+        Dt4 = crandn(k4, f4)
+        y4 = (crandn(mb4, k4) * rng.rand(mb4, k4)).dot(Dt4) + 0.1 * crandn(mb4, f4)
+        m4 = (rng.rand(mb4, f4) > 0.1).astype(np.float64)
+        t0 = time.perf_counter()
+        cpu.dictionary_learning(y4 * m4, Dt4 + 0.2 * crandn(k4, f4), 0.1, tol=0.0, minibatch=mb4, maxiter=2,
+                                lasso_method='fista', lasso_iter=10, mask=m4, random_seed=0)
+        dt = time.perf_counter() - t0
+        if 'c4_dl_masked_step' in extra:
+            gpu_rows = extra['c4_dl_masked_step']['minibatch'] * extra['c4_dl_masked_step']['value']
+            extra['c4_dl_masked_step']['rows_per_s'] = gpu_rows
+            extra['c4_dl_masked_step']['cpu_baseline'] = {
+                'value': mb4 / dt, 'unit': 'rows/s', 'cores': cpu_cores, 'kind': cpu.kind,
+                'sample': 'one minibatch step of %d rows (complex128, f=%d, k=%d, 10 %% mask, fista x10; '
+                          '%.1f s); a step also pays fixed passes over the [k, f, k] statistics, so rows/s grows '
+                          'with the minibatch; %s' % (mb4, f4, k4, dt, cpu.where)}
+
     if 'configs' in legs:
         guarded('configs', leg_configs)
+        if cpu_arm_mod is not None:
+            guarded('configs_cpu', leg_configs_cpu)
 
     # ---------------------------------------------------------------- multi-GPU parity self-check (outside timing)
     def leg_parity():
