@@ -19,6 +19,8 @@ The epoch shuffle uses ``numpy.random.RandomState(random_seed)`` on the host exa
 (the permutation is cumulative, utils/data.py:147-156); the rows are permuted on the device by a gather kernel
 and the final ``x`` is un-permuted the same way.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -107,6 +109,10 @@ def _pair_chunks(k, cap, device):
     return out
 
 
+OVERLAP_STATS_EXCHANGE = os.environ.get('DECOMP_DL_OVERLAP', '1') != '0'   # sharded masked statistics: reduce-scatter on
+                                                                           # a side stream under the next chunk's GEMM
+
+
 def _row_layout(n_local, group, device):
     """(total rows, first global row of this rank, ranks, rank) for row-sharded inputs."""
     if group is None:
@@ -188,9 +194,16 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
             # Hermitian half crosses the links, and no dense [k, f, k] send buffer exists): contiguous send buffers
             # of fs * world rows (rows beyond f stay zero), one per distinct chunk width
             # (row pitch rounded up to an even number of doubles: the GEMM epilogue stores 16-byte pairs)
-            Psend = {wd: torch.zeros((fs * world, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev)
-                     for wd in set(c[0].numel() for c in chunks)}
-            Precv = {wd: torch.empty((fs, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev) for wd in Psend}
+            # Two buffers per width: the reduce-scatter of chunk i runs on a side stream while the pair-product GEMM of
+            # chunk i + 1 fills the other buffer on the compute stream (OVERLAP_STATS_EXCHANGE)
+            Psend = {wd: [torch.zeros((fs * world, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev)
+                          for _ in range(2)] for wd in set(c[0].numel() for c in chunks)}
+            Precv = {wd: [torch.empty((fs, wd * cw + (wd * cw & 1)), dtype=torch.float64, device=dev)
+                          for _ in range(2)] for wd in Psend}
+            comm_stream = torch.cuda.Stream(device=dev) if OVERLAP_STATS_EXCHANGE else None
+            ev_filled = [torch.cuda.Event() for _ in range(2)]       # send buffer written (compute stream)
+            ev_reduced = [torch.cuda.Event() for _ in range(2)]      # receive buffer complete (side stream)
+            ev_folded = [torch.cuda.Event() for _ in range(2)]       # receive buffer consumed (compute stream)
             stats = torch.zeros(k * 4, dtype=torch.float64, device=dev)
             D_slab = torch.zeros((k, fs * cw), dtype=torch.float64, device=dev)
             D_all = torch.empty((world, k, fs * cw), dtype=torch.float64, device=dev)
@@ -258,19 +271,44 @@ def block_cd_device(y, D0, alpha, x, tol, minibatch, maxiter, rule, positive, la
                     if m:
                         ops.make_rhs(xr, False, False, out=Xt[:, :m])
                         ops.make_rhs(m_mb, False, False, out=Mt[:, :m])
-                    for colA, colB in chunks:
+                    cur = torch.cuda.current_stream(dev)
+                    pending = None                        # (slot, width, colA, colB) whose reduce-scatter is in flight
+                    for ci, (colA, colB) in enumerate(chunks):
                         wd = colA.numel()
-                        Pc = rview(Ptmp[:, :wd]) if not sharded else Psend[wd][:f, :wd * cw]
+                        slot = ci & 1
+                        Pc = rview(Ptmp[:, :wd]) if not sharded else Psend[wd][slot][:f, :wd * cw]
+                        # (stream order already guarantees that the reduce-scatter which last read this send buffer,
+                        # chunk ci - 2, is complete: its result was folded into S on this stream one chunk ago)
                         if m:
                             Wc = Wt[:wd * cw, :m]
                             ops.dl_pair_products_t(Xt[:, :m], cplx, colA, colB, Wc)
                             ops.gemm_nt(Mt[:, :m], Wc, ops.epilogue(ops.EPI_STORE, Pc))
                         else:
                             Pc.zero_()                    # (only a sharded run can leave a rank without rows)
-                        if sharded:
-                            comm.reduce_scatter_sum(Precv[wd], Psend[wd], group)                        # along f
-                            Pc = Precv[wd][:, :wd * cw]
-                        ops.dl_scatter_stats(Pc, cplx, colA, colB, k, beta, S)                          # S <- beta S + .
+                        if not sharded:
+                            ops.dl_scatter_stats(Pc, cplx, colA, colB, k, beta, S)                      # S <- beta S + .
+                            continue
+                        if comm_stream is None:
+                            comm.reduce_scatter_sum(Precv[wd][slot], Psend[wd][slot], group)            # along f
+                            ops.dl_scatter_stats(Precv[wd][slot][:, :wd * cw], cplx, colA, colB, k, beta, S)
+                            continue
+                        ev_filled[slot].record(cur)
+                        with torch.cuda.stream(comm_stream):
+                            comm_stream.wait_event(ev_filled[slot])
+                            comm_stream.wait_event(ev_folded[slot])   # the receive buffer's previous contents are used up
+                            comm.reduce_scatter_sum(Precv[wd][slot], Psend[wd][slot], group)
+                            ev_reduced[slot].record(comm_stream)
+                        if pending is not None:           # fold the previous chunk in while this one is on the links
+                            ps, pw, pA, pB = pending
+                            cur.wait_event(ev_reduced[ps])
+                            ops.dl_scatter_stats(Precv[pw][ps][:, :pw * cw], cplx, pA, pB, k, beta, S)
+                            ev_folded[ps].record(cur)
+                        pending = (slot, wd, colA, colB)
+                    if pending is not None:
+                        ps, pw, pA, pB = pending
+                        cur.wait_event(ev_reduced[ps])
+                        ops.dl_scatter_stats(Precv[pw][ps][:, :pw * cw], cplx, pA, pB, k, beta, S)
+                        ev_folded[ps].record(cur)
                     if m:
                         ops.mask_mul(rview(y_mb), m_mb, rview(YM[:m]), cwidth=cw)
                         ops.gemm_tn(xr, rview(YM[:m]), rview(T_dst), combine=comb, beta=beta, workspace=ws)   # :214
