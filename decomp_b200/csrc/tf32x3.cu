@@ -1,25 +1,26 @@
-// TF32-split ("3xTF32") path of the unmasked ISTA/FISTA iteration on the 5th-generation tensor cores.
+// TF32-split ("3xTF32") kernels on the 5th-generation tensor cores (precision='tf32x3'): the unmasked ISTA/FISTA
+// iteration, the NMF multiplicative update (x update fused into y D^T, split-K statistics x^T y / x^T x) and the masked
+// models' [rows, f] intermediate (x D) * mask / (w A) * mask.
 //
-//   z = c + w Q           w = w_hi + w_lo, Q = Q_hi + Q_lo   (TF32 pieces: 11 + 11 significant bits)
-//   w Q ~= w_lo Q_hi + w_hi Q_lo + w_hi Q_hi                  (three tcgen05.mma kind::tf32 per k-step, FP32
-//                                                              accumulators in tensor memory)
+//   A B^T ~= A_lo B_hi^T + A_hi B_lo^T + A_hi B_hi^T          A = A_hi + A_lo, B = B_hi + B_lo (TF32 pieces: 11 + 11
+//                                                             significant bits; three tcgen05.mma kind::tf32 per
+//                                                             k-step, FP32 accumulators in tensor memory)
 //
-// Kernel 1, tf32x3_gemm_kernel: warp-specialised, persistent, one CTA per SM.
-//   warp 0   TMA producer: per 32-wide k-block the [128, 32] tiles of w_hi / w_lo and the [N, 32] tiles of Q_hi /
-//            Q_lo (FP32 in memory, already TF32-valued) land in shared memory in the 128-byte-swizzled K-major
-//            layout that the UMMA shared-memory descriptors describe (2-stage ring, mbarrier full/empty)
-//   warp 1   MMA issuer: one elected thread issues 3 x 4 tcgen05.mma (M = 128, N <= 256, K = 8) per k-block into
-//            one of two TMEM accumulators (2 x N columns) and commits to the ring's `empty` barrier / the
-//            accumulator's `full` barrier
+// tf32x3_gemm_kernel<MODE> (one CTA per SM, M = 128) and tf32x3_gemm_pair_kernel<MODE> (cluster of two CTAs,
+// tcgen05.mma.cta_group::2, M = 256): warp-specialised, persistent.
+//   warp 0   TMA producer: per 32-wide k-block the [128, 32] tiles of A_hi / A_lo and the [N, 32] tiles of B_hi / B_lo
+//            (FP32 in memory, already TF32-valued) land in shared memory in the 128-byte-swizzled K-major layout that
+//            the UMMA shared-memory descriptors describe (ring of stages, mbarrier full/empty)
+//   warp 1   MMA issuer: one elected thread issues 3 x 4 tcgen05.mma (N <= 256, K = 8) per k-block into one of two
+//            TMEM accumulators (2 x N columns) and commits to the ring's `empty` barrier / the accumulator's `full`
+//            barrier
 //   warp 2   allocates / frees the tensor memory
-//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> FP32 row-major P (each thread owns one
-//            output row, 128 contiguous bytes per chunk; two warps per TMEM lane quarter take alternate chunks), then
-//            release the accumulator
-// Kernel 2, proxq_apply_kernel: the FP64 part of the iteration as one coalesced streaming pass
-//   z = c + P;  x_new = shrink(z, thr);  w_next = x_new + momentum (x_new - x_prev) -> written directly as the
-//   TF32 pair (w_hi, w_lo) the next GEMM reads; convergence test + last-CTA latch as in the FP64 kernels.
-// Per iteration: GEMM reads 2 x 4 B and writes 4 B per element, the pass reads 4 + 8 + 8 B and writes 8 + 4 + 4 B:
-// 48 B per element against 40 B for the fused FP64 launch, but nothing is bound by the FP64 tensor pipe any more.
+//   warps 4-11 epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> memory by MODE (STORE / PARTIAL / XUPD /
+//            FMASK, see below; two warps per TMEM lane quarter take alternate chunks), then release the accumulator
+// proxq_apply_kernel: the FP64 part of a Lasso iteration as one coalesced streaming pass
+//   unmasked: z = c + P;  masked: z = w + step (c - P);  x_new = shrink(z, thr);  w_next = x_new + momentum (x_new -
+//   x_prev) -> written directly as the TF32 pair (w_hi, w_lo) the next GEMM reads; convergence test + last-CTA latch as
+//   in the FP64 kernels.
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 #include <string.h>
