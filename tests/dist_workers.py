@@ -186,6 +186,20 @@ def gpu_sharded_solves(rank, world, port, out):
                                      mask=None if m is None else shard(m, rank, world), group=dist.group.WORLD)
         it0, x_ref = orc.lasso(yl, A, 0.05, tol=1e-6, method='fista', maxiter=1000, mask=m)
         res[name] = (it, it0, rel(x, shard(x_ref, rank, world)))
+    # the TF32-split paths sharded the same way (statistics all-reduced in FP64): against the FP64 oracle at the
+    # TF32 tolerance; k a multiple of 32
+    y2, D2, mask2 = gc._nmf_data(2001, 260, 32, 7)
+    for name, m in (('nmf_tf32', None), ('nmf_mask_tf32', mask2)):
+        it, D, x = nmf.solve(shard(y2, rank, world), D2.copy(), tol=0.0, maxiter=16,
+                             mask=None if m is None else shard(m, rank, world), group=dist.group.WORLD,
+                             precision='tf32x3')
+        it0, D_ref, x_ref = orc.nmf_mu(y2, D2.copy(), tol=0.0, maxiter=16, mask=m)
+        res[name] = (it, it0, rel(D, D_ref), rel(x, shard(x_ref, rank, world)))
+    A2, yl2, maskl2, _ = gc._lasso_data((901,), 32, 40, 3)
+    it, x = lasso.solve_fastpath(shard(yl2, rank, world), A2, 0.05, None, 1e-6, 1000, 'fista', None,
+                                 mask=shard(maskl2, rank, world), group=dist.group.WORLD, precision='tf32x3')
+    it0, x_ref = orc.lasso(yl2, A2, 0.05, tol=1e-6, method='fista', maxiter=1000, mask=maskl2)
+    res['lasso_mask_tf32'] = (it, it0, rel(x, shard(x_ref, rank, world)))
     from decomp_b200 import comm
     comm.destroy_all()
     out[rank] = res

@@ -51,6 +51,12 @@ def test_world_size_2_nccl_sharded_solves():
         for name in ('lasso', 'lasso_mask'):
             it, it0, ex = res[name]
             assert it == it0 and ex < 1e-10, (rank, name, res[name])
+        # TF32-split paths: tolerance of tests/test_tf32x3_gpu.py
+        for name in ('nmf_tf32', 'nmf_mask_tf32'):
+            it, it0, eD, ex = res[name]
+            assert it == it0 and eD < 1e-4 and ex < 1e-4, (rank, name, res[name])
+        it, it0, ex = res['lasso_mask_tf32']
+        assert abs(it - it0) <= 10 and ex < 1e-3, (rank, res['lasso_mask_tf32'])
 
 
 @pytest.mark.gpu
