@@ -3,8 +3,8 @@
 // A batch row only ever needs its own row of w, so a CTA keeps a block of BM rows for all iterations of the launch:
 //   * w (the A operand of the next GEMM) lives in shared memory in the swizzled k-block layout the DMMA fragment
 //     loads expect, and the update writes w_next straight back into it
-//   * c = (y A^H)/L sits in a thread-private shared-memory array, x_prev in registers (every thread owns the same
-//     accumulator fragment in every iteration)
+//   * c = (y A^H)/L sits in tensor memory (thread-private columns, see RES_TMEM_COLS), x_prev in registers (every
+//     thread owns the same accumulator fragment in every iteration)
 //   * only Q = (I - G/L)^T streams, from L2, through a TMA ring
 // so HBM sees one read of (w, c, x) and one write of (x, w) per launch instead of per iteration, and there is one
 // launch per `iters` iterations.  BM * N = 8192 elements; 16 MMA warps, each owning a 16 x 32 piece of the block
@@ -15,7 +15,9 @@
 // its DMMAs: 84 % of the DMMA issue rate).  The k-loop is straight-line code per number of live 8-row groups.
 // The 16 warps form two groups of 8 that own the two halves of the row block and share nothing but the Q ring
 // (rows are independent): each group has its own w tile, TMA barrier and named barrier, and group 1 starts every
-// iteration two k-blocks behind group 0 (the lead the 3-stage ring allows).  When group 0 reaches its update --
+// iteration three k-blocks behind group 0 (of the five stages of the ring; a stage is refilled when both groups
+// have released it, so the lead comes out of the prefetch distance -- with the three stages the ring had while c
+// lived in shared memory a lead bought nothing).  When group 0 reaches its update --
 // scalar FP64 work plus two barriers during which its warps issue no DMMA -- group 1 still has two k-blocks to go and
 // has the tensor pipe to itself, and vice versa at the start of the next iteration: the update of one half runs
 // under the DMMAs of the other instead of idling the pipe (it was 7 % of the iteration with all warps in lockstep).
@@ -36,12 +38,43 @@ constexpr int RES_THREADS = RES_MMA_THREADS + 128;   // + the producer warp grou
 constexpr int RES_MAX_ITERS = 32;
 constexpr int RES_MAX_STAGES = 8;
 
+// c (16 doubles per thread, 64 KB per CTA) lives in TENSOR MEMORY: the DMMA path does not use it otherwise, a
+// tcgen05.ld/st.32x32b gives every thread 32 private 32-bit columns of its lane, and the 64 KB of shared memory this
+// frees make the Q ring five stages deep instead of three -- which is what the lead of warp group 0 over group 1
+// needs (a stage is refilled only when both groups have released it: lead + prefetch distance must fit the ring).
+constexpr int RES_TMEM_COLS = 128;   // 4 warps per TMEM lane quarter x 32 columns
+
 struct ResidentSmem {
-  static constexpr int W_BYTES = 65536, C_BYTES = 65536, RING_BYTES = 98304;
-  static constexpr int RING_OFF = W_BYTES + C_BYTES;
+  static constexpr int W_BYTES = 65536, RING_BYTES = 163840;
+  static constexpr int RING_OFF = W_BYTES;
   static constexpr int BAR_OFF = RING_OFF + RING_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + (2 * RES_MAX_STAGES + 3) * 8;   // + wbar[2] + the skew counter
+  // full[8] + empty[8] + wbar[2] + the skew counter + the tensor-memory base address
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * RES_MAX_STAGES + 4) * 8;
 };
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32_res(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 struct ResidentArgs {
   long long M;
@@ -128,13 +161,13 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   using S = ResidentSmem;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* Wt = smem;
-  double2* Ct = reinterpret_cast<double2*>(smem + S::W_BYTES);
   unsigned char* ring = smem + S::RING_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + RES_MAX_STAGES;
   uint64_t* wbar = empty_bar + RES_MAX_STAGES;
 
   volatile int* skew = reinterpret_cast<volatile int*>(wbar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 3);
 
   // two groups of 8 warps, each owning BMG rows of the block of BM = 2 BMG rows
   const int N = a.N, KB = N >> 4, WN = N >> 5, WMG = 8 / WN, BMG = 16 * WMG, BM = 2 * BMG;
@@ -165,7 +198,16 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     tma_prefetch_desc(&tmW);
     tma_prefetch_desc(&tmQ);
   }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(RES_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
 
   bool violated = false;
   // Registers are allocated to warps in groups of four: 640 threads leave 96 each.  The producer group hands most of
@@ -215,7 +257,7 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     // ================================================================ MMA warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int group = warp >> 3, lw = warp & 7;
-    const int wn = lw % WN, wm = lw / WN, g = lane >> 2, q = lane & 3, tid = threadIdx.x;
+    const int wn = lw % WN, wm = lw / WN, g = lane >> 2, q = lane & 3;
     unsigned char* Wg = Wt + group * (S::W_BYTES / 2);
     int iter_no = 0;   // iterations this CTA has started, over all its row blocks
     int offA[4], offB[4];
@@ -226,6 +268,8 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       offB[s4] = (wn * 32 + g) * 128 + o;
     }
     const int col_lane = wn * 32 + 2 * q;   // + 8 j
+    // this thread's 32 columns of tensor memory: lane quarter warp % 4 (the only one the warp may touch), lane = lane
+    const uint32_t c_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
     // w_next goes back into the swizzled tile as 16-byte stores; a quarter warp (rows g = 2a, 2a + 1) would hit every
     // bank twice if all its lanes stored the same column pair j, so odd rows store pair j ^ 1 first (chunks
     // (q + 4 (j & 1)) ^ g: the two rows then cover all eight 16-byte chunks of the 128-byte line)
@@ -251,16 +295,23 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       // into the matrix, computed on and never stored
       const long long row_lane = m0 + wm * 16 + g;
       double2 prev[2][4];
+      {
+        uint32_t cbits[32];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        long long r = row_lane + 8 * i;
-        if (r > a.M - 1) r = a.M - 1;
+        for (int i = 0; i < 2; ++i) {
+          long long r = row_lane + 8 * i;
+          if (r > a.M - 1) r = a.M - 1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          prev[i][j] = *reinterpret_cast<const double2*>(a.x + r * a.ldx + col_lane + 8 * j);
-          Ct[(i * 4 + j) * RES_MMA_THREADS + tid] =
-              *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
+          for (int j = 0; j < 4; ++j) {
+            prev[i][j] = *reinterpret_cast<const double2*>(a.x + r * a.ldx + col_lane + 8 * j);
+            const double2 cc = *reinterpret_cast<const double2*>(a.c + r * a.ldc + col_lane + 8 * j);
+            cbits[(i * 4 + j) * 4 + 0] = (uint32_t)__double2loint(cc.x);
+            cbits[(i * 4 + j) * 4 + 1] = (uint32_t)__double2hiint(cc.x);
+            cbits[(i * 4 + j) * 4 + 2] = (uint32_t)__double2loint(cc.y);
+            cbits[(i * 4 + j) * 4 + 3] = (uint32_t)__double2hiint(cc.y);
+          }
         }
+        tmem_st32(c_taddr, cbits);
       }
       mbar_wait(&wbar[group], wph);
       wph ^= 1u;
@@ -269,14 +320,17 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       for (int it = 0; it < a.iters; ++it) {
         // the accumulators start from c, so the mainloop ends with z = c + w Q
         double acc[2][4][2];
+        {
+          uint32_t cbits[32];
+          tmem_ld32_res(c_taddr, cbits);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double2 cc = Ct[(i * 4 + j) * RES_MMA_THREADS + tid];
-            acc[i][j][0] = cc.x;
-            acc[i][j][1] = cc.y;
-          }
+            for (int j = 0; j < 4; ++j) {
+              acc[i][j][0] = __hiloint2double((int)cbits[(i * 4 + j) * 4 + 1], (int)cbits[(i * 4 + j) * 4 + 0]);
+              acc[i][j][1] = __hiloint2double((int)cbits[(i * 4 + j) * 4 + 3], (int)cbits[(i * 4 + j) * 4 + 2]);
+            }
+        }
         ++iter_no;
         volatile int* signal = nullptr;
         if (group == 0) {
@@ -405,6 +459,11 @@ lasso_resident_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     }
   }
   if (a.check) latch_vote(a.scratch, a.latch, a.latch_value, violated);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();       // nobody uses the tensor memory any more
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(RES_TMEM_COLS) : "memory");
+  }
 }
 
 }  // namespace dcp
