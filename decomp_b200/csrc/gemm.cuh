@@ -47,6 +47,9 @@ struct GemmGeom {
   long long ld_partial;  // TN: leading dimension of one partial slab (even)
   int zero;              // always 0, opaque to the compiler
   int tn3d;              // TN: operands are described by 3-D tensor maps (one TMA instruction per operand)
+  int m_fast;            // tile order: the m tiles of one (n tile, K split) run side by side.  TN x^T y: the big operand
+                         // is B (y), read once per m tile -- with k = 256 = two m tiles 60 % of y came from DRAM twice
+                         // when the two CTAs that share a y tile sat 64 CTAs apart (ncu: 51.6 GB for a 32.8 GB y)
 };
 
 template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int NBUF_, int EPI_WARPS_, int EPI_BATCH_>
@@ -282,8 +285,8 @@ struct TileInfo {
 
 __device__ __forceinline__ TileInfo tile_info(const GemmGeom& gs, int tiles_mn, int tile, int BM, int BN) {
   TileInfo t;
-  const int tn = tile % gs.tiles_n;
-  const int tm = (tile / gs.tiles_n) % gs.tiles_m;
+  const int tn = gs.m_fast ? (tile / gs.tiles_m) % gs.tiles_n : tile % gs.tiles_n;
+  const int tm = gs.m_fast ? tile % gs.tiles_m : (tile / gs.tiles_n) % gs.tiles_m;
   t.z = tile / tiles_mn;
   t.m0 = tm * BM;
   t.n0 = tn * BN;

@@ -229,6 +229,7 @@ static void tn_plan(long long M, long long N, long long K, GemmGeom* gs) {
   gs->splits = (gs->kblocks_total + gs->kblocks_per_split - 1) / gs->kblocks_per_split;
   if (gs->splits < 1) gs->splits = 1;
   gs->ld_partial = (N + 1) & ~1LL;
+  gs->m_fast = 1;
 }
 
 }  // namespace dcp
@@ -269,6 +270,7 @@ int decomp_gemm_nt_f64(const double* A, int64_t lda, const double* B, int64_t ld
   gs.ld_partial = 0;
   gs.tn3d = 0;
   gs.zero = 0;
+  gs.m_fast = 0;
   cudaStream_t st = as_stream(stream);
   switch (epi->kind) {
     case DECOMP_EPI_STORE:
