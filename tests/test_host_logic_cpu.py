@@ -139,3 +139,35 @@ def test_numpy_views_torch_cannot_alias_are_copied():
     ro = a.copy()
     ro.flags.writeable = False
     assert np.array_equal(_device._from_numpy(ro).numpy(), a)
+
+
+def test_sweep_traffic_sums_the_last_sweep(tmp_path):
+    """tools/sweep_traffic.py: DRAM bytes of the kernels between the last two normalize_rows launches of an ncu log."""
+    import json
+    import os
+    import subprocess
+    import sys
+    rows = ['"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size",'
+            '"Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"']
+
+    def launch(i, name, ns, rd, wr):
+        for metric, unit, v in (('dram__bytes_read.sum', 'Mbyte', rd), ('dram__bytes_write.sum', 'byte', wr),
+                                ('gpu__time_duration.sum', 'us', ns)):
+            rows.append('"%d","1","python","h","%s","1","7","(256, 1, 1)","(148, 1, 1)","0","10.0","Command line '
+                        'profiler metrics","%s","%s","%s"' % (i, name, metric, unit, v))
+
+    launch(0, 'dcp::normalize_rows_kernel(a)', '4', '0.1', '1,000')
+    launch(1, 'void dcp::gemm_f64_kernel<X>(b)', '1,500', '10', '2,000,000')
+    launch(2, 'dcp::normalize_rows_kernel(a)', '4', '0', '0')
+    launch(3, 'void dcp::gemm_f64_kernel<X>(b)', '2,000', '20.5', '3,000,000')
+    launch(4, 'dcp::mu_update_kernel(c)', '10', '1', '500,000')
+    launch(5, 'dcp::normalize_rows_kernel(a)', '4', '0', '0')
+    log = tmp_path / 'ncu.csv'
+    log.write_text('==PROF== Connected\n' + '\n'.join(rows) + '\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'sweep_traffic.py'), str(log)],
+                         capture_output=True, text=True, check=True).stdout
+    res = json.loads(out)
+    assert res['dram_bytes_read'] == pytest.approx(21.5e6) and res['dram_bytes_written'] == pytest.approx(3.5e6)
+    assert res['kernel_time_ms'] == pytest.approx(2.014)
+    assert [k['name'][:20] for k in res['kernels']] == ['void dcp::gemm_f64_k']      # launches above 0.1 ms only
