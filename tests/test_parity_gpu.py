@@ -298,3 +298,55 @@ def test_dictionary_learning_masked_complex_multi_chunk_statistics():
     assert it == it0
     assert_close(D, D_ref, what='D')
     assert_close(x, x_ref, what='x')
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_likelihood_seam(masked):
+    """The reference's operator seam (grads.py:17-93): a Likelihood with GPU gradients, driven by the reference's own
+    update rules -- a stand-in for the ABC here, and the unmodified reference driver when baseline/_ref is installed."""
+    from decomp_b200.likelihood import gaussian
+    from oracle import cpu_arm
+    from oracle import decomp_oracle as orc
+    y, D0, mask = gc._nmf_data(301, 75, 6, 3)
+    m = mask if masked else None
+
+    class Base(object):                      # the two update rules of the reference ABC, restated (grads.py:77-93)
+        def __init__(self):
+            pass
+
+        def update_x(self, y, x, d, mask):
+            p, n = self.grad_x(y, x, d, mask)
+            return x * np.maximum(p, 0.0) / np.maximum(n, 1.0e-15)
+
+        def update_d(self, y, x, d, mask):
+            p, n = self.grad_d(y, x, d, mask)
+            return d * np.maximum(p, 0.0) / np.maximum(n, 1.0e-15)
+
+    lk = gaussian(Base)()
+    x = np.ones((y.shape[0], D0.shape[0]))
+    D = D0 / np.sqrt(np.sum(D0 * D0, axis=-1, keepdims=True))
+    w = np.ones_like(y) if m is None else m
+    f = x.dot(D) * w
+    for (got_p, got_n), (ref_p, ref_n) in ((lk.grad_x(y, x, D, m), ((y * w).dot(D.T), f.dot(D.T))),
+                                           (lk.grad_d(y, x, D, m), (x.T.dot(y * w), x.T.dot(f)))):
+        assert np.max(np.abs(got_p - ref_p)) <= 1e-12 * np.max(np.abs(ref_p))
+        assert np.max(np.abs(got_n - ref_n)) <= 1e-12 * np.max(np.abs(ref_n))
+    # batch_mu's recursion (batch_mu.py:16-24) through the seam against the oracle
+    for _ in range(5):
+        x = lk.update_x(y, x, D, m)
+        Dn = lk.update_d(y, x, D, m)
+        D = Dn / np.sqrt(np.sum(Dn * Dn, axis=-1, keepdims=True))
+    it0, D_ref, x_ref = orc.nmf_mu(y, D0.copy(), tol=0.0, maxiter=6, mask=m)
+    assert np.max(np.abs(D - D_ref)) <= 1e-10 * np.max(np.abs(D_ref))
+    assert np.max(np.abs(x - x_ref)) <= 1e-10 * np.max(np.abs(x_ref))
+    # inside the unmodified reference's own driver
+    arm = cpu_arm.load()
+    if arm.kind == 'reference':
+        import decomp
+        from decomp.nmf_methods import grads
+        it_a, D_a, x_a = decomp.nmf.solve(y, D0.copy(), tol=1e-5, maxiter=300, mask=m)
+        it_b, D_b, x_b = decomp.nmf.solve(y, D0.copy(), tol=1e-5, maxiter=300, mask=m,
+                                          likelihood=gaussian(grads.Likelihood)())
+        assert it_a == it_b
+        assert np.max(np.abs(D_a - D_b)) <= 1e-10 * np.max(np.abs(D_a))
+        assert np.max(np.abs(x_a - x_b)) <= 1e-10 * np.max(np.abs(x_a))
